@@ -1,0 +1,163 @@
+/*
+ * qgsb.h -- C ABI of libqgsb.so, the B200 (sm_100a) ensemble integrator for the qgs hot path.
+ *
+ * Every entry point replaces one numba-jitted function (or worker pool) of the reference; the
+ * reference file:line it stands in for is cited next to each declaration (paths relative to the
+ * reference repository root).  The reference-side binding a maintainer would add is the ctypes stub
+ * shown in INTEGRATION.md; qgs_b200/_lib.py is that stub.
+ *
+ * Conventions
+ *   - plain C types only; all array arguments are HOST pointers owned by the caller for the duration
+ *     of the call unless the name starts with d_ (device pointer) -- the library owns every device
+ *     allocation it makes (tensor handles, ensembles, scratch).
+ *   - arithmetic is IEEE float64; indices are int32 (the Python side converts the reference's
+ *     F-ordered int64 `coords.T` view, tendencies.py:92, to C-ordered int32).
+ *   - return value 0 = success; non-zero = failure, message in qgsb_last_error() (thread local).
+ *   - calls are synchronous (they return when results are in the caller's buffers), like the
+ *     reference's integrate() which blocks on queue.join() (integrator.py:391).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with an error.
+ */
+#ifndef QGSB_H
+#define QGSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define QGSB_API __attribute__((visibility("default")))
+#else
+#define QGSB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qgsb_tensor qgsb_tensor;     /* device-resident tendencies + Jacobian tensor */
+typedef struct qgsb_ensemble qgsb_ensemble; /* device-resident ensemble state (structure of arrays) */
+
+/* ---- runtime ---------------------------------------------------------------------------------- */
+
+/* Bind the calling process to one CUDA device (device < 0: LOCAL_RANK from the environment, else 0)
+ * and create the library stream.  Replaces RungeKuttaIntegrator.start() spawning the worker pool
+ * (qgs/integrators/integrator.py:121-142).  Idempotent. */
+QGSB_API int qgsb_init(int device);
+/* Release scratch memory and the stream; replaces terminate() (integrator.py:113-119).  Idempotent. */
+QGSB_API void qgsb_shutdown(void);
+/* Launch on a caller-provided cudaStream_t (e.g. torch's current stream); NULL restores the own stream. */
+QGSB_API int qgsb_set_stream(void *cuda_stream);
+QGSB_API const char *qgsb_last_error(void);
+QGSB_API const char *qgsb_version(void);
+QGSB_API int qgsb_device_info(int *device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
+/* Number of kernels this library has launched since load (bench.py's "gpu_launches"). */
+QGSB_API long qgsb_launch_count(void);
+/* Load a shared object holding tensor-specialised kernels built by qgs_b200/codegen.py; handles
+ * created earlier pick it up through qgsb_tensor_use_specialised(t, 1). */
+QGSB_API int qgsb_load_plugin(const char *path);
+
+/* ---- tensor hand-off (qgs/functions/tendencies.py:92-96) ---------------------------------------
+ * coo (nnz, rank) row-major, val (nnz); jcoo/jval the Jacobian tensor (may be NULL/0).  rank is 3
+ * (sparse_mul3/sparse_mul2) or 5 (sparse_mul5/sparse_mul4).  Index 0 is the constant x_0 = 1. */
+QGSB_API int qgsb_tensor_create(int ndim, int rank, long nnz, const int32_t *coo, const double *val,
+                       long jnnz, const int32_t *jcoo, const double *jval, qgsb_tensor **out);
+QGSB_API void qgsb_tensor_destroy(qgsb_tensor *t);
+/* kernel_kind: 0 generic thread-per-member, 1 generic warp-per-member, 2 tensor-specialised.
+ * tensor_hash: FNV-1a over (ndim, rank, nnz, row-sorted coo, values), the key of a specialised module. */
+QGSB_API int qgsb_tensor_info(const qgsb_tensor *t, int *ndim, int *rank, long *nnz, long *jnnz, int *kernel_kind,
+                     uint64_t *tensor_hash);
+/* Forbid / allow the tensor-specialised kernels for this handle (testing and benchmarking). */
+QGSB_API int qgsb_tensor_use_specialised(qgsb_tensor *t, int enable);
+
+/* ---- raw contractions, qgs/functions/sparse_mul.py ---------------------------------------------- */
+/* sparse_mul3 (sparse_mul.py:48-81): res_i = sum T_ijk a_j b_k, res_0 = 1.        vectors length n1 */
+QGSB_API int qgsb_sparse_mul3(long nnz, const int32_t *coo, const double *val, int n1,
+                     const double *vec_a, const double *vec_b, double *res);
+/* sparse_mul5 (sparse_mul.py:121-158) */
+QGSB_API int qgsb_sparse_mul5(long nnz, const int32_t *coo, const double *val, int n1, const double *vec_a,
+                     const double *vec_b, const double *vec_c, const double *vec_d, double *res);
+/* sparse_mul2 (sparse_mul.py:13-45): res_ij = sum_k T_ijk a_k, res is (n1, n1) */
+QGSB_API int qgsb_sparse_mul2(long nnz, const int32_t *coo, const double *val, int n1, const double *vec, double *res);
+/* sparse_mul4 (sparse_mul.py:84-118) */
+QGSB_API int qgsb_sparse_mul4(long nnz, const int32_t *coo, const double *val, int n1, const double *vec_a,
+                     const double *vec_b, const double *vec_c, double *res);
+
+/* ---- f / Df closures, qgs/functions/tendencies.py:98-121, batched over members ------------------ */
+QGSB_API int qgsb_tendencies(const qgsb_tensor *t, long n_traj, const double *x /* (N, n) */, double *out /* (N, n) */);
+QGSB_API int qgsb_jacobian(const qgsb_tensor *t, long n_traj, const double *x /* (N, n) */, double *out /* (N, n, n) */);
+
+/* ---- _integrate_runge_kutta_jit, qgs/integrators/integrate.py:182-223 ---------------------------
+ * dt (n_steps): the signed step lengths in execution order, i.e. np.diff(directed_time).  The model
+ * is autonomous (tendencies.py:99 ignores t) so the times themselves are not needed.
+ * a (s, s) row-major, b (s), c (s) the Butcher tableau (explicit part j < i is used; c is accepted
+ * for signature parity).  write_steps / n_records follow integrate.py:190-196, 210-212, 221;
+ * time_direction -1 reverses the record axis like integrate.py:223.
+ * traj (n_traj, n_dim, n_records) C-ordered.  device_ms (may be NULL): kernel time by CUDA events. */
+QGSB_API int qgsb_rk_integrate(const qgsb_tensor *t, long n_traj, const double *ic /* (N, n) */, long n_steps,
+                      const double *dt, int s, const double *a, const double *b, const double *c,
+                      long write_steps, int time_direction, long n_records, double *traj,
+                      double *device_ms);
+
+/* ---- _integrate_runge_kutta_tgls_jit, integrate.py:555-614 (+ :226-231) ---------------------------
+ * tg_ic (N, n, m); adjoint != 0 integrates with J^T; inverse_sign is the reference's `inverse`
+ * (+1. or -1., integrate.py:519-521); the inhomogeneous term is the reference default _zeros_func.
+ * fmat (N, n, m, n_records). */
+QGSB_API int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long n_traj, const double *ic, int m, const double *tg_ic,
+                           long n_steps, const double *dt, int s, const double *a, const double *b,
+                           const double *c, long write_steps, int time_direction, int adjoint,
+                           double inverse_sign, long n_records, double *traj, double *fmat,
+                           double *device_ms);
+
+/* ---- Benettin steps, qgs/toolbox/lyapunov.py:471-632 ----------------------------------------------
+ * One call runs n_pre + n_rec macro steps for every member.  Macro step i advances the nonlinear
+ * state with dt_macro[i] (the stored write_steps=1 trajectory of lyapunov.py:558 / :474) and the
+ * n x n_vec tangent matrix with the micro steps sub_dt[sub_ptr[i] .. sub_ptr[i+1]) starting from the
+ * same point (lyapunov.py:598-601), then re-orthonormalises by Householder QR (np.linalg.qr, :602).
+ * forward == 0 (BLV, :564-632): members start at ic; records taken during the last n_rec steps.
+ * forward == 1 (FLV, :480-552): the trajectory is first integrated forward over dt_macro reversed and
+ *   stored in HBM, then walked backwards; dt_macro / sub_dt are given in execution (backward) order, negative.
+ * forward == 2: like 0 but the nonlinear state follows the micro steps (Ginelli forward pass, :1212-1218).
+ * q0 (N, n, n_vec), r0 (N, n_vec, n_vec) or NULL: the start basis (the reference draws
+ * qr(random((n_dim, n_vec))), lyapunov.py:592-593, on the host side).
+ * rec_* follow _compute_*_lyap_traj_jit's return values: traj (N, n, R), exp (N, n_vec, R),
+ * vec (N, n, n_vec, R).  r_all (N, n_steps_total, n_vec, n_vec) or NULL stores every R factor and
+ * q_all (N, n_rec + 1, n, n_vec) or NULL the basis at every recorded-phase point (Ginelli, :1220-1250). */
+QGSB_API int qgsb_lyap_benettin(const qgsb_tensor *t, long n_traj, const double *ic, int forward, int n_vec,
+                       const double *q0, const double *r0, long n_pre, long n_rec,
+                       const double *dt_macro, const long *sub_ptr, const double *sub_dt,
+                       int s, const double *a, const double *b, const double *c, long write_steps,
+                       int adjoint, double inverse_sign, long n_records,
+                       double *rec_traj, double *rec_exp, double *rec_vec,
+                       double *r_all, double *q_all, double *device_ms);
+
+/* ---- device-resident ensemble (state stays in HBM between calls) ---------
+ * State layout in HBM: tiled structure of arrays -- members in tiles of 128, variable i of member m at
+ * (m / 128) * (n * 128) + i * 128 + m % 128; ld = n_traj rounded up to 128. */
+QGSB_API int qgsb_ensemble_create(const qgsb_tensor *t, long n_traj, qgsb_ensemble **out);
+QGSB_API void qgsb_ensemble_destroy(qgsb_ensemble *e);
+QGSB_API int qgsb_ensemble_upload(qgsb_ensemble *e, const double *ic /* host (N, n) */);
+QGSB_API int qgsb_ensemble_download(qgsb_ensemble *e, double *out /* host (N, n) */);
+/* Advance all members n_steps (write_steps = 0 semantics: only the end state is kept).  One fused
+ * launch; returns without host synchronisation when device_ms is NULL. */
+QGSB_API int qgsb_ensemble_integrate(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                            const double *b, const double *c, double *device_ms);
+/* Same, recording like qgsb_rk_integrate into a device buffer d_rec of n_records tiled-SoA states
+ * (record r starts at r * n * ld). */
+QGSB_API int qgsb_ensemble_integrate_record(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                                   const double *b, const double *c, long write_steps, long n_records,
+                                   double *d_rec, double *device_ms);
+/* Sum and sum of squares over members for every variable (ensemble statistics; NCCL all-reduce of
+ * these 2n doubles is done by the caller across ranks). */
+QGSB_API int qgsb_ensemble_moments(qgsb_ensemble *e, double *sum /* (n) */, double *sumsq /* (n) */);
+QGSB_API void *qgsb_ensemble_device_ptr(qgsb_ensemble *e);
+QGSB_API long qgsb_ensemble_ld(const qgsb_ensemble *e);
+QGSB_API int qgsb_synchronize(void);
+
+/* ---- measurement helpers ------------------------------------------------------------------------ */
+/* Dependent-chain-free DFMA micro-benchmark: measured FP64 FMA peak of this device in TFLOP/s
+ * (the roofline denominator MEASURED_PEAKS.json lacks). */
+QGSB_API int qgsb_fp64_peak(double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QGSB_H */

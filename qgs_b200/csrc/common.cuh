@@ -1,0 +1,170 @@
+// common.cuh -- shared declarations of libqgsb (context, error convention, device tensor layout).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/qgsb.h"
+
+namespace qgsb {
+
+// ------------------------------------------------------------------------------------------------
+// error convention: every extern "C" entry point returns 0 / non-zero and stores a message
+// ------------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+struct Failure {};  // thrown internally, caught at the ABI boundary
+
+#define QGSB_CUDA(call)                                                                          \
+    do {                                                                                         \
+        cudaError_t err__ = (call);                                                              \
+        if (err__ != cudaSuccess) {                                                              \
+            qgsb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__,  \
+                            __LINE__);                                                           \
+            throw qgsb::Failure();                                                               \
+        }                                                                                        \
+    } while (0)
+
+#define QGSB_REQUIRE(cond, ...)               \
+    do {                                      \
+        if (!(cond)) {                        \
+            qgsb::set_error(__VA_ARGS__);     \
+            throw qgsb::Failure();            \
+        }                                     \
+    } while (0)
+
+#define QGSB_API_BEGIN try {
+#define QGSB_API_END                                       \
+    return 0;                                              \
+    }                                                      \
+    catch (const qgsb::Failure &) { return 1; }            \
+    catch (const std::exception &e) {                      \
+        qgsb::set_error("exception: %s", e.what());        \
+        return 2;                                          \
+    }
+
+// ------------------------------------------------------------------------------------------------
+// process-wide context: one device, one stream (one process per GPU)
+// ------------------------------------------------------------------------------------------------
+struct Context {
+    bool ready = false;
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    size_t smem_optin = 0;  // max dynamic shared memory per block
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long launches = 0;
+};
+Context &ctx();
+void ensure_init();
+inline void count_launch(long n = 1) { ctx().launches += n; }
+
+// ------------------------------------------------------------------------------------------------
+// ensemble layout in HBM ("tiled structure of arrays"): members are grouped in tiles of TILE = 128;
+// inside a tile variable i of member m sits at i * TILE + (m % TILE), tiles follow each other with
+// stride rows * TILE.  A thread block that owns a tile reads and writes one contiguous
+// rows * 1 KiB chunk with fully coalesced 8-byte accesses, and every per-variable offset inside the
+// tile is a compile-time constant for the tensor-specialised kernels.  ld = n_members rounded up to
+// TILE; padding members are zero-filled.
+// ------------------------------------------------------------------------------------------------
+constexpr int TILE = 128;
+__host__ __device__ inline size_t tile_base(long member, long rows)
+{
+    return (size_t)(member / TILE) * (size_t)rows * TILE + (size_t)(member % TILE);
+}
+
+// RAII device buffer
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) QGSB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void upload(const T *h, size_t count, cudaStream_t s) {
+        QGSB_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T *h, size_t count, cudaStream_t s) const {
+        QGSB_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// device tensor layout
+//
+// One 16-byte entry per non-zero, rows (first index) sorted ascending with CSR row pointers so that
+// every thread walks the same entry stream: {value, j | k << 16, l | m << 16}.  Rank-3 entries use
+// l = m = 0, i.e. they multiply by x_0 = 1 like the reference's rank-5 tensors do for low orders.
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) Entry {
+    double v;
+    uint32_t jk;
+    uint32_t lm;
+};
+
+// Jacobian in "position" form: the distinct (i, j >= 1) matrix positions, CSR by row i (for J @ X)
+// and CSC by column j (for J^T @ X); every position owns a contiguous run of entries
+// {value, k | l << 16, m} whose products are summed to give J_ij.
+struct JacView {
+    int npos = 0;               // number of structurally non-zero J_ij, i,j in 1..n
+    const int *pos_ptr = nullptr;    // (npos + 1) run boundaries into ent
+    const Entry *ent = nullptr;      // jk = k | l << 16, lm = m
+    const int *pos_i = nullptr;      // (npos) row index   (1-based variable index)
+    const int *pos_j = nullptr;      // (npos) column index
+    const int *row_ptr = nullptr;    // (n + 2) CSR over positions, by i
+    const int *col_ptr = nullptr;    // (n + 2) CSC over positions, by j
+    const int *col_perm = nullptr;   // (npos) position ids ordered by (j, i)
+};
+
+struct TensorView {
+    int n = 0;        // ndim
+    int rank = 3;
+    int nnz = 0;
+    const Entry *ent = nullptr;   // (nnz) sorted by row
+    const int *row_ptr = nullptr; // (n + 2): entries of row i are [row_ptr[i], row_ptr[i+1])
+    JacView jac;
+};
+
+struct SpecKernels;  // tensor-specialised kernels (spec_registry.h)
+
+}  // namespace qgsb
+
+struct qgsb_tensor {
+    qgsb::TensorView view;
+    int max_deg = 2;           // largest number of non-trivial factors of an entry
+    int jac_max_deg = 1;
+    long nnz_in = 0, jnnz_in = 0;
+    uint64_t hash = 0;
+    std::vector<double> val_sorted;      // values in device entry order (for the specialised kernels)
+    std::vector<int32_t> coo_sorted;     // (nnz, rank) in device entry order
+    qgsb::DevBuf<qgsb::Entry> d_ent, d_jent;
+    qgsb::DevBuf<int> d_row_ptr, d_pos_ptr, d_pos_i, d_pos_j, d_jrow_ptr, d_jcol_ptr, d_jcol_perm;
+    const qgsb::SpecKernels *spec = nullptr;
+    bool use_spec = true;
+};
+
+struct qgsb_ensemble {
+    const qgsb_tensor *tensor = nullptr;
+    long N = 0, ld = 0;
+    qgsb::DevBuf<double> d_y;        // (n, ld)
+    qgsb::DevBuf<double> d_stage;    // scratch for AoS <-> SoA staging (N * n)
+};

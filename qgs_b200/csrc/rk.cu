@@ -1,0 +1,593 @@
+// rk.cu -- fused explicit Runge-Kutta ensemble kernels (generic tensors) and their C entry points.
+//
+// Replaces _integrate_runge_kutta_jit (qgs/integrators/integrate.py:182-223) and the
+// TrajectoryProcess pool that fans it over members (qgs/integrators/integrator.py:453-512).
+// One launch integrates every member over all time steps and all stages; the tensor is staged once
+// into shared memory and reused for every evaluation of f.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "spec_registry.h"
+
+namespace qgsb {
+
+// ------------------------------------------------------------------------------------------------
+Tableau make_tableau(int s, const double *a, const double *b)
+{
+    QGSB_REQUIRE(s >= 1 && s <= 16, "number of Runge-Kutta stages must be in 1..16, got %d", s);
+    QGSB_REQUIRE(a && b, "null Butcher tableau");
+    Tableau t;
+    t.s = s;
+    t.a.assign((size_t)s * s, 0.);
+    t.b.assign(b, b + s);
+    t.chain = true;
+    t.alpha.assign(s, 0.);
+    for (int i = 0; i < s; ++i)
+        for (int j = 0; j < i; ++j) {  // k[j >= i] is still zero when stage i is formed (integrate.py:214-217)
+            t.a[(size_t)i * s + j] = a[(size_t)i * s + j];
+            if (a[(size_t)i * s + j] != 0.) {
+                if (j == i - 1) t.alpha[i] = a[(size_t)i * s + j];
+                else t.chain = false;
+            }
+        }
+    return t;
+}
+
+struct RkParams {
+    long ld;          // member stride of the state / record arrays
+    long n_members;
+    long n_steps;
+    const double *dt; // (n_steps) device
+    long write_steps;
+    long n_records;
+    double *rec;      // (R, n, ld) or nullptr
+    double *y;        // (n, ld) in/out
+    int s;
+    int chain;
+    int tensor_in_smem;
+    double a[16 * 16];
+    double b[16];
+    double alpha[16];
+};
+
+// ------------------------------------------------------------------------------------------------
+// G1: one thread per member, state in shared memory as [variable][thread] (conflict-free), tensor
+// entries broadcast to the warp from shared memory (or L1 when the tensor is too large).
+// ------------------------------------------------------------------------------------------------
+template <int RANK, int BS>
+__device__ __forceinline__ double row_eval(const Entry *__restrict__ ent, int e0, int e1,
+                                           const double *__restrict__ xs)
+{
+    double acc = 0.;
+#pragma unroll 4
+    for (int e = e0; e < e1; ++e) {
+        const Entry en = ent[e];
+        double p = xs[(en.jk & 0xffffu) * BS] * xs[(en.jk >> 16) * BS];
+        if (RANK == 5) p = p * xs[(en.lm & 0xffffu) * BS] * xs[(en.lm >> 16) * BS];
+        acc += p * en.v;  // (a*b)*value, then +=   (sparse_mul.py:79)
+    }
+    return acc;
+}
+
+template <int RANK, int BS>
+__global__ void __launch_bounds__(BS) rk_g1_kernel(TensorView T, const __grid_constant__ RkParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = T.n, tid = threadIdx.x, s = P.s;
+    const long member = (long)blockIdx.x * BS + tid;
+
+    // ---- carve shared memory ----
+    Entry *s_ent = reinterpret_cast<Entry *>(smem_raw);
+    size_t off = P.tensor_in_smem ? sizeof(Entry) * (size_t)T.nnz : 0;
+    double *xs = reinterpret_cast<double *>(smem_raw + off);        // (n+1, BS)
+    double *y = xs + (size_t)(n + 1) * BS;                           // (n, BS)
+    double *buf2 = y + (size_t)n * BS;                               // chain: xn (n+1, BS); general: K (s, n, BS)
+    double *acc = buf2 + (size_t)(n + 1) * BS;                       // chain only: (n, BS)
+    int *s_row = reinterpret_cast<int *>(buf2 + (P.chain ? (size_t)(2 * n + 1) * BS : (size_t)s * n * BS));
+
+    const Entry *ent = T.ent;
+    if (P.tensor_in_smem) {
+        const int4 *src = reinterpret_cast<const int4 *>(T.ent);
+        int4 *dst = reinterpret_cast<int4 *>(s_ent);
+        for (int e = tid; e < T.nnz; e += BS) dst[e] = src[e];
+        ent = s_ent;
+    }
+    for (int i = tid; i < n + 2; i += BS) s_row[i] = T.row_ptr[i];
+    xs += tid;
+    y += tid;
+    buf2 += tid;
+    acc += tid;
+    const size_t gbase = tile_base(member, n);
+    for (int i = 0; i < n; ++i) {
+        double v = P.y[gbase + (size_t)i * TILE];
+        y[(size_t)i * BS] = v;
+        xs[(size_t)(i + 1) * BS] = v;
+    }
+    xs[0] = 1.;
+    if (P.chain) buf2[0] = 1.;
+    __syncthreads();
+
+    long iw = 0;
+    for (long ti = 0; ti < P.n_steps; ++ti) {
+        const double dt = P.dt[ti];
+        if (P.rec && P.write_steps > 0 && ti % P.write_steps == 0) {       // integrate.py:210-212
+            double *r = P.rec + (size_t)iw * n * P.ld + gbase;
+            for (int i = 0; i < n; ++i) r[(size_t)i * TILE] = y[(size_t)i * BS];
+            ++iw;
+        }
+        if (P.chain) {
+            double *xin = xs, *xout = buf2;
+            for (int st = 0; st < s; ++st) {
+                const double wb = dt * P.b[st];
+                const double wa = st + 1 < s ? dt * P.alpha[st + 1] : 0.;
+                const bool last = st + 1 == s;
+                for (int i = 1; i <= n; ++i) {
+                    const double k = row_eval<RANK, BS>(ent, s_row[i], s_row[i + 1], xin);
+                    const size_t o = (size_t)(i - 1) * BS;
+                    const double ac = st == 0 ? wb * k : acc[o] + wb * k;
+                    if (!last) {
+                        acc[o] = ac;
+                        xout[(size_t)i * BS] = y[o] + wa * k;              // y + (dt a[i]) @ k   integrate.py:216
+                    } else {
+                        const double yn = y[o] + ac;                        // y + (dt b) @ k      integrate.py:218
+                        y[o] = yn;
+                        xout[(size_t)i * BS] = yn;
+                    }
+                }
+                double *tmp = xin;
+                xin = xout;
+                xout = tmp;
+            }
+            if (s & 1) {  // keep the convention "xs holds the current state" for the next step
+                for (int i = 1; i <= n; ++i) xs[(size_t)i * BS] = y[(size_t)(i - 1) * BS];
+            }
+        } else {
+            double *K = buf2;
+            for (int st = 0; st < s; ++st) {
+                for (int i = 1; i <= n; ++i) {
+                    double v = 0.;
+                    for (int j = 0; j < st; ++j) {
+                        const double w = P.a[st * s + j];
+                        if (w != 0.) v += (dt * w) * K[((size_t)j * n + (i - 1)) * BS];
+                    }
+                    xs[(size_t)i * BS] = y[(size_t)(i - 1) * BS] + v;
+                }
+                for (int i = 1; i <= n; ++i)
+                    K[((size_t)st * n + (i - 1)) * BS] = row_eval<RANK, BS>(ent, s_row[i], s_row[i + 1], xs);
+            }
+            for (int i = 0; i < n; ++i) {
+                double v = 0.;
+                for (int j = 0; j < s; ++j) v += (dt * P.b[j]) * K[((size_t)j * n + i) * BS];
+                y[(size_t)i * BS] += v;
+            }
+        }
+    }
+    if (P.rec) {                                                            // integrate.py:221
+        double *r = P.rec + (size_t)(P.n_records - 1) * n * P.ld + gbase;
+        for (int i = 0; i < n; ++i) r[(size_t)i * TILE] = y[(size_t)i * BS];
+    }
+    for (int i = 0; i < n; ++i) P.y[gbase + (size_t)i * TILE] = y[(size_t)i * BS];
+}
+
+// ------------------------------------------------------------------------------------------------
+// G2: one warp per member for large bases (state does not fit a thread's share of shared memory).
+// Lanes stride over the entries of a row (coalesced 512 B reads of the tensor stream) and the row
+// sum is reduced by warp shuffles.
+// ------------------------------------------------------------------------------------------------
+template <int RANK>
+__device__ __forceinline__ double row_eval_warp(const Entry *__restrict__ ent, int e0, int e1,
+                                                const double *__restrict__ xs, int lane)
+{
+    double acc = 0.;
+    for (int e = e0 + lane; e < e1; e += 32) {
+        const Entry en = ent[e];
+        double p = xs[en.jk & 0xffffu] * xs[en.jk >> 16];
+        if (RANK == 5) p = p * xs[en.lm & 0xffffu] * xs[en.lm >> 16];
+        acc += p * en.v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+
+constexpr int G2_WARPS = 4;
+
+template <int RANK>
+__global__ void __launch_bounds__(G2_WARPS * 32) rk_g2_kernel(TensorView T, const __grid_constant__ RkParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = T.n, s = P.s, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long member = (long)blockIdx.x * G2_WARPS + warp;
+    const size_t per_member = P.chain ? (size_t)(4 * n + 2) : (size_t)(2 * n + 1) + (size_t)s * n;
+    double *xs = reinterpret_cast<double *>(smem_raw) + per_member * warp;  // (n+1)
+    double *y = xs + (n + 1);                                               // (n)
+    double *buf2 = y + n;                                                    // chain: xn (n+1); general: K (s, n)
+    double *acc = buf2 + (n + 1);                                            // chain only (n)
+    const bool active = member < P.ld;
+    const int *row = T.row_ptr;
+    const Entry *ent = T.ent;
+
+    const size_t gbase = tile_base(member, n);
+    if (active) {
+        for (int i = lane; i < n; i += 32) {
+            double v = P.y[gbase + (size_t)i * TILE];
+            y[i] = v;
+            xs[i + 1] = v;
+        }
+        if (lane == 0) {
+            xs[0] = 1.;
+            if (P.chain) buf2[0] = 1.;
+        }
+    }
+    __syncwarp();
+    if (!active) return;
+
+    long iw = 0;
+    for (long ti = 0; ti < P.n_steps; ++ti) {
+        const double dt = P.dt[ti];
+        if (P.rec && P.write_steps > 0 && ti % P.write_steps == 0) {
+            double *r = P.rec + (size_t)iw * n * P.ld + gbase;
+            for (int i = lane; i < n; i += 32) r[(size_t)i * TILE] = y[i];
+            ++iw;
+        }
+        if (P.chain) {
+            double *xin = xs, *xout = buf2;
+            for (int st = 0; st < s; ++st) {
+                const double wb = dt * P.b[st];
+                const double wa = st + 1 < s ? dt * P.alpha[st + 1] : 0.;
+                const bool last = st + 1 == s;
+                for (int i = 1; i <= n; ++i) {
+                    const double k = row_eval_warp<RANK>(ent, row[i], row[i + 1], xin, lane);
+                    if (lane == 0) {
+                        const double ac = st == 0 ? wb * k : acc[i - 1] + wb * k;
+                        if (!last) {
+                            acc[i - 1] = ac;
+                            xout[i] = y[i - 1] + wa * k;
+                        } else {
+                            const double yn = y[i - 1] + ac;
+                            y[i - 1] = yn;
+                            xout[i] = yn;
+                        }
+                    }
+                }
+                __syncwarp();
+                double *tmp = xin;
+                xin = xout;
+                xout = tmp;
+            }
+            if (s & 1) {
+                for (int i = lane; i < n; i += 32) xs[i + 1] = y[i];
+                __syncwarp();
+            }
+        } else {
+            double *K = buf2;
+            for (int st = 0; st < s; ++st) {
+                for (int i = lane; i < n; i += 32) {
+                    double v = 0.;
+                    for (int j = 0; j < st; ++j) {
+                        const double w = P.a[st * s + j];
+                        if (w != 0.) v += (dt * w) * K[(size_t)j * n + i];
+                    }
+                    xs[i + 1] = y[i] + v;
+                }
+                __syncwarp();
+                for (int i = 1; i <= n; ++i) {
+                    const double k = row_eval_warp<RANK>(ent, row[i], row[i + 1], xs, lane);
+                    if (lane == 0) K[(size_t)st * n + (i - 1)] = k;
+                }
+                __syncwarp();
+            }
+            for (int i = lane; i < n; i += 32) {
+                double v = 0.;
+                for (int j = 0; j < s; ++j) v += (dt * P.b[j]) * K[(size_t)j * n + i];
+                y[i] += v;
+            }
+            __syncwarp();
+        }
+    }
+    if (P.rec) {
+        double *r = P.rec + (size_t)(P.n_records - 1) * n * P.ld + gbase;
+        for (int i = lane; i < n; i += 32) r[(size_t)i * TILE] = y[i];
+    }
+    for (int i = lane; i < n; i += 32) P.y[gbase + (size_t)i * TILE] = y[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+template <typename K>
+static void set_smem(K kernel, size_t bytes)
+{
+    QGSB_REQUIRE(bytes <= ctx().smem_optin, "kernel needs %zu bytes of shared memory, device allows %zu", bytes,
+                 ctx().smem_optin);
+    if (bytes > 48 * 1024)
+        QGSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+static void fill_params(RkParams &P, const Tableau &tab, double *d_y, long ld, long N, long n_steps,
+                        const double *d_dt, long write_steps, long R, double *d_rec)
+{
+    memset(&P, 0, sizeof(P));
+    P.ld = ld;
+    P.n_members = N;
+    P.n_steps = n_steps;
+    P.dt = d_dt;
+    P.write_steps = write_steps;
+    P.n_records = R;
+    P.rec = d_rec;
+    P.y = d_y;
+    P.s = tab.s;
+    P.chain = tab.chain ? 1 : 0;
+    for (int i = 0; i < tab.s; ++i) {
+        P.b[i] = tab.b[i];
+        P.alpha[i] = tab.alpha[i];
+        for (int j = 0; j < tab.s; ++j) P.a[i * tab.s + j] = tab.a[(size_t)i * tab.s + j];
+    }
+}
+
+template <int BS>
+static void launch_g1(const qgsb_tensor *t, RkParams &P)
+{
+    const int n = t->view.n, s = P.s;
+    const size_t per_thread = P.chain ? (size_t)(4 * n + 2) : (size_t)(2 * n + 1) + (size_t)s * n;
+    const size_t ent_bytes = sizeof(Entry) * (size_t)t->view.nnz;
+    size_t state = per_thread * 8 * BS + sizeof(int) * (n + 2);
+    P.tensor_in_smem = (ent_bytes <= 32 * 1024 && state + ent_bytes <= ctx().smem_optin) ? 1 : 0;
+    const size_t bytes = state + (P.tensor_in_smem ? ent_bytes : 0);
+    const unsigned grid = (unsigned)(P.ld / BS);
+    if (t->view.rank == 5) {
+        set_smem(rk_g1_kernel<5, BS>, bytes);
+        rk_g1_kernel<5, BS><<<grid, BS, bytes, ctx().stream>>>(t->view, P);
+    } else {
+        set_smem(rk_g1_kernel<3, BS>, bytes);
+        rk_g1_kernel<3, BS><<<grid, BS, bytes, ctx().stream>>>(t->view, P);
+    }
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+}
+
+static void launch_g2(const qgsb_tensor *t, RkParams &P)
+{
+    const int n = t->view.n, s = P.s;
+    const size_t per_member = P.chain ? (size_t)(4 * n + 2) : (size_t)(2 * n + 1) + (size_t)s * n;
+    const size_t bytes = per_member * 8 * G2_WARPS;
+    const unsigned grid = (unsigned)((P.ld + G2_WARPS - 1) / G2_WARPS);
+    if (t->view.rank == 5) {
+        set_smem(rk_g2_kernel<5>, bytes);
+        rk_g2_kernel<5><<<grid, G2_WARPS * 32, bytes, ctx().stream>>>(t->view, P);
+    } else {
+        set_smem(rk_g2_kernel<3>, bytes);
+        rk_g2_kernel<3><<<grid, G2_WARPS * 32, bytes, ctx().stream>>>(t->view, P);
+    }
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+}
+
+void rk_advance(const qgsb_tensor *t, double *d_y, long ld, long N, long n_steps, const double *d_dt,
+                const Tableau &tab, long write_steps, long R, double *d_rec)
+{
+    if (t->spec && t->use_spec && tab.chain && tab.s <= 8 && t->spec->rk_chain) {
+        QGSB_CUDA(t->spec->rk_chain(d_y, ld, N, n_steps, d_dt, tab.s, tab.alpha.data(), tab.b.data(), write_steps, R,
+                                    d_rec, ctx().sm_count, ctx().stream));
+        count_launch();
+        return;
+    }
+    RkParams P;
+    fill_params(P, tab, d_y, ld, N, n_steps, d_dt, write_steps, R, d_rec);
+    const int n = t->view.n;
+    if (n <= QGSB_G1_MAX_NDIM) {
+        const size_t per_thread = tab.chain ? (size_t)(4 * n + 2) : (size_t)(2 * n + 1) + (size_t)tab.s * n;
+        if (per_thread * 8 * 64 + 4096 <= ctx().smem_optin) return launch_g1<64>(t, P);
+        if (per_thread * 8 * 32 + 4096 <= ctx().smem_optin) return launch_g1<32>(t, P);
+    }
+    launch_g2(t, P);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DFMA peak micro-benchmark: 16 independent chains per thread, no memory traffic
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double seed)
+{
+    double a[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[q] = seed + q + threadIdx.x * 1e-9;
+    const double m = 0.999999, c = 1e-7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) a[q] = fma(a[q], m, c);
+    }
+    double ssum = 0.;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) ssum += a[q];
+    if (ssum == 12345.678) out[0] = ssum;  // never true: keeps the chains alive
+}
+
+}  // namespace qgsb
+
+using namespace qgsb;
+
+static long records_for(long n_steps, long write_steps)
+{
+    // integrate.py:190-196 with L = n_steps + 1 time points
+    if (write_steps == 0) return 1;
+    const long L = n_steps + 1;
+    long r = (L + write_steps - 1) / write_steps;
+    if ((r - 1) * write_steps != L - 1) r += 1;
+    return r;
+}
+
+extern "C" {
+
+int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_steps, const double *dt, int s,
+                      const double *a, const double *b, const double *c, long write_steps, int time_direction,
+                      long R, double *traj, double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t && ic && traj, "null argument");
+    QGSB_REQUIRE(N >= 1, "need at least one trajectory, got %ld", N);
+    QGSB_REQUIRE(n_steps >= 0 && write_steps >= 0, "negative step count");
+    QGSB_REQUIRE(n_steps == 0 || dt != nullptr, "null dt array");
+    QGSB_REQUIRE(time_direction == 1 || time_direction == -1, "time_direction must be +1 or -1");
+    QGSB_REQUIRE(R == records_for(n_steps, write_steps), "n_records %ld inconsistent with %ld steps / write_steps %ld",
+                 R, n_steps, write_steps);
+    ensure_init();
+    Context &cx = ctx();
+    cudaStream_t st = cx.stream;
+    const Tableau tab = make_tableau(s, a, b);
+    const int n = t->view.n;
+    const long ld = round_up(N, TILE);
+    DevBuf<double> d_ic((size_t)N * n), d_y((size_t)n * ld), d_dt(std::max<long>(n_steps, 1));
+    DevBuf<double> d_rec((size_t)R * n * ld), d_out((size_t)N * n * R);
+    d_ic.upload(ic, (size_t)N * n, st);
+    if (n_steps) d_dt.upload(dt, n_steps, st);
+    launch_aos_to_soa(d_ic.p, d_y.p, N, n, ld);
+    QGSB_CUDA(cudaEventRecord(cx.ev0, st));
+    rk_advance(t, d_y.p, ld, N, n_steps, d_dt.p, tab, write_steps, R, d_rec.p);
+    QGSB_CUDA(cudaEventRecord(cx.ev1, st));
+    launch_rec_to_api(d_rec.p, d_out.p, N, n, R, ld, time_direction == -1);
+    d_out.download(traj, (size_t)N * n * R, st);
+    QGSB_CUDA(cudaStreamSynchronize(st));
+    if (device_ms) {
+        float ms = 0.f;
+        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+        *device_ms = ms;
+    }
+    QGSB_API_END
+}
+
+// ---- resident ensemble ---------------------------------------------------------------------------
+int qgsb_ensemble_create(const qgsb_tensor *t, long N, qgsb_ensemble **out)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t && out, "null argument");
+    QGSB_REQUIRE(N >= 1, "need at least one trajectory");
+    ensure_init();
+    qgsb_ensemble *e = new qgsb_ensemble();
+    try {
+        e->tensor = t;
+        e->N = N;
+        e->ld = round_up(N, TILE);
+        e->d_y.alloc((size_t)t->view.n * e->ld);
+        e->d_stage.alloc((size_t)N * t->view.n);
+        QGSB_CUDA(cudaMemsetAsync(e->d_y.p, 0, sizeof(double) * t->view.n * e->ld, ctx().stream));
+    } catch (...) {
+        delete e;
+        throw;
+    }
+    *out = e;
+    QGSB_API_END
+}
+
+void qgsb_ensemble_destroy(qgsb_ensemble *e)
+{
+    if (!e) return;
+    if (ctx().ready) {
+        cudaSetDevice(ctx().device);
+        cudaStreamSynchronize(ctx().stream);
+    }
+    delete e;
+}
+
+int qgsb_ensemble_upload(qgsb_ensemble *e, const double *ic)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(e && ic, "null argument");
+    ensure_init();
+    const int n = e->tensor->view.n;
+    e->d_stage.upload(ic, (size_t)e->N * n, ctx().stream);
+    launch_aos_to_soa(e->d_stage.p, e->d_y.p, e->N, n, e->ld);
+    QGSB_API_END
+}
+
+int qgsb_ensemble_download(qgsb_ensemble *e, double *out)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(e && out, "null argument");
+    ensure_init();
+    const int n = e->tensor->view.n;
+    launch_soa_to_aos(e->d_y.p, e->d_stage.p, e->N, n, e->ld);
+    e->d_stage.download(out, (size_t)e->N * n, ctx().stream);
+    QGSB_CUDA(cudaStreamSynchronize(ctx().stream));
+    QGSB_API_END
+}
+
+static void ensemble_run(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a, const double *b,
+                         long write_steps, long R, double *d_rec, double *device_ms)
+{
+    QGSB_REQUIRE(e, "null ensemble");
+    QGSB_REQUIRE(n_steps >= 0, "negative step count");
+    ensure_init();
+    Context &cx = ctx();
+    const Tableau tab = make_tableau(s, a, b);
+    // dt staging buffer lives with the context so the launch can stay asynchronous
+    static DevBuf<double> d_dt;
+    if (d_dt.n < (size_t)std::max<long>(n_steps, 1)) {
+        QGSB_CUDA(cudaStreamSynchronize(cx.stream));
+        d_dt.alloc(std::max<long>(n_steps, 1));
+    }
+    if (n_steps) d_dt.upload(dt, n_steps, cx.stream);
+    if (device_ms) QGSB_CUDA(cudaEventRecord(cx.ev0, cx.stream));
+    rk_advance(e->tensor, e->d_y.p, e->ld, e->N, n_steps, d_dt.p, tab, write_steps, R, d_rec);
+    if (device_ms) {
+        QGSB_CUDA(cudaEventRecord(cx.ev1, cx.stream));
+        QGSB_CUDA(cudaEventSynchronize(cx.ev1));
+        float ms = 0.f;
+        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+        *device_ms = ms;
+    }
+}
+
+int qgsb_ensemble_integrate(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                            const double *b, const double *c, double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    ensemble_run(e, n_steps, dt, s, a, b, 0, 1, nullptr, device_ms);
+    QGSB_API_END
+}
+
+int qgsb_ensemble_integrate_record(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                                   const double *b, const double *c, long write_steps, long R, double *d_rec,
+                                   double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(d_rec != nullptr, "null record buffer");
+    QGSB_REQUIRE(R == records_for(n_steps, write_steps), "n_records %ld inconsistent with %ld steps / write_steps %ld",
+                 R, n_steps, write_steps);
+    ensemble_run(e, n_steps, dt, s, a, b, write_steps, R, d_rec, device_ms);
+    QGSB_API_END
+}
+
+void *qgsb_ensemble_device_ptr(qgsb_ensemble *e) { return e ? (void *)e->d_y.p : nullptr; }
+long qgsb_ensemble_ld(const qgsb_ensemble *e) { return e ? e->ld : 0; }
+
+int qgsb_fp64_peak(double *tflops, double *ms_out)
+{
+    QGSB_API_BEGIN
+    ensure_init();
+    Context &cx = ctx();
+    DevBuf<double> d_out(1);
+    const int iters = 4096, blocks = cx.sm_count * 8, threads = 256;
+    dfma_peak_kernel<<<blocks, threads, 0, cx.stream>>>(d_out.p, 64, 1.0);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        QGSB_CUDA(cudaEventRecord(cx.ev0, cx.stream));
+        dfma_peak_kernel<<<blocks, threads, 0, cx.stream>>>(d_out.p, iters, 1.0 + rep);
+        QGSB_CUDA(cudaEventRecord(cx.ev1, cx.stream));
+        QGSB_CUDA(cudaEventSynchronize(cx.ev1));
+        float ms = 0.f;
+        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+        best = std::min(best, ms);
+    }
+    count_launch(6);
+    const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    QGSB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,676 @@
+// runtime.cu -- context, error convention, tensor hand-off, layout kernels, batched f / Df and the
+// raw sparse_mul* contractions of libqgsb.
+#include <dlfcn.h>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <map>
+#include <numeric>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "spec_registry.h"
+
+namespace qgsb {
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+Context &ctx()
+{
+    static Context c;
+    return c;
+}
+
+static void init_device(int device)
+{
+    Context &c = ctx();
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    QGSB_REQUIRE(e == cudaSuccess && count > 0,
+                 "no CUDA device available (%s); libqgsb has no CPU fallback",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0) {
+        const char *lr = getenv("LOCAL_RANK");
+        device = lr ? atoi(lr) % count : 0;
+    }
+    QGSB_REQUIRE(device < count, "device %d requested but only %d visible", device, count);
+    if (c.ready && c.device == device) return;
+    if (c.ready) {
+        cudaStreamDestroy(c.own_stream);
+        cudaEventDestroy(c.ev0);
+        cudaEventDestroy(c.ev1);
+        c.ready = false;
+    }
+    QGSB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    QGSB_CUDA(cudaGetDeviceProperties(&p, device));
+    c.device = device;
+    c.sm_count = p.multiProcessorCount;
+    c.cc_major = p.major;
+    c.cc_minor = p.minor;
+    c.total_mem = p.totalGlobalMem;
+    c.smem_optin = p.sharedMemPerBlockOptin;
+    QGSB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
+    QGSB_CUDA(cudaEventCreate(&c.ev0));
+    QGSB_CUDA(cudaEventCreate(&c.ev1));
+    c.ready = true;
+}
+
+void ensure_init()
+{
+    if (!ctx().ready) init_device(-1);
+    else cudaSetDevice(ctx().device);
+}
+
+// ------------------------------------------------------------------------------------------------
+// specialised-kernel registry
+// ------------------------------------------------------------------------------------------------
+static std::map<uint64_t, const SpecKernels *> &registry()
+{
+    static std::map<uint64_t, const SpecKernels *> r;
+    return r;
+}
+
+void register_spec(const SpecKernels *k) { registry()[k->hash] = k; }
+
+const SpecKernels *find_spec(uint64_t hash)
+{
+    auto it = registry().find(hash);
+    return it == registry().end() ? nullptr : it->second;
+}
+
+uint64_t tensor_hash(int n, int rank, long nnz, const int32_t *coo_sorted, const double *val_sorted)
+{
+    uint64_t h = 1469598103934665603ULL;
+    auto mix_bytes = [&h](const void *p, size_t bytes) {
+        const unsigned char *c = (const unsigned char *)p;
+        for (size_t q = 0; q < bytes; ++q) {
+            h ^= (uint64_t)c[q];
+            h *= 1099511628211ULL;
+        }
+    };
+    const int32_t head[3] = {n, rank, (int32_t)nnz};
+    mix_bytes(head, sizeof(head));
+    mix_bytes(coo_sorted, sizeof(int32_t) * (size_t)nnz * rank);
+    mix_bytes(val_sorted, sizeof(double) * (size_t)nnz);
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side tensor preparation
+// ------------------------------------------------------------------------------------------------
+struct HostTensor {
+    std::vector<Entry> ent;
+    std::vector<int> row_ptr;
+    std::vector<int32_t> coo_sorted;
+    std::vector<double> val_sorted;
+};
+
+static void check_indices(int n1, int rank, long nnz, const int32_t *coo)
+{
+    QGSB_REQUIRE(rank == 3 || rank == 5, "tensor rank must be 3 or 5, got %d", rank);
+    QGSB_REQUIRE(n1 >= 1 && n1 <= 65535, "dimension %d out of range (1..65535)", n1);
+    QGSB_REQUIRE(nnz >= 0 && nnz < (1L << 31) / 8, "nnz %ld out of range", nnz);
+    for (long e = 0; e < nnz * rank; ++e)
+        QGSB_REQUIRE(coo[e] >= 0 && coo[e] < n1, "tensor index %d outside [0, %d) at entry %ld", coo[e], n1,
+                     e / rank);
+}
+
+// tendencies form: entries stably sorted by row, CSR over rows 0..n1-1
+static HostTensor prepare_vec(int n1, int rank, long nnz, const int32_t *coo, const double *val)
+{
+    check_indices(n1, rank, nnz, coo);
+    std::vector<long> order(nnz);
+    std::iota(order.begin(), order.end(), 0L);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](long x, long y) { return coo[x * rank] < coo[y * rank]; });
+    HostTensor h;
+    h.ent.resize(nnz);
+    h.row_ptr.assign(n1 + 1, 0);
+    h.coo_sorted.resize(nnz * rank);
+    h.val_sorted.resize(nnz);
+    for (long q = 0; q < nnz; ++q) {
+        const int32_t *c = coo + order[q] * rank;
+        Entry &e = h.ent[q];
+        e.v = val[order[q]];
+        e.jk = (uint32_t)c[1] | ((uint32_t)c[2] << 16);
+        e.lm = rank == 5 ? ((uint32_t)c[3] | ((uint32_t)c[4] << 16)) : 0u;
+        h.row_ptr[c[0] + 1]++;
+        for (int r = 0; r < rank; ++r) h.coo_sorted[q * rank + r] = c[r];
+        h.val_sorted[q] = e.v;
+    }
+    for (int i = 0; i < n1; ++i) h.row_ptr[i + 1] += h.row_ptr[i];
+    return h;
+}
+
+struct HostJac {
+    std::vector<Entry> ent;
+    std::vector<int> pos_ptr, pos_i, pos_j, row_ptr, col_ptr, col_perm;
+};
+
+// matrix form: distinct (i, j) positions with their entry runs; keep_zero keeps row/column 0
+static HostJac prepare_mat(int n1, int rank, long nnz, const int32_t *coo, const double *val, bool keep_zero)
+{
+    check_indices(n1, rank, nnz, coo);
+    std::vector<long> order;
+    order.reserve(nnz);
+    for (long e = 0; e < nnz; ++e)
+        if (keep_zero || (coo[e * rank] > 0 && coo[e * rank + 1] > 0)) order.push_back(e);
+    std::stable_sort(order.begin(), order.end(), [&](long x, long y) {
+        const int32_t *a = coo + x * rank, *b = coo + y * rank;
+        return a[0] != b[0] ? a[0] < b[0] : a[1] < b[1];
+    });
+    HostJac h;
+    h.ent.resize(order.size());
+    h.row_ptr.assign(n1 + 1, 0);
+    h.col_ptr.assign(n1 + 1, 0);
+    int li = -1, lj = -1;
+    for (size_t q = 0; q < order.size(); ++q) {
+        const int32_t *c = coo + order[q] * rank;
+        if (c[0] != li || c[1] != lj) {
+            h.pos_ptr.push_back((int)q);
+            h.pos_i.push_back(c[0]);
+            h.pos_j.push_back(c[1]);
+            h.row_ptr[c[0] + 1]++;
+            h.col_ptr[c[1] + 1]++;
+            li = c[0];
+            lj = c[1];
+        }
+        Entry &e = h.ent[q];
+        e.v = val[order[q]];
+        e.jk = rank == 5 ? ((uint32_t)c[2] | ((uint32_t)c[3] << 16)) : (uint32_t)c[2];
+        e.lm = rank == 5 ? (uint32_t)c[4] : 0u;
+    }
+    h.pos_ptr.push_back((int)order.size());
+    for (int i = 0; i < n1; ++i) {
+        h.row_ptr[i + 1] += h.row_ptr[i];
+        h.col_ptr[i + 1] += h.col_ptr[i];
+    }
+    const int npos = (int)h.pos_i.size();
+    h.col_perm.resize(npos);
+    std::iota(h.col_perm.begin(), h.col_perm.end(), 0);
+    std::stable_sort(h.col_perm.begin(), h.col_perm.end(),
+                     [&](int x, int y) { return h.pos_j[x] < h.pos_j[y]; });
+    return h;
+}
+
+template <typename T>
+static void to_device(DevBuf<T> &d, const std::vector<T> &h)
+{
+    d.alloc(std::max<size_t>(h.size(), 1));
+    if (!h.empty()) QGSB_CUDA(cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: layout changes
+// ------------------------------------------------------------------------------------------------
+// (N, n) member-major  ->  tiled SoA over ld members; padding members are zero-filled
+__global__ void aos_to_soa_kernel(const double *__restrict__ in, double *__restrict__ out, long N, int n, long ld)
+{
+    __shared__ double tile[32][33];
+    const long m0 = (long)blockIdx.x * 32;
+    const int i0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        long m = m0 + r;
+        int i = i0 + threadIdx.x;
+        tile[r][threadIdx.x] = (m < N && i < n) ? in[m * n + i] : 0.;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int i = i0 + r;
+        long m = m0 + threadIdx.x;
+        if (i < n && m < ld) out[tile_base(m, n) + (size_t)i * TILE] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void soa_to_aos_kernel(const double *__restrict__ in, double *__restrict__ out, long N, int n, long ld)
+{
+    __shared__ double tile[32][33];
+    const long m0 = (long)blockIdx.x * 32;
+    const int i0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int i = i0 + r;
+        long m = m0 + threadIdx.x;
+        tile[r][threadIdx.x] = (i < n && m < N) ? in[tile_base(m, n) + (size_t)i * TILE] : 0.;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        long m = m0 + r;
+        int i = i0 + threadIdx.x;
+        if (m < N && i < n) out[m * n + i] = tile[threadIdx.x][r];
+    }
+}
+
+// records (R, tiled SoA of `rows` variables) -> API layout (N, rows, R); flip reverses the record axis
+// (integrate.py:223).  One (record, member) tile per block and per row.
+__global__ void rec_to_api_kernel(const double *__restrict__ in, double *__restrict__ out, long N, int rows,
+                                  long R, long ld, int flip, long m_tiles, int row0)
+{
+    __shared__ double tile[32][33];
+    const long m0 = ((long)blockIdx.x % m_tiles) * 32;
+    const long r0 = ((long)blockIdx.x / m_tiles) * 32;
+    const int i = blockIdx.y + row0;
+    for (int q = threadIdx.y; q < 32; q += blockDim.y) {
+        long r = r0 + q;
+        long m = m0 + threadIdx.x;
+        tile[q][threadIdx.x] = (r < R && m < N) ? in[(size_t)r * rows * ld + tile_base(m, rows) + (size_t)i * TILE] : 0.;
+    }
+    __syncthreads();
+    for (int q = threadIdx.y; q < 32; q += blockDim.y) {
+        long m = m0 + q;
+        long r = r0 + threadIdx.x;
+        if (m < N && r < R) {
+            long ro = flip ? R - 1 - r : r;
+            out[(m * rows + i) * R + ro] = tile[threadIdx.x][q];
+        }
+    }
+}
+
+void launch_aos_to_soa(const double *d_in, double *d_out, long N, int n, long ld)
+{
+    dim3 grid((unsigned)((ld + 31) / 32), (unsigned)((n + 31) / 32)), block(32, 8);
+    aos_to_soa_kernel<<<grid, block, 0, ctx().stream>>>(d_in, d_out, N, n, ld);
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+}
+
+void launch_soa_to_aos(const double *d_in, double *d_out, long N, int n, long ld)
+{
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((n + 31) / 32)), block(32, 8);
+    soa_to_aos_kernel<<<grid, block, 0, ctx().stream>>>(d_in, d_out, N, n, ld);
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+}
+
+void launch_rec_to_api(const double *d_in, double *d_out, long N, long rows, long R, long ld, int flip)
+{
+    const long m_tiles = (N + 31) / 32, r_tiles = (R + 31) / 32;
+    QGSB_REQUIRE(m_tiles * r_tiles < (1L << 31), "record buffer too large for one layout-change launch");
+    // rows can exceed the grid y limit (65535) for n * m fundamental matrices: chunk it
+    for (long z0 = 0; z0 < rows; z0 += 65535) {
+        long nz = std::min<long>(65535, rows - z0);
+        dim3 grid((unsigned)(m_tiles * r_tiles), (unsigned)nz), block(32, 8);
+        rec_to_api_kernel<<<grid, block, 0, ctx().stream>>>(d_in, d_out, N, (int)rows, R, ld, flip, m_tiles, (int)z0);
+        count_launch();
+    }
+    QGSB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: batched contractions on member-major input (the f / Df closures and sparse_mul*)
+// ------------------------------------------------------------------------------------------------
+// one thread per (member, row): out[m][i - shift] = sum over row i.  The four vectors may differ
+// (sparse_mul3/5 proper) or all alias x (the f closure).  stride = distance between members.
+template <int RANK>
+__global__ void mulvec_kernel(TensorView T, long N, int n1, const double *__restrict__ va,
+                              const double *__restrict__ vb, const double *__restrict__ vc,
+                              const double *__restrict__ vd, long stride, int with_x0, double *__restrict__ out,
+                              int shift, int out_stride)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int rows = n1 - shift;
+    if (t >= N * rows) return;
+    const long m = t / rows;
+    const int i = (int)(t % rows) + shift;
+    // with_x0: vectors hold only x_1..x_n and x_0 = 1 is implied (the closures' concatenate, tendencies.py:112)
+    auto ld = [&](const double *v, uint32_t idx) -> double {
+        if (with_x0) return idx == 0 ? 1. : v[m * stride + idx - 1];
+        return v[m * stride + idx];
+    };
+    double acc = 0.;
+    for (int e = T.row_ptr[i]; e < T.row_ptr[i + 1]; ++e) {
+        const Entry en = T.ent[e];
+        double p = ld(va, en.jk & 0xffffu) * ld(vb, en.jk >> 16);
+        if (RANK == 5) p = p * ld(vc, en.lm & 0xffffu) * ld(vd, en.lm >> 16);
+        acc += p * en.v;
+    }
+    if (i == 0) acc = 1.;  // sparse_mul.py:80 / :157
+    out[m * out_stride + (i - shift)] = acc;
+}
+
+// one thread per (member, matrix position): out[m][i - shift][j - shift] = J_ij
+template <int RANK>
+__global__ void mulmat_kernel(JacView J, long N, const double *__restrict__ va, const double *__restrict__ vb,
+                              const double *__restrict__ vc, long stride, int with_x0, double *__restrict__ out,
+                              int shift, int ldo)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * J.npos) return;
+    const long m = t / J.npos;
+    const int p = (int)(t % J.npos);
+    auto ld = [&](const double *v, uint32_t idx) -> double {
+        if (with_x0) return idx == 0 ? 1. : v[m * stride + idx - 1];
+        return v[m * stride + idx];
+    };
+    double acc = 0.;
+    for (int e = J.pos_ptr[p]; e < J.pos_ptr[p + 1]; ++e) {
+        const Entry en = J.ent[e];
+        double q = ld(va, en.jk & 0xffffu);
+        if (RANK == 5) q = q * ld(vb, en.jk >> 16) * ld(vc, en.lm);
+        acc += q * en.v;
+    }
+    out[(m * ldo + (J.pos_i[p] - shift)) * ldo + (J.pos_j[p] - shift)] = acc;
+}
+
+}  // namespace qgsb
+
+using namespace qgsb;
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char *qgsb_last_error(void) { return g_err; }
+const char *qgsb_version(void) { return "qgsb 0.1 (sm_100a)"; }
+long qgsb_launch_count(void) { return ctx().launches; }
+
+int qgsb_init(int device)
+{
+    QGSB_API_BEGIN
+    init_device(device);
+    QGSB_API_END
+}
+
+void qgsb_shutdown(void)
+{
+    Context &c = ctx();
+    if (!c.ready) return;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    cudaStreamDestroy(c.own_stream);
+    cudaEventDestroy(c.ev0);
+    cudaEventDestroy(c.ev1);
+    c.own_stream = c.stream = nullptr;
+    c.ready = false;
+}
+
+int qgsb_set_stream(void *cuda_stream)
+{
+    QGSB_API_BEGIN
+    ensure_init();
+    ctx().stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx().own_stream;
+    QGSB_API_END
+}
+
+int qgsb_synchronize(void)
+{
+    QGSB_API_BEGIN
+    ensure_init();
+    QGSB_CUDA(cudaStreamSynchronize(ctx().stream));
+    QGSB_API_END
+}
+
+int qgsb_device_info(int *device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem)
+{
+    QGSB_API_BEGIN
+    ensure_init();
+    Context &c = ctx();
+    if (device) *device = c.device;
+    if (sm_count) *sm_count = c.sm_count;
+    if (cc_major) *cc_major = c.cc_major;
+    if (cc_minor) *cc_minor = c.cc_minor;
+    if (total_mem) *total_mem = c.total_mem;
+    QGSB_API_END
+}
+
+int qgsb_load_plugin(const char *path)
+{
+    QGSB_API_BEGIN
+    void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    QGSB_REQUIRE(h != nullptr, "dlopen(%s) failed: %s", path, dlerror());
+    typedef const SpecKernels *(*entry_fn)(void);
+    entry_fn entry = (entry_fn)dlsym(h, "qgsb_plugin_kernels");
+    QGSB_REQUIRE(entry != nullptr, "%s does not export qgsb_plugin_kernels", path);
+    const SpecKernels *k = entry();
+    QGSB_REQUIRE(k != nullptr && k->rk_chain != nullptr, "%s returned an empty kernel table", path);
+    register_spec(k);
+    QGSB_API_END
+}
+
+int qgsb_tensor_create(int ndim, int rank, long nnz, const int32_t *coo, const double *val, long jnnz,
+                       const int32_t *jcoo, const double *jval, qgsb_tensor **out)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(out != nullptr, "null output handle");
+    QGSB_REQUIRE(ndim >= 1, "ndim must be positive");
+    ensure_init();
+    HostTensor h = prepare_vec(ndim + 1, rank, nnz, coo, val);
+    HostJac j = prepare_mat(ndim + 1, rank, jnnz, jcoo, jval, false);
+    qgsb_tensor *t = new qgsb_tensor();
+    try {
+        to_device(t->d_ent, h.ent);
+        to_device(t->d_row_ptr, h.row_ptr);
+        to_device(t->d_jent, j.ent);
+        to_device(t->d_pos_ptr, j.pos_ptr);
+        to_device(t->d_pos_i, j.pos_i);
+        to_device(t->d_pos_j, j.pos_j);
+        to_device(t->d_jrow_ptr, j.row_ptr);
+        to_device(t->d_jcol_ptr, j.col_ptr);
+        to_device(t->d_jcol_perm, j.col_perm);
+    } catch (...) {
+        delete t;
+        throw;
+    }
+    t->nnz_in = nnz;
+    t->jnnz_in = jnnz;
+    t->view.n = ndim;
+    t->view.rank = rank;
+    t->view.nnz = (int)nnz;
+    t->view.ent = t->d_ent.p;
+    t->view.row_ptr = t->d_row_ptr.p;
+    t->view.jac.npos = (int)j.pos_i.size();
+    t->view.jac.pos_ptr = t->d_pos_ptr.p;
+    t->view.jac.ent = t->d_jent.p;
+    t->view.jac.pos_i = t->d_pos_i.p;
+    t->view.jac.pos_j = t->d_pos_j.p;
+    t->view.jac.row_ptr = t->d_jrow_ptr.p;
+    t->view.jac.col_ptr = t->d_jcol_ptr.p;
+    t->view.jac.col_perm = t->d_jcol_perm.p;
+    t->hash = tensor_hash(ndim, rank, nnz, h.coo_sorted.data(), h.val_sorted.data());
+    t->coo_sorted.swap(h.coo_sorted);
+    t->val_sorted.swap(h.val_sorted);
+    t->spec = find_spec(t->hash);
+    if (t->spec && (t->spec->n != ndim || t->spec->rank != rank || t->spec->nnz != (int)nnz)) t->spec = nullptr;
+    *out = t;
+    QGSB_API_END
+}
+
+void qgsb_tensor_destroy(qgsb_tensor *t)
+{
+    if (!t) return;
+    if (ctx().ready) cudaSetDevice(ctx().device);
+    delete t;
+}
+
+int qgsb_tensor_info(const qgsb_tensor *t, int *ndim, int *rank, long *nnz, long *jnnz, int *kernel_kind,
+                     uint64_t *hash)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t != nullptr, "null tensor handle");
+    if (ndim) *ndim = t->view.n;
+    if (rank) *rank = t->view.rank;
+    if (nnz) *nnz = t->nnz_in;
+    if (jnnz) *jnnz = t->jnnz_in;
+    if (kernel_kind) *kernel_kind = (t->spec && t->use_spec) ? 2 : (t->view.n > QGSB_G1_MAX_NDIM ? 1 : 0);
+    if (hash) *hash = t->hash;
+    QGSB_API_END
+}
+
+int qgsb_tensor_use_specialised(qgsb_tensor *t, int enable)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t != nullptr, "null tensor handle");
+    t->use_spec = enable != 0;
+    if (enable) {  // pick up modules registered after the handle was created (qgsb_load_plugin)
+        const SpecKernels *k = find_spec(t->hash);
+        if (k && k->n == t->view.n && k->rank == t->view.rank && k->nnz == (int)t->nnz_in) t->spec = k;
+    }
+    QGSB_API_END
+}
+
+// ---- raw contractions --------------------------------------------------------------------------
+static void raw_mulvec(int rank, long nnz, const int32_t *coo, const double *val, int n1, const double *va,
+                       const double *vb, const double *vc, const double *vd, double *res)
+{
+    ensure_init();
+    cudaStream_t s = ctx().stream;
+    HostTensor h = prepare_vec(n1, rank, nnz, coo, val);
+    DevBuf<Entry> d_ent;
+    DevBuf<int> d_row;
+    to_device(d_ent, h.ent);
+    to_device(d_row, h.row_ptr);
+    DevBuf<double> d_v((size_t)4 * n1), d_out(n1);
+    const double *vs[4] = {va, vb, vc ? vc : va, vd ? vd : va};
+    for (int q = 0; q < 4; ++q)
+        QGSB_CUDA(cudaMemcpyAsync(d_v.p + (size_t)q * n1, vs[q], sizeof(double) * n1, cudaMemcpyHostToDevice, s));
+    TensorView T;
+    T.n = n1 - 1;
+    T.rank = rank;
+    T.nnz = (int)nnz;
+    T.ent = d_ent.p;
+    T.row_ptr = d_row.p;
+    const int threads = 128, blocks = (n1 + threads - 1) / threads;
+    if (rank == 5)
+        mulvec_kernel<5><<<blocks, threads, 0, s>>>(T, 1, n1, d_v.p, d_v.p + n1, d_v.p + 2 * n1, d_v.p + 3 * n1, 0, 0,
+                                                    d_out.p, 0, n1);
+    else
+        mulvec_kernel<3><<<blocks, threads, 0, s>>>(T, 1, n1, d_v.p, d_v.p + n1, d_v.p, d_v.p, 0, 0, d_out.p, 0, n1);
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+    d_out.download(res, n1, s);
+    QGSB_CUDA(cudaStreamSynchronize(s));
+}
+
+static void raw_mulmat(int rank, long nnz, const int32_t *coo, const double *val, int n1, const double *va,
+                       const double *vb, const double *vc, double *res)
+{
+    ensure_init();
+    cudaStream_t s = ctx().stream;
+    HostJac h = prepare_mat(n1, rank, nnz, coo, val, true);
+    DevBuf<Entry> d_ent;
+    DevBuf<int> d_pp, d_pi, d_pj;
+    to_device(d_ent, h.ent);
+    to_device(d_pp, h.pos_ptr);
+    to_device(d_pi, h.pos_i);
+    to_device(d_pj, h.pos_j);
+    DevBuf<double> d_v((size_t)3 * n1), d_out((size_t)n1 * n1);
+    const double *vs[3] = {va, vb ? vb : va, vc ? vc : va};
+    for (int q = 0; q < 3; ++q)
+        QGSB_CUDA(cudaMemcpyAsync(d_v.p + (size_t)q * n1, vs[q], sizeof(double) * n1, cudaMemcpyHostToDevice, s));
+    QGSB_CUDA(cudaMemsetAsync(d_out.p, 0, sizeof(double) * n1 * n1, s));
+    JacView J;
+    J.npos = (int)h.pos_i.size();
+    J.pos_ptr = d_pp.p;
+    J.ent = d_ent.p;
+    J.pos_i = d_pi.p;
+    J.pos_j = d_pj.p;
+    if (J.npos > 0) {
+        const int threads = 128, blocks = (J.npos + threads - 1) / threads;
+        if (rank == 5)
+            mulmat_kernel<5><<<blocks, threads, 0, s>>>(J, 1, d_v.p, d_v.p + n1, d_v.p + 2 * n1, 0, 0, d_out.p, 0, n1);
+        else
+            mulmat_kernel<3><<<blocks, threads, 0, s>>>(J, 1, d_v.p, d_v.p, d_v.p, 0, 0, d_out.p, 0, n1);
+        count_launch();
+        QGSB_CUDA(cudaGetLastError());
+    }
+    d_out.download(res, (size_t)n1 * n1, s);
+    QGSB_CUDA(cudaStreamSynchronize(s));
+}
+
+int qgsb_sparse_mul3(long nnz, const int32_t *coo, const double *val, int n1, const double *vec_a,
+                     const double *vec_b, double *res)
+{
+    QGSB_API_BEGIN
+    raw_mulvec(3, nnz, coo, val, n1, vec_a, vec_b, nullptr, nullptr, res);
+    QGSB_API_END
+}
+
+int qgsb_sparse_mul5(long nnz, const int32_t *coo, const double *val, int n1, const double *vec_a,
+                     const double *vec_b, const double *vec_c, const double *vec_d, double *res)
+{
+    QGSB_API_BEGIN
+    raw_mulvec(5, nnz, coo, val, n1, vec_a, vec_b, vec_c, vec_d, res);
+    QGSB_API_END
+}
+
+int qgsb_sparse_mul2(long nnz, const int32_t *coo, const double *val, int n1, const double *vec, double *res)
+{
+    QGSB_API_BEGIN
+    raw_mulmat(3, nnz, coo, val, n1, vec, nullptr, nullptr, res);
+    QGSB_API_END
+}
+
+int qgsb_sparse_mul4(long nnz, const int32_t *coo, const double *val, int n1, const double *vec_a,
+                     const double *vec_b, const double *vec_c, double *res)
+{
+    QGSB_API_BEGIN
+    raw_mulmat(5, nnz, coo, val, n1, vec_a, vec_b, vec_c, res);
+    QGSB_API_END
+}
+
+// ---- f / Df closures -----------------------------------------------------------------------------
+int qgsb_tendencies(const qgsb_tensor *t, long N, const double *x, double *out)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t && x && out, "null argument");
+    QGSB_REQUIRE(N >= 0, "negative member count");
+    if (N == 0) return 0;
+    ensure_init();
+    cudaStream_t s = ctx().stream;
+    const int n = t->view.n;
+    DevBuf<double> d_x((size_t)N * n), d_out((size_t)N * n);
+    d_x.upload(x, (size_t)N * n, s);
+    const long total = N * n;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    if (t->view.rank == 5)
+        mulvec_kernel<5><<<blocks, threads, 0, s>>>(t->view, N, n + 1, d_x.p, d_x.p, d_x.p, d_x.p, n, 1, d_out.p, 1, n);
+    else
+        mulvec_kernel<3><<<blocks, threads, 0, s>>>(t->view, N, n + 1, d_x.p, d_x.p, d_x.p, d_x.p, n, 1, d_out.p, 1, n);
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+    d_out.download(out, (size_t)N * n, s);
+    QGSB_CUDA(cudaStreamSynchronize(s));
+    QGSB_API_END
+}
+
+int qgsb_jacobian(const qgsb_tensor *t, long N, const double *x, double *out)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t && x && out, "null argument");
+    QGSB_REQUIRE(N >= 0, "negative member count");
+    if (N == 0) return 0;
+    ensure_init();
+    cudaStream_t s = ctx().stream;
+    const int n = t->view.n;
+    DevBuf<double> d_x((size_t)N * n), d_out((size_t)N * n * n);
+    d_x.upload(x, (size_t)N * n, s);
+    QGSB_CUDA(cudaMemsetAsync(d_out.p, 0, sizeof(double) * N * n * n, s));
+    const long total = N * t->view.jac.npos;
+    if (total > 0) {
+        const int threads = 128;
+        const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+        if (t->view.rank == 5)
+            mulmat_kernel<5><<<blocks, threads, 0, s>>>(t->view.jac, N, d_x.p, d_x.p, d_x.p, n, 1, d_out.p, 1, n);
+        else
+            mulmat_kernel<3><<<blocks, threads, 0, s>>>(t->view.jac, N, d_x.p, d_x.p, d_x.p, n, 1, d_out.p, 1, n);
+        count_launch();
+        QGSB_CUDA(cudaGetLastError());
+    }
+    d_out.download(out, (size_t)N * n * n, s);
+    QGSB_CUDA(cudaStreamSynchronize(s));
+    QGSB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,718 @@
+// tgls.cu -- tangent-linear / adjoint propagation and Benettin re-orthonormalisation kernels.
+//
+// Replaces _integrate_runge_kutta_tgls_jit (qgs/integrators/integrate.py:555-614), the
+// TglsTrajectoryProcess pool (qgs/integrators/integrator.py:1103-1169) and the per-member Benettin
+// loops of qgs/toolbox/lyapunov.py:471-632 (propagate, np.linalg.qr, log|diag R| / dt).
+//
+// One thread block owns one ensemble member.  The nonlinear state, the Jacobian (as the values of
+// its structurally non-zero positions, never as a dense matrix) and the n x m tangent matrices of
+// all Runge-Kutta stages live in shared memory; the product J @ X walks the CSR list of Jacobian
+// positions (CSC for the adjoint), so the work is nnz(J) * m instead of the reference's dense n*n*m.
+// Data layout in HBM is member-major ((N, n), (N, n, m)), i.e. the API layout: a block reads and
+// writes contiguous chunks.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace qgsb {
+
+constexpr int TG_THREADS = 128;
+
+struct TgParams {
+    long n_members;
+    int m;                 // tangent columns
+    int s;
+    int adjoint;
+    double inverse;
+    double a[16 * 16];
+    double b[16];
+    // --- plain TGLS integration (integrate.py:555-614) ---
+    long n_steps;
+    const double *dt;      // (n_steps)
+    long write_steps;
+    long n_records;
+    double *y;             // (N, n)     in: ic, out: end state
+    double *fm;            // (N, n, m)  in: tg_ic, out: end state
+    double *rec_y;         // (R, N, n) or null
+    double *rec_fm;        // (R, N, n, m) or null
+    // --- Benettin (lyapunov.py:471-632) ---
+    int forward;
+    long n_pre, n_rec;
+    const double *dt_macro;   // (n_pre + n_rec)
+    const long *sub_ptr;      // (n_pre + n_rec + 1)
+    const double *sub_dt;
+    const double *stored;     // forward mode: write_steps=1 trajectory, tiled SoA records; else null
+    long stored_ld;
+    const long *start_idx;    // forward mode: stored-trajectory index used by every step
+    long final_idx;
+    const double *r0;         // (N, m, m) or null
+    double *rec_exp;          // (R, N, m)
+    double *r_all;            // (N, steps, m, m) or null
+    double *q_all;            // (N, n_rec + 1, n, m) or null
+    // --- placement of the big matrices ---
+    double *scratch;          // global scratch when shared memory is too small, else null
+    size_t scratch_per_member;
+};
+
+struct TgShared {
+    double *xs, *y, *Y, *K, *Jv, *rdiag, *red, *fm, *kms, *KM;
+};
+
+__device__ __forceinline__ TgShared carve(unsigned char *raw, const TensorView &T, const TgParams &P, long member)
+{
+    const int n = T.n, m = P.m, s = P.s;
+    TgShared S;
+    double *p = reinterpret_cast<double *>(raw);
+    S.xs = p;            p += n + 1;
+    S.y = p;             p += n;
+    S.Y = p;             p += n;
+    S.K = p;             p += (size_t)s * n;
+    S.Jv = p;            p += T.jac.npos;
+    S.rdiag = p;         p += m;
+    S.red = p;           p += 64;
+    double *mat = P.scratch ? P.scratch + (size_t)member * P.scratch_per_member : p;
+    S.fm = mat;
+    S.kms = mat + (size_t)n * m;
+    S.KM = mat + (size_t)2 * n * m;
+    return S;
+}
+
+template <int RANK>
+__device__ __forceinline__ double f_row(const TensorView &T, int i, const double *xs)
+{
+    double acc = 0.;
+    for (int e = T.row_ptr[i]; e < T.row_ptr[i + 1]; ++e) {
+        const Entry en = T.ent[e];
+        double p = xs[en.jk & 0xffffu] * xs[en.jk >> 16];
+        if (RANK == 5) p = p * xs[en.lm & 0xffffu] * xs[en.lm >> 16];
+        acc += p * en.v;
+    }
+    return acc;
+}
+
+template <int RANK>
+__device__ __forceinline__ double jac_pos(const JacView &J, int p, const double *xs)
+{
+    double acc = 0.;
+    for (int e = J.pos_ptr[p]; e < J.pos_ptr[p + 1]; ++e) {
+        const Entry en = J.ent[e];
+        double q = xs[en.jk & 0xffffu];
+        if (RANK == 5) q = q * xs[en.jk >> 16] * xs[en.lm];
+        acc += q * en.v;
+    }
+    return acc;
+}
+
+// one explicit Runge-Kutta step of the nonlinear state only: S.y <- RK(S.y, dt)
+template <int RANK>
+__device__ void nl_step(const TensorView &T, const TgParams &P, const TgShared &S, double dt)
+{
+    const int n = T.n, s = P.s, tid = threadIdx.x;
+    for (int st = 0; st < s; ++st) {
+        for (int r = tid; r < n; r += TG_THREADS) {
+            double v = 0.;
+            for (int j = 0; j < st; ++j) {
+                const double w = P.a[st * s + j];
+                if (w != 0.) v += (dt * w) * S.K[(size_t)j * n + r];
+            }
+            S.xs[r + 1] = S.y[r] + v;
+        }
+        __syncthreads();
+        for (int r = tid; r < n; r += TG_THREADS) S.K[(size_t)st * n + r] = f_row<RANK>(T, r + 1, S.xs);
+        __syncthreads();
+    }
+    for (int r = tid; r < n; r += TG_THREADS) {
+        double v = 0.;
+        for (int j = 0; j < s; ++j) v += (dt * P.b[j]) * S.K[(size_t)j * n + r];
+        S.y[r] += v;
+    }
+    __syncthreads();
+}
+
+// one step of the coupled system (integrate.py:590-609): S.y and S.fm advance by dt
+template <int RANK>
+__device__ void tg_step(const TensorView &T, const TgParams &P, const TgShared &S, double dt)
+{
+    const int n = T.n, m = P.m, s = P.s, tid = threadIdx.x;
+    const int nm = n * m;
+    const JacView &J = T.jac;
+    for (int st = 0; st < s; ++st) {
+        // stage state of the nonlinear part and of the tangent part
+        for (int r = tid; r < n; r += TG_THREADS) {
+            double v = 0.;
+            for (int j = 0; j < st; ++j) {
+                const double w = P.a[st * s + j];
+                if (w != 0.) v += (dt * w) * S.K[(size_t)j * n + r];
+            }
+            S.xs[r + 1] = S.y[r] + v;
+        }
+        for (int q = tid; q < nm; q += TG_THREADS) {
+            double v = S.fm[q];                                            // km_s = fm + sum dt a_ij km_j  :598-600
+            for (int j = 0; j < st; ++j) {
+                const double w = P.a[st * s + j];
+                if (w != 0.) v += (dt * w) * S.KM[(size_t)j * nm + q];
+            }
+            S.kms[q] = v;
+        }
+        __syncthreads();
+        // tendencies and Jacobian positions at the stage state
+        for (int r = tid; r < n; r += TG_THREADS) S.K[(size_t)st * n + r] = f_row<RANK>(T, r + 1, S.xs);
+        for (int p = tid; p < J.npos; p += TG_THREADS) S.Jv[p] = jac_pos<RANK>(J, p, S.xs);
+        __syncthreads();
+        // km_i = inverse * (J or J^T) @ km_s          :601-603 with boundary == 0
+        double *out = S.KM + (size_t)st * nm;
+        for (int q = tid; q < nm; q += TG_THREADS) {
+            const int r = q / m + 1, c = q - (r - 1) * m;
+            double acc = 0.;
+            if (!P.adjoint) {
+                for (int p = J.row_ptr[r]; p < J.row_ptr[r + 1]; ++p)
+                    acc += S.Jv[p] * S.kms[(size_t)(J.pos_j[p] - 1) * m + c];
+            } else {
+                for (int pp = J.col_ptr[r]; pp < J.col_ptr[r + 1]; ++pp) {
+                    const int p = J.col_perm[pp];
+                    acc += S.Jv[p] * S.kms[(size_t)(J.pos_i[p] - 1) * m + c];
+                }
+            }
+            out[q] = P.inverse * acc;
+        }
+        __syncthreads();
+    }
+    for (int r = tid; r < n; r += TG_THREADS) {
+        double v = 0.;
+        for (int j = 0; j < s; ++j) v += (dt * P.b[j]) * S.K[(size_t)j * n + r];
+        S.y[r] += v;
+    }
+    for (int q = tid; q < nm; q += TG_THREADS) {
+        double v = S.fm[q];
+        for (int j = 0; j < s; ++j) v += (dt * P.b[j]) * S.KM[(size_t)j * nm + q];   // :605-607
+        S.fm[q] = v;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// plain TGLS integration
+// ------------------------------------------------------------------------------------------------
+template <int RANK>
+__global__ void __launch_bounds__(TG_THREADS) tgls_kernel(TensorView T, const __grid_constant__ TgParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const long member = blockIdx.x;
+    const int n = T.n, m = P.m, tid = threadIdx.x, nm = n * m;
+    TgShared S = carve(smem_raw, T, P, member);
+    for (int r = tid; r < n; r += TG_THREADS) S.y[r] = P.y[member * n + r];
+    for (int q = tid; q < nm; q += TG_THREADS) S.fm[q] = P.fm[member * nm + q];
+    if (tid == 0) S.xs[0] = 1.;
+    __syncthreads();
+    long iw = 0;
+    for (long ti = 0; ti < P.n_steps; ++ti) {
+        if (P.rec_y && P.write_steps > 0 && ti % P.write_steps == 0) {      // integrate.py:585-588
+            double *ry = P.rec_y + ((size_t)iw * P.n_members + member) * n;
+            double *rf = P.rec_fm + ((size_t)iw * P.n_members + member) * nm;
+            for (int r = tid; r < n; r += TG_THREADS) ry[r] = S.y[r];
+            for (int q = tid; q < nm; q += TG_THREADS) rf[q] = S.fm[q];
+            ++iw;
+        }
+        tg_step<RANK>(T, P, S, P.dt[ti]);
+    }
+    if (P.rec_y) {                                                           // integrate.py:611-612
+        double *ry = P.rec_y + ((size_t)(P.n_records - 1) * P.n_members + member) * n;
+        double *rf = P.rec_fm + ((size_t)(P.n_records - 1) * P.n_members + member) * nm;
+        for (int r = tid; r < n; r += TG_THREADS) ry[r] = S.y[r];
+        for (int q = tid; q < nm; q += TG_THREADS) rf[q] = S.fm[q];
+    }
+    for (int r = tid; r < n; r += TG_THREADS) P.y[member * n + r] = S.y[r];
+    for (int q = tid; q < nm; q += TG_THREADS) P.fm[member * nm + q] = S.fm[q];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Householder QR of the n x m matrix A (row-major, in place) with LAPACK's dgeqr2 / dorg2r
+// conventions -- np.linalg.qr of lyapunov.py:602-604.  On exit A holds Q (n x m), Rout (m x m,
+// row-major, may be null) the upper-triangular factor and rdiag its diagonal.  W is a workspace of
+// n m + 2 m doubles, red three doubles of scratch.
+// ------------------------------------------------------------------------------------------------
+__device__ void block_qr(int n, int m, double *A, double *W, double *rdiag, double *red, double *Rout)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // workspace carving: tau_j in W[0..m), column weights in W[m..2m), Q built in W[2m..2m + n m).
+    // (W is the stage-input buffer followed by the stage-derivative buffers, all free during the QR.)
+    double *taus = W;
+    double *wv = W + m;
+    for (int j = 0; j < m; ++j) {
+        // ---- reflector for column j ----
+        if (warp == 0) {
+            double ss = 0.;
+            for (int i = j + 1 + lane; i < n; i += 32) {
+                const double v = A[(size_t)i * m + j];
+                ss += v * v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0) {
+                const double alpha = A[(size_t)j * m + j];
+                const double xnorm = sqrt(ss);
+                if (xnorm == 0.) {
+                    red[0] = 0.;        // tau
+                    red[1] = 0.;        // scale (unused)
+                    red[2] = alpha;     // beta
+                } else {
+                    const double beta = -copysign(hypot(alpha, xnorm), alpha);
+                    red[0] = (beta - alpha) / beta;
+                    red[1] = 1. / (alpha - beta);
+                    red[2] = beta;
+                }
+            }
+        }
+        __syncthreads();
+        const double tj = red[0], scal = red[1], beta = red[2];
+        if (tj != 0.)
+            for (int i = j + 1 + tid; i < n; i += TG_THREADS) A[(size_t)i * m + j] *= scal;
+        __syncthreads();
+        if (tid == 0) {
+            A[(size_t)j * m + j] = beta;
+            rdiag[j] = beta;
+            taus[j] = tj;
+        }
+        // ---- apply H_j = I - tau v v^T to the trailing columns (v_j = 1) ----
+        // w_c = tau * (A[j][c] + sum_{i>j} v_i A[i][c]), one thread per trailing column
+        for (int c = j + 1 + tid; c < m; c += TG_THREADS) {
+            double w = A[(size_t)j * m + c];
+            for (int i = j + 1; i < n; ++i) w += A[(size_t)i * m + j] * A[(size_t)i * m + c];
+            wv[c] = w * tj;
+        }
+        __syncthreads();
+        const int rows = n - j, cols = m - j - 1;
+        for (int q = tid; q < rows * cols; q += TG_THREADS) {
+            const int i = j + q / cols, c = j + 1 + q % cols;
+            const double vi = i == j ? 1. : A[(size_t)i * m + j];
+            A[(size_t)i * m + c] -= wv[c] * vi;
+        }
+        __syncthreads();
+    }
+    if (Rout)
+        for (int q = tid; q < m * m; q += TG_THREADS) {
+            const int i = q / m, c = q % m;
+            Rout[q] = c >= i ? A[(size_t)i * m + c] : 0.;
+        }
+    // ---- form Q = H_0 ... H_{m-1} [I; 0]   (dorg2r) in W2 = W + 2m, then copy back ----
+    double *Q = W + 2 * (size_t)m;
+    __syncthreads();
+    for (int q = tid; q < n * m; q += TG_THREADS) Q[q] = (q / m == q % m) ? 1. : 0.;
+    __syncthreads();
+    for (int j = m - 1; j >= 0; --j) {
+        const double tj = taus[j];
+        for (int c = j + tid; c < m; c += TG_THREADS) {
+            double w = Q[(size_t)j * m + c];
+            for (int i = j + 1; i < n; ++i) w += A[(size_t)i * m + j] * Q[(size_t)i * m + c];
+            wv[c] = w * tj;
+        }
+        __syncthreads();
+        const int rows = n - j, cols = m - j;
+        for (int q = tid; q < rows * cols; q += TG_THREADS) {
+            const int i = j + q / cols, c = j + q % cols;
+            const double vi = i == j ? 1. : A[(size_t)i * m + j];
+            Q[(size_t)i * m + c] -= wv[c] * vi;
+        }
+        __syncthreads();
+    }
+    for (int q = tid; q < n * m; q += TG_THREADS) A[q] = Q[q];
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Benettin loop
+// ------------------------------------------------------------------------------------------------
+template <int RANK>
+__global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __grid_constant__ TgParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const long member = blockIdx.x;
+    const int n = T.n, m = P.m, tid = threadIdx.x, nm = n * m;
+    TgShared S = carve(smem_raw, T, P, member);
+    const long steps = P.n_pre + P.n_rec;
+    const long R = P.n_records;
+    // Y: macro (stored-trajectory) state; y: micro state of the tangent propagation
+    for (int r = tid; r < n; r += TG_THREADS) S.Y[r] = P.y[member * n + r];
+    for (int q = tid; q < nm; q += TG_THREADS) S.fm[q] = P.fm[member * nm + q];
+    for (int c = tid; c < m; c += TG_THREADS) S.rdiag[c] = P.r0 ? P.r0[((size_t)member * m + c) * m + c] : 0.;
+    if (tid == 0) S.xs[0] = 1.;
+    __syncthreads();
+    const size_t sbase = P.stored ? tile_base(member, n) : 0;
+    long iw = 0;
+    double mexp = 0.;  // thread c < m keeps the local exponent of vector c
+    for (long step = 0; step < steps; ++step) {
+        if (P.stored) {                                                   // lyapunov.py:513 / :527
+            const double *src = P.stored + (size_t)P.start_idx[step] * n * P.stored_ld + sbase;
+            for (int r = tid; r < n; r += TG_THREADS) S.Y[r] = src[(size_t)r * TILE];
+            __syncthreads();
+        }
+        if (step >= P.n_pre) {
+            const long ti = step - P.n_pre;
+            if (tid < m) mexp = log(fabs(S.rdiag[tid])) / P.dt_macro[step];   // :611 / :531
+            if (P.q_all) {
+                double *qa = P.q_all + ((size_t)member * (P.n_rec + 1) + ti) * nm;
+                for (int q = tid; q < nm; q += TG_THREADS) qa[q] = S.fm[q];
+            }
+            if (P.write_steps > 0 && ti % P.write_steps == 0) {
+                const long col = P.forward == 1 ? R - 1 - iw : iw;
+                double *ry = P.rec_y + ((size_t)col * P.n_members + member) * n;
+                double *rv = P.rec_fm + ((size_t)col * P.n_members + member) * nm;
+                double *re = P.rec_exp + ((size_t)col * P.n_members + member) * m;
+                for (int r = tid; r < n; r += TG_THREADS) ry[r] = S.Y[r];
+                for (int q = tid; q < nm; q += TG_THREADS) rv[q] = S.fm[q];
+                if (tid < m) re[tid] = mexp;
+                ++iw;
+            }
+        }
+        // propagate the basis over the micro steps starting from the stored point (:598-600)
+        for (int r = tid; r < n; r += TG_THREADS) S.y[r] = S.Y[r];
+        __syncthreads();
+        for (long q = P.sub_ptr[step]; q < P.sub_ptr[step + 1]; ++q) tg_step<RANK>(T, P, S, P.sub_dt[q]);
+        // q_new = prop @ q ; q, r = qr(q_new)   (:602-604) -- fm already holds prop @ q by linearity
+        block_qr(n, m, S.fm, S.kms, S.rdiag, S.red, P.r_all ? P.r_all + ((size_t)member * steps + step) * m * m : nullptr);
+        // next point of the stored trajectory (:601 / :622): one nonlinear step of length dt_macro
+        if (P.forward == 2) {
+            // Ginelli forward pass (lyapunov.py:1212-1218): the trajectory follows the micro-steps
+            for (int r = tid; r < n; r += TG_THREADS) S.Y[r] = S.y[r];
+            __syncthreads();
+        } else if (!P.stored) {
+            for (int r = tid; r < n; r += TG_THREADS) S.y[r] = S.Y[r];
+            __syncthreads();
+            nl_step<RANK>(T, P, S, P.dt_macro[step]);
+            for (int r = tid; r < n; r += TG_THREADS) S.Y[r] = S.y[r];
+            __syncthreads();
+        }
+    }
+    {
+        // final record (:628-630 / :548-550)
+        if (P.stored) {
+            const double *src = P.stored + (size_t)P.final_idx * n * P.stored_ld + sbase;
+            for (int r = tid; r < n; r += TG_THREADS) S.Y[r] = src[(size_t)r * TILE];
+            __syncthreads();
+        }
+        const long col = P.forward == 1 ? 0 : R - 1;
+        double *ry = P.rec_y + ((size_t)col * P.n_members + member) * n;
+        double *rv = P.rec_fm + ((size_t)col * P.n_members + member) * nm;
+        double *re = P.rec_exp + ((size_t)col * P.n_members + member) * m;
+        for (int r = tid; r < n; r += TG_THREADS) ry[r] = S.Y[r];
+        for (int q = tid; q < nm; q += TG_THREADS) rv[q] = S.fm[q];
+        if (tid < m) re[tid] = mexp;
+        if (P.q_all) {
+            double *qa = P.q_all + ((size_t)member * (P.n_rec + 1) + P.n_rec) * nm;
+            for (int q = tid; q < nm; q += TG_THREADS) qa[q] = S.fm[q];
+        }
+    }
+    for (int r = tid; r < n; r += TG_THREADS) P.y[member * n + r] = S.Y[r];
+    for (int q = tid; q < nm; q += TG_THREADS) P.fm[member * nm + q] = S.fm[q];
+}
+
+// (R, X) -> (X, R) with optional flip of the record axis
+__global__ void transpose_rec_kernel(const double *__restrict__ in, double *__restrict__ out, long R, long X,
+                                     int flip, long x_tiles)
+{
+    __shared__ double tile[32][33];
+    const long x0 = ((long)blockIdx.x % x_tiles) * 32;
+    const long r0 = ((long)blockIdx.x / x_tiles) * 32;
+    for (int q = threadIdx.y; q < 32; q += blockDim.y) {
+        const long r = r0 + q, x = x0 + threadIdx.x;
+        tile[q][threadIdx.x] = (r < R && x < X) ? in[r * X + x] : 0.;
+    }
+    __syncthreads();
+    for (int q = threadIdx.y; q < 32; q += blockDim.y) {
+        const long x = x0 + q, r = r0 + threadIdx.x;
+        if (x < X && r < R) out[x * R + (flip ? R - 1 - r : r)] = tile[threadIdx.x][q];
+    }
+}
+
+static void launch_transpose_rec(const double *d_in, double *d_out, long R, long X, int flip)
+{
+    const long x_tiles = (X + 31) / 32, r_tiles = (R + 31) / 32;
+    QGSB_REQUIRE(x_tiles * r_tiles < (1L << 31), "record buffer too large for one layout-change launch");
+    dim3 block(32, 8);
+    transpose_rec_kernel<<<(unsigned)(x_tiles * r_tiles), block, 0, ctx().stream>>>(d_in, d_out, R, X, flip, x_tiles);
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+}
+
+// per-variable sum and sum of squares over members (ensemble statistics)
+__global__ void moments_kernel(const double *__restrict__ y, long N, int n, double *__restrict__ out)
+{
+    const int i = blockIdx.x;
+    double s1 = 0., s2 = 0.;
+    for (long mbr = threadIdx.x; mbr < N; mbr += blockDim.x) {
+        const double v = y[tile_base(mbr, n) + (size_t)i * TILE];
+        s1 += v;
+        s2 += v * v;
+    }
+    __shared__ double sh1[256], sh2[256];
+    sh1[threadIdx.x] = s1;
+    sh2[threadIdx.x] = s2;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh1[threadIdx.x] += sh1[threadIdx.x + o];
+            sh2[threadIdx.x] += sh2[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[i] = sh1[0];
+        out[n + i] = sh2[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+static size_t tg_small_doubles(const qgsb_tensor *t, int m, int s)
+{
+    const int n = t->view.n;
+    return (size_t)(n + 1) + 2 * (size_t)n + (size_t)s * n + t->view.jac.npos + m + 64;
+}
+
+static void fill_common(TgParams &P, const Tableau &tab, long N, int m, int adjoint, double inverse)
+{
+    memset(&P, 0, sizeof(P));
+    P.n_members = N;
+    P.m = m;
+    P.s = tab.s;
+    P.adjoint = adjoint ? 1 : 0;
+    P.inverse = inverse;
+    for (int i = 0; i < tab.s; ++i) {
+        P.b[i] = tab.b[i];
+        for (int j = 0; j < tab.s; ++j) P.a[i * tab.s + j] = tab.a[(size_t)i * tab.s + j];
+    }
+}
+
+// decides shared vs global placement of the (s + 2) n m matrix block; returns dynamic smem bytes
+static size_t place_matrices(const qgsb_tensor *t, TgParams &P, DevBuf<double> &scratch, size_t extra_mats)
+{
+    const int n = t->view.n;
+    const size_t small = tg_small_doubles(t, P.m, P.s) * 8;
+    const size_t mats = ((size_t)(P.s + 2) * n * P.m + extra_mats) * 8;
+    QGSB_REQUIRE(small + 1024 <= ctx().smem_optin, "model too large for the tangent-linear kernel (%zu bytes of state)",
+                 small);
+    if (small + mats <= ctx().smem_optin) {
+        P.scratch = nullptr;
+        return small + mats;
+    }
+    P.scratch_per_member = mats / 8;
+    scratch.alloc(P.scratch_per_member * (size_t)P.n_members);
+    P.scratch = scratch.p;
+    return small;
+}
+
+template <typename K>
+static void set_smem_attr(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024)
+        QGSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+}  // namespace qgsb
+
+using namespace qgsb;
+
+extern "C" {
+
+int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long N, const double *ic, int m, const double *tg_ic, long n_steps,
+                           const double *dt, int s, const double *a, const double *b, const double *c,
+                           long write_steps, int time_direction, int adjoint, double inverse_sign, long R,
+                           double *traj, double *fmat, double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t && ic && tg_ic && traj && fmat, "null argument");
+    QGSB_REQUIRE(N >= 1 && m >= 1, "need at least one trajectory and one tangent vector");
+    QGSB_REQUIRE(n_steps >= 0 && write_steps >= 0, "negative step count");
+    QGSB_REQUIRE(t->jnnz_in > 0, "tensor handle has no Jacobian tensor");
+    QGSB_REQUIRE(time_direction == 1 || time_direction == -1, "time_direction must be +1 or -1");
+    ensure_init();
+    Context &cx = ctx();
+    cudaStream_t st = cx.stream;
+    const Tableau tab = make_tableau(s, a, b);
+    const int n = t->view.n;
+    const size_t nm = (size_t)n * m;
+    {
+        long L = n_steps + 1, r = write_steps == 0 ? 1 : (L + write_steps - 1) / write_steps;
+        if (write_steps > 0 && (r - 1) * write_steps != L - 1) r += 1;
+        QGSB_REQUIRE(R == r, "n_records %ld inconsistent with %ld steps / write_steps %ld", R, n_steps, write_steps);
+    }
+    DevBuf<double> d_y((size_t)N * n), d_fm((size_t)N * nm), d_dt(std::max<long>(n_steps, 1));
+    DevBuf<double> d_ry((size_t)R * N * n), d_rf((size_t)R * N * nm), d_oy((size_t)R * N * n), d_of((size_t)R * N * nm);
+    DevBuf<double> scratch;
+    d_y.upload(ic, (size_t)N * n, st);
+    d_fm.upload(tg_ic, (size_t)N * nm, st);
+    if (n_steps) d_dt.upload(dt, n_steps, st);
+    TgParams P;
+    fill_common(P, tab, N, m, adjoint, inverse_sign);
+    P.n_steps = n_steps;
+    P.dt = d_dt.p;
+    P.write_steps = write_steps;
+    P.n_records = R;
+    P.y = d_y.p;
+    P.fm = d_fm.p;
+    P.rec_y = d_ry.p;
+    P.rec_fm = d_rf.p;
+    const size_t bytes = place_matrices(t, P, scratch, 0);
+    QGSB_CUDA(cudaEventRecord(cx.ev0, st));
+    if (t->view.rank == 5) {
+        set_smem_attr(tgls_kernel<5>, bytes);
+        tgls_kernel<5><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
+    } else {
+        set_smem_attr(tgls_kernel<3>, bytes);
+        tgls_kernel<3><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
+    }
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+    QGSB_CUDA(cudaEventRecord(cx.ev1, st));
+    launch_transpose_rec(d_ry.p, d_oy.p, R, (long)N * n, time_direction == -1);
+    launch_transpose_rec(d_rf.p, d_of.p, R, (long)N * (long)nm, time_direction == -1);
+    d_oy.download(traj, (size_t)R * N * n, st);
+    d_of.download(fmat, (size_t)R * N * nm, st);
+    QGSB_CUDA(cudaStreamSynchronize(st));
+    if (device_ms) {
+        float ms = 0.f;
+        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+        *device_ms = ms;
+    }
+    QGSB_API_END
+}
+
+int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forward, int n_vec, const double *q0,
+                       const double *r0, long n_pre, long n_rec, const double *dt_macro, const long *sub_ptr,
+                       const double *sub_dt, int s, const double *a, const double *b, const double *c,
+                       long write_steps, int adjoint, double inverse_sign, long R, double *rec_traj,
+                       double *rec_exp, double *rec_vec, double *r_all, double *q_all, double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t && ic && q0 && dt_macro && sub_ptr && sub_dt && rec_traj && rec_exp && rec_vec, "null argument");
+    QGSB_REQUIRE(N >= 1, "need at least one trajectory");
+    QGSB_REQUIRE(forward >= 0 && forward <= 2, "mode must be 0 (BLV), 1 (FLV) or 2 (BLV following the micro-steps)");
+    QGSB_REQUIRE(n_vec >= 1 && n_vec <= t->view.n, "n_vec must be in 1..n_dim");
+    QGSB_REQUIRE(n_vec <= TG_THREADS, "n_vec larger than %d is not supported by the Benettin kernel", TG_THREADS);
+    QGSB_REQUIRE(n_pre >= 0 && n_rec >= 0 && write_steps >= 0, "negative step count");
+    QGSB_REQUIRE(t->jnnz_in > 0, "tensor handle has no Jacobian tensor");
+    ensure_init();
+    Context &cx = ctx();
+    cudaStream_t st = cx.stream;
+    const Tableau tab = make_tableau(s, a, b);
+    const int n = t->view.n, m = n_vec;
+    const size_t nm = (size_t)n * m;
+    const long steps = n_pre + n_rec;
+    {
+        long L = n_rec + 1, r = write_steps == 0 ? 1 : (L + write_steps - 1) / write_steps;
+        if (write_steps > 0 && (r - 1) * write_steps != L - 1) r += 1;
+        QGSB_REQUIRE(R == r, "n_records %ld inconsistent with %ld recorded steps / write_steps %ld", R, n_rec,
+                     write_steps);
+    }
+    const long n_sub = sub_ptr[steps];
+    DevBuf<double> d_y((size_t)N * n), d_q((size_t)N * nm), d_dtm(std::max<long>(steps, 1)), d_sub(std::max<long>(n_sub, 1));
+    DevBuf<long> d_ptr(steps + 1), d_idx(std::max<long>(steps, 1));
+    DevBuf<double> d_r0, d_rall, d_qall, d_stored, d_ys, scratch;
+    DevBuf<double> d_ry((size_t)R * N * n), d_rv((size_t)R * N * nm), d_re((size_t)R * N * m);
+    DevBuf<double> d_oy((size_t)R * N * n), d_ov((size_t)R * N * nm), d_oe((size_t)R * N * m);
+    d_y.upload(ic, (size_t)N * n, st);
+    d_q.upload(q0, (size_t)N * nm, st);
+    if (steps) d_dtm.upload(dt_macro, steps, st);
+    if (n_sub) d_sub.upload(sub_dt, n_sub, st);
+    QGSB_CUDA(cudaMemcpyAsync(d_ptr.p, sub_ptr, sizeof(long) * (steps + 1), cudaMemcpyHostToDevice, st));
+    TgParams P;
+    fill_common(P, tab, N, m, adjoint, inverse_sign);
+    P.forward = forward;
+    P.n_pre = n_pre;
+    P.n_rec = n_rec;
+    P.dt_macro = d_dtm.p;
+    P.sub_ptr = d_ptr.p;
+    P.sub_dt = d_sub.p;
+    P.write_steps = write_steps;
+    P.n_records = R;
+    P.y = d_y.p;
+    P.fm = d_q.p;
+    P.rec_y = d_ry.p;
+    P.rec_fm = d_rv.p;
+    P.rec_exp = d_re.p;
+    if (r0) {
+        d_r0.alloc((size_t)N * m * m);
+        d_r0.upload(r0, (size_t)N * m * m, st);
+        P.r0 = d_r0.p;
+    }
+    if (r_all) {
+        d_rall.alloc((size_t)N * std::max<long>(steps, 1) * m * m);
+        P.r_all = d_rall.p;
+    }
+    if (q_all) {
+        d_qall.alloc((size_t)N * (n_rec + 1) * nm);
+        P.q_all = d_qall.p;
+    }
+    QGSB_CUDA(cudaEventRecord(cx.ev0, st));
+    std::vector<long> idx;
+    if (forward == 1) {
+        // lyapunov.py:474: store the whole write_steps=1 trajectory, then walk it backwards.  The
+        // steps come in execution (backward) order with negative dt; the forward integration uses
+        // them reversed and positive.
+        const long ld = round_up(N, TILE);
+        std::vector<double> fdt(steps);
+        for (long q = 0; q < steps; ++q) fdt[q] = -dt_macro[steps - 1 - q];
+        DevBuf<double> d_fdt(std::max<long>(steps, 1)), d_state((size_t)n * ld);
+        if (steps) d_fdt.upload(fdt.data(), steps, st);
+        d_stored.alloc((size_t)(steps + 1) * n * ld);
+        launch_aos_to_soa(d_y.p, d_state.p, N, n, ld);
+        rk_advance(t, d_state.p, ld, N, steps, d_fdt.p, tab, 1, steps + 1, d_stored.p);
+        idx.resize(std::max<long>(steps, 1));
+        for (long q = 0; q < steps; ++q) idx[q] = steps - q;  // step q starts from point steps - q
+        QGSB_CUDA(cudaMemcpyAsync(d_idx.p, idx.data(), sizeof(long) * std::max<long>(steps, 1), cudaMemcpyHostToDevice, st));
+        P.stored = d_stored.p;
+        P.stored_ld = ld;
+        P.start_idx = d_idx.p;
+        P.final_idx = steps > 0 ? idx[steps - 1] : 0;   // lyapunov.py:549: y[0] of the last pass
+        QGSB_CUDA(cudaStreamSynchronize(st));           // fdt / idx host vectors must outlive the copies
+    }
+    const size_t bytes = place_matrices(t, P, scratch, 0);
+    if (t->view.rank == 5) {
+        set_smem_attr(lyap_kernel<5>, bytes);
+        lyap_kernel<5><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
+    } else {
+        set_smem_attr(lyap_kernel<3>, bytes);
+        lyap_kernel<3><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
+    }
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+    QGSB_CUDA(cudaEventRecord(cx.ev1, st));
+    launch_transpose_rec(d_ry.p, d_oy.p, R, (long)N * n, 0);
+    launch_transpose_rec(d_rv.p, d_ov.p, R, (long)N * (long)nm, 0);
+    launch_transpose_rec(d_re.p, d_oe.p, R, (long)N * m, 0);
+    d_oy.download(rec_traj, (size_t)R * N * n, st);
+    d_ov.download(rec_vec, (size_t)R * N * nm, st);
+    d_oe.download(rec_exp, (size_t)R * N * m, st);
+    if (r_all) d_rall.download(r_all, (size_t)N * steps * m * m, st);
+    if (q_all) d_qall.download(q_all, (size_t)N * (n_rec + 1) * nm, st);
+    QGSB_CUDA(cudaStreamSynchronize(st));
+    if (device_ms) {
+        float ms = 0.f;
+        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+        *device_ms = ms;
+    }
+    QGSB_API_END
+}
+
+int qgsb_ensemble_moments(qgsb_ensemble *e, double *sum, double *sumsq)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(e && sum && sumsq, "null argument");
+    ensure_init();
+    const int n = e->tensor->view.n;
+    DevBuf<double> d_out((size_t)2 * n);
+    moments_kernel<<<n, 256, 0, ctx().stream>>>(e->d_y.p, e->N, n, d_out.p);
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+    std::vector<double> h((size_t)2 * n);
+    d_out.download(h.data(), (size_t)2 * n, ctx().stream);
+    QGSB_CUDA(cudaStreamSynchronize(ctx().stream));
+    memcpy(sum, h.data(), sizeof(double) * n);
+    memcpy(sumsq, h.data() + n, sizeof(double) * n);
+    QGSB_API_END
+}
+
+}  // extern "C"
