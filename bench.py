@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- ensemble RK4 member-steps/s, MAOOAM-36 (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One bench "step" = one pass of the hot path over one batch: every rank integrates its shard of
+MEMBERS_PER_GPU MAOOAM-36 members (qgs_maooam.py parameters, tests/golden/tensor_maooam36.npz) over
+STEPS_PER_LAUNCH classic-RK4 time steps of dt = 0.1 with write_steps = 0 -- one fused kernel launch.
+
+  value     device-timed (CUDA events on the launching stream) whole-job member-steps/s with the
+            ensemble already resident in HBM; max over ranks of the summed launch times.
+  e2e       the same work through the reference-facing call (qgsb_rk_integrate == what
+            RungeKuttaIntegrator.integrate()/get_trajectories() run) with PINNED HOST buffers: the
+            host->device copy of the initial conditions and the device->host copy of the final states
+            are inside the timed region, every step.
+  roofline  FP64: algorithmic flops (4132 per member-step) / launch time against the
+            DFMA peak measured on this device in this run (MEASURED_PEAKS.json has no FP64 entry).
+  cpu_baseline  the CPU oracle port (oracle/qgs_oracle.c, all host threads) on a bounded sample.
+
+--impl reference times the CPU implementation of the path (the oracle port of the reference's
+_integrate_runge_kutta_jit + worker pool; the Python reference itself cannot travel to the GPU box).
+Under torchrun rank 0 alone runs it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "ensemble RK4 member-steps/sec, MAOOAM-36"
+UNIT = "member-steps/s"
+MEMBERS_PER_GPU = 1 << 20
+STEPS_PER_LAUNCH = 1000
+DT = 0.1
+NDIM = 36
+FLOPS_PER_MEMBER_STEP = 4132          # 4 * sum_nnz(p + 1) + 14 * ndim, SURVEY.md section 8d
+TENSOR = os.path.join(REPO, "tests", "golden", "tensor_maooam36.npz")
+
+
+def workload_config(n_gpus):
+    return {"workload": "MAOOAM-36 (qgs_maooam.py parameters, nnz 351), %d members/GPU x %d classic-RK4 steps per "
+                        "launch, dt=0.1, write_steps=0" % (MEMBERS_PER_GPU, STEPS_PER_LAUNCH),
+            "members_per_gpu": MEMBERS_PER_GPU, "steps_per_launch": STEPS_PER_LAUNCH, "n_dim": NDIM,
+            "parallelism": "members sharded over %d GPU(s), no inter-GPU traffic during integration" % n_gpus,
+            "l2": "ensemble state 302 MB per GPU > 126 MB L2 (inputs larger than L2)"}
+
+
+def initial_conditions(rank, members):
+    rng = np.random.default_rng(21217 + rank)
+    return rng.random((members, NDIM)) * 0.01
+
+
+def time_vector(steps):
+    return np.concatenate((np.arange(0., steps * DT, DT), np.full((1,), steps * DT)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples in the upper half of the power range seen
+        thr = 0.5 * (min(power) + max(power))
+        loaded = [s for s, p in zip(sm, power) if p >= thr] or sm
+        return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(power)), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_rate(target_seconds=12.0):
+    target_seconds = float(os.environ.get("QGSB_BENCH_CPU_SECONDS", target_seconds))
+    """member-steps/s of the CPU port with all host threads on a bounded sample of the same workload."""
+    import oracle
+    T = oracle.Tensor.from_npz(TENSOR)
+    b, c, a = oracle.rk4_tableau()
+    cores = os.cpu_count() or 1
+    oracle.set_num_threads(cores)
+    time_v = time_vector(STEPS_PER_LAUNCH)
+    probe = initial_conditions(0, 512)
+    t0 = time.perf_counter()
+    oracle.integrate_runge_kutta_jit(T, time_v, probe, 1, 0, b, c, a)       # warm-up + calibration
+    est = 512 * STEPS_PER_LAUNCH / (time.perf_counter() - t0)
+    members = int(min(max(est * target_seconds / STEPS_PER_LAUNCH // 1024 * 1024, 1024), 1 << 18))
+    ic = initial_conditions(0, members)
+    t0 = time.perf_counter()
+    oracle.integrate_runge_kutta_jit(T, time_v, ic, 1, 0, b, c, a)
+    wall = time.perf_counter() - t0
+    return {"value": members * STEPS_PER_LAUNCH / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d members x %d RK4 steps (write_steps=0), oracle/qgs_oracle.c with %d pthreads, %.1f s wall"
+                      % (members, STEPS_PER_LAUNCH, cores, wall)}, members, wall
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    rates, walls = [], []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base, members, wall = cpu_rate(target_seconds=6.0)
+        if i >= args.warmup:
+            rates.append(base["value"])
+            walls.append(wall)
+    value = float(np.mean(rates))
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(walls) * 1e3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus), "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import ctypes
+    import torch
+    from qgs_b200 import _lib
+    from qgs_b200.functions.tendencies import tendencies_from_tensor
+    from qgs_b200.integrators.integrate import rk4_tableau, directed_dt
+
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.init(local_rank)
+    lib = _lib.load()
+
+    z = np.load(TENSOR)
+    f, _ = tendencies_from_tensor(int(z["ndim"]), z["coo"], z["val"], z["jcoo"], z["jval"])
+    if f.tensor.kernel_kind != 2:
+        raise RuntimeError("the MAOOAM-36 specialised kernels are not linked into libqgsb.so")
+    b, c, a = rk4_tableau()
+    time_v = time_vector(STEPS_PER_LAUNCH)
+    dt = directed_dt(time_v, 1)
+    n_steps = len(dt)
+    members = MEMBERS_PER_GPU
+
+    # pinned host buffers for the end-to-end leg
+    ic_host = torch.empty((members, NDIM), dtype=torch.float64).pin_memory()
+    out_host = torch.empty((members, NDIM, 1), dtype=torch.float64).pin_memory()
+    ic_np, out_np = ic_host.numpy(), out_host.numpy()
+    ic_np[:] = initial_conditions(rank, members)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        _lib.check(lib.qgsb_synchronize())
+
+    # ---- resident leg: `value` ----
+    ens = ctypes.c_void_p()
+    _lib.check(lib.qgsb_ensemble_create(f.tensor.handle, members, ctypes.byref(ens)))
+    _lib.check(lib.qgsb_ensemble_upload(ens, _lib.dptr(ic_np)))
+    ms = ctypes.c_double()
+
+    def launch():
+        _lib.check(lib.qgsb_ensemble_integrate(ens, n_steps, _lib.dptr(dt), 4, _lib.dptr(a), _lib.dptr(b),
+                                               _lib.dptr(c), ctypes.byref(ms)))
+        return ms.value
+
+    for _ in range(args.warmup):
+        launch()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    t_wall = time.perf_counter()
+    dev_ms = [launch() for _ in range(args.steps)]
+    barrier()
+    wall_s = time.perf_counter() - t_wall
+    n_launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(sum(dev_ms))
+
+    # ---- end-to-end leg through the reference-facing C ABI with host buffers ----
+    def e2e_call():
+        _lib.check(lib.qgsb_rk_integrate(f.tensor.handle, members, _lib.dptr(ic_np), n_steps, _lib.dptr(dt), 4,
+                                         _lib.dptr(a), _lib.dptr(b), _lib.dptr(c), 0, 1, 1, _lib.dptr(out_np), None))
+
+    for _ in range(min(args.warmup, 3)):
+        e2e_call()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_call()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- ensemble statistics: the one place the path has an exchange step (NCCL all-reduce of 2n sums) ----
+    s1 = np.empty(NDIM)
+    s2 = np.empty(NDIM)
+    _lib.check(lib.qgsb_ensemble_moments(ens, _lib.dptr(s1), _lib.dptr(s2)))
+    moments = torch.from_numpy(np.concatenate((s1, s2))).cuda()
+    if dist is not None:
+        dist.all_reduce(moments)
+        worst = torch.tensor([total_ms, e2e_s, wall_s], dtype=torch.float64).cuda()
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s, wall_s = [float(v) for v in worst.cpu()]
+    mean = (moments[:NDIM] / (members * world)).cpu().numpy()
+    finite = bool(np.all(np.isfinite(mean)))
+    lib.qgsb_ensemble_destroy(ens)
+
+    if rank == 0:
+        member_steps = float(members) * n_steps * args.steps * world
+        value = member_steps / (total_ms * 1e-3)
+        peak = _lib.fp64_peak()
+        ach = FLOPS_PER_MEMBER_STEP * float(members) * n_steps / (total_ms / args.steps * 1e-3) / 1e12
+        traffic = None
+        prof = os.path.join(REPO, "profiles", "r01_rk_chain_ncu_200steps.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except (ValueError, OSError):
+                traffic = None
+        base, _, _ = cpu_rate()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(world),
+                "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                             "traffic": traffic,
+                             "peak_source": "DFMA micro-benchmark measured on this device in this run "
+                                            "(qgsb_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                             "flops_per_member_step": FLOPS_PER_MEMBER_STEP, "kernel": "rk_chain_kernel (maooam36)"},
+                "cpu_baseline": base,
+                "e2e": {"value": member_steps / e2e_s, "unit": UNIT,
+                        "h2d_bytes_per_step": members * NDIM * 8 + n_steps * 8,
+                        "d2h_bytes_per_step": members * NDIM * 8,
+                        "call": "qgsb_rk_integrate (C ABI behind RungeKuttaIntegrator.integrate), pinned host buffers"},
+                "gpu_launches": int(n_launches), "clocks": clocks,
+                "wall_s_timed_region": wall_s, "ensemble_mean_finite": finite}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    if world == 1 and args.gpus > 1:
+        # not under torchrun: launch one rank per GPU ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"),
+               os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
+               "--warmup", str(args.warmup)]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,9 @@ QGSB_API void qgsb_tensor_destroy(qgsb_tensor *t);
  * tensor_hash: FNV-1a over (ndim, rank, nnz, row-sorted coo, values), the key of a specialised module. */
 QGSB_API int qgsb_tensor_info(const qgsb_tensor *t, int *ndim, int *rank, long *nnz, long *jnnz, int *kernel_kind,
                      uint64_t *tensor_hash);
+/* Host-only: the key qgsb_tensor_info reports, computed without touching the device (coo is sorted by
+ * row internally).  Mirrors qgs_b200.codegen.tensor_hash. */
+QGSB_API int qgsb_tensor_hash(int ndim, int rank, long nnz, const int32_t *coo, const double *val, uint64_t *hash);
 /* Forbid / allow the tensor-specialised kernels for this handle (testing and benchmarking). */
 QGSB_API int qgsb_tensor_use_specialised(qgsb_tensor *t, int enable);
 

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -97,6 +98,39 @@ struct DevBuf {
     }
     void release() {
         if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void upload(const T *h, size_t count, cudaStream_t s) {
+        QGSB_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T *h, size_t count, cudaStream_t s) const {
+        QGSB_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+};
+
+// Scratch buffer drawn from a grow-only pool owned by the context: the host-buffer entry points
+// run many times with the same sizes (one integrate() per chunk of a long run), and cudaMalloc /
+// cudaFree of hundreds of MB per call would dominate their end-to-end time.
+void *pool_acquire(size_t bytes);
+void pool_release(void *p);
+void pool_trim();
+template <typename T>
+struct PoolBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    PoolBuf() {}
+    explicit PoolBuf(size_t count) { alloc(count); }
+    PoolBuf(const PoolBuf &) = delete;
+    PoolBuf &operator=(const PoolBuf &) = delete;
+    ~PoolBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        p = (T *)pool_acquire(std::max<size_t>(count, 1) * sizeof(T));
+    }
+    void release() {
+        if (p) pool_release(p);
         p = nullptr;
         n = 0;
     }

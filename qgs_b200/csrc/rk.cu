@@ -439,15 +439,24 @@ int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_ste
     const Tableau tab = make_tableau(s, a, b);
     const int n = t->view.n;
     const long ld = round_up(N, TILE);
-    DevBuf<double> d_ic((size_t)N * n), d_y((size_t)n * ld), d_dt(std::max<long>(n_steps, 1));
-    DevBuf<double> d_rec((size_t)R * n * ld), d_out((size_t)N * n * R);
+    PoolBuf<double> d_ic((size_t)N * n), d_y((size_t)n * ld), d_dt(std::max<long>(n_steps, 1));
+    PoolBuf<double> d_rec, d_out((size_t)N * n * R);
     d_ic.upload(ic, (size_t)N * n, st);
     if (n_steps) d_dt.upload(dt, n_steps, st);
     launch_aos_to_soa(d_ic.p, d_y.p, N, n, ld);
-    QGSB_CUDA(cudaEventRecord(cx.ev0, st));
-    rk_advance(t, d_y.p, ld, N, n_steps, d_dt.p, tab, write_steps, R, d_rec.p);
-    QGSB_CUDA(cudaEventRecord(cx.ev1, st));
-    launch_rec_to_api(d_rec.p, d_out.p, N, n, R, ld, time_direction == -1);
+    if (R == 1) {
+        // write_steps == 0 (or a single time point): only the end state is returned (integrate.py:221)
+        QGSB_CUDA(cudaEventRecord(cx.ev0, st));
+        rk_advance(t, d_y.p, ld, N, n_steps, d_dt.p, tab, 0, 1, nullptr);
+        QGSB_CUDA(cudaEventRecord(cx.ev1, st));
+        launch_soa_to_aos(d_y.p, d_out.p, N, n, ld);
+    } else {
+        d_rec.alloc((size_t)R * n * ld);
+        QGSB_CUDA(cudaEventRecord(cx.ev0, st));
+        rk_advance(t, d_y.p, ld, N, n_steps, d_dt.p, tab, write_steps, R, d_rec.p);
+        QGSB_CUDA(cudaEventRecord(cx.ev1, st));
+        launch_rec_to_api(d_rec.p, d_out.p, N, n, R, ld, time_direction == -1);
+    }
     d_out.download(traj, (size_t)N * n * R, st);
     QGSB_CUDA(cudaStreamSynchronize(st));
     if (device_ms) {

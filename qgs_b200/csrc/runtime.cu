@@ -66,6 +66,67 @@ static void init_device(int device)
     c.ready = true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// scratch pool
+// ------------------------------------------------------------------------------------------------
+struct PoolBlock {
+    void *p;
+    size_t bytes;
+    bool used;
+};
+static std::vector<PoolBlock> &pool()
+{
+    static std::vector<PoolBlock> blocks;
+    return blocks;
+}
+
+void pool_trim()
+{
+    auto &b = pool();
+    for (size_t i = 0; i < b.size();) {
+        if (!b[i].used) {
+            cudaFree(b[i].p);
+            b.erase(b.begin() + i);
+        } else {
+            ++i;
+        }
+    }
+}
+
+void *pool_acquire(size_t bytes)
+{
+    auto &b = pool();
+    int best = -1;
+    for (size_t i = 0; i < b.size(); ++i)
+        if (!b[i].used && b[i].bytes >= bytes && (best < 0 || b[i].bytes < b[best].bytes)) best = (int)i;
+    if (best >= 0 && b[best].bytes <= 2 * bytes + (1 << 20)) {
+        b[best].used = true;
+        return b[best].p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_trim();  // give cached blocks back and retry once
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        throw Failure();
+    }
+    b.push_back({p, bytes, true});
+    return p;
+}
+
+void pool_release(void *p)
+{
+    for (auto &blk : pool())
+        if (blk.p == p) {
+            blk.used = false;
+            return;
+        }
+}
+
 void ensure_init()
 {
     if (!ctx().ready) init_device(-1);
@@ -388,6 +449,7 @@ void qgsb_shutdown(void)
     if (!c.ready) return;
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
+    pool_trim();
     cudaStreamDestroy(c.own_stream);
     cudaEventDestroy(c.ev0);
     cudaEventDestroy(c.ev1);
@@ -483,6 +545,15 @@ int qgsb_tensor_create(int ndim, int rank, long nnz, const int32_t *coo, const d
     t->spec = find_spec(t->hash);
     if (t->spec && (t->spec->n != ndim || t->spec->rank != rank || t->spec->nnz != (int)nnz)) t->spec = nullptr;
     *out = t;
+    QGSB_API_END
+}
+
+int qgsb_tensor_hash(int ndim, int rank, long nnz, const int32_t *coo, const double *val, uint64_t *hash)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(hash != nullptr, "null output");
+    HostTensor h = prepare_vec(ndim + 1, rank, nnz, coo, val);
+    *hash = tensor_hash(ndim, rank, nnz, h.coo_sorted.data(), h.val_sorted.data());
     QGSB_API_END
 }
 

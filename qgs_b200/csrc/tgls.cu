@@ -538,8 +538,8 @@ int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long N, const double *ic, int m
         if (write_steps > 0 && (r - 1) * write_steps != L - 1) r += 1;
         QGSB_REQUIRE(R == r, "n_records %ld inconsistent with %ld steps / write_steps %ld", R, n_steps, write_steps);
     }
-    DevBuf<double> d_y((size_t)N * n), d_fm((size_t)N * nm), d_dt(std::max<long>(n_steps, 1));
-    DevBuf<double> d_ry((size_t)R * N * n), d_rf((size_t)R * N * nm), d_oy((size_t)R * N * n), d_of((size_t)R * N * nm);
+    PoolBuf<double> d_y((size_t)N * n), d_fm((size_t)N * nm), d_dt(std::max<long>(n_steps, 1));
+    PoolBuf<double> d_ry((size_t)R * N * n), d_rf((size_t)R * N * nm), d_oy((size_t)R * N * n), d_of((size_t)R * N * nm);
     DevBuf<double> scratch;
     d_y.upload(ic, (size_t)N * n, st);
     d_fm.upload(tg_ic, (size_t)N * nm, st);

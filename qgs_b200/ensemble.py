@@ -1,0 +1,149 @@
+"""Device-resident ensembles, member sharding across ranks and ensemble statistics.
+
+Two callers sit either side of the integrate kernels in the reference and are the "next" rows of
+SURVEY.md section 8f:
+
+* the chunked-run idiom of ``qgs_maooam.py:115-136`` / ``RungeKuttaIntegrator.initialize``
+  (integrator.py:198-295) feeds the final state of one ``integrate(..., write_steps=0)`` call back as
+  the initial condition of the next; :class:`DeviceEnsemble` keeps that state in HBM between calls;
+* ``TrajectoriesStatistics.compute_stats`` (qgs/integrators/statistics.py:33-66) averages functions
+  of the trajectories over the ensemble; :meth:`DeviceEnsemble.moments` reduces the first two moments
+  on the device and, when the members are sharded over ranks (one process per GPU), sums the
+  ``2 * n_dim`` partial sums with one ``torch.distributed`` all-reduce -- the only collective of the
+  path (NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+Members are independent ODE solves (integrator.py:388-389): rank ``g`` of ``G`` owns the contiguous
+block ``shard_bounds(N, G, g)`` and nothing is exchanged during integration.
+"""
+import ctypes
+
+import numpy as np
+
+from qgs_b200 import _lib
+from qgs_b200.integrators.integrate import directed_dt, rk4_tableau, tensor_of
+
+
+def shard_bounds(n_traj, world_size, rank):
+    """Contiguous partition of the members: rank ``g`` gets ``[g * ceil(N/G), min(N, (g+1) * ceil(N/G)))``."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("bad rank %d / world size %d" % (rank, world_size))
+    per = -(-int(n_traj) // world_size)
+    lo = min(rank * per, n_traj)
+    hi = min(lo + per, n_traj)
+    return lo, hi
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return None
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def all_reduce_sums(local, device=None):
+    """Sum a small float64 vector over all ranks (no-op without an initialised process group)."""
+    dist = _dist()
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    if dist is None or dist.get_world_size() == 1:
+        return local
+    import torch
+    t = torch.from_numpy(local.copy())
+    if dist.get_backend() == "nccl":
+        t = t.cuda() if device is None else t.to(device)
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
+def combine_moments(local_sum, local_sumsq, local_count):
+    """Global mean and (population) variance per variable from per-rank partial sums."""
+    n = len(local_sum)
+    packed = np.concatenate((local_sum, local_sumsq, [float(local_count)]))
+    tot = all_reduce_sums(packed)
+    count = tot[-1]
+    mean = tot[:n] / count
+    var = np.maximum(tot[n:2 * n] / count - mean * mean, 0.)
+    return mean, var, int(round(count))
+
+
+def gather_states(local_states):
+    """All ranks' final states concatenated in rank order (the optional final gather of SURVEY.md section 8e)."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return local_states
+    import torch
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, np.ascontiguousarray(local_states))
+    return np.concatenate(parts, axis=0)
+
+
+class DeviceEnsemble(object):
+    """Ensemble state resident in HBM (tiled structure-of-arrays, see ``include/qgsb.h``).
+
+    ``f`` is a tendencies callable from ``create_tendencies``.  ``ic`` is ``(n_traj, n_dim)``; with
+    ``sharded=True`` and an initialised ``torch.distributed`` group only this rank's block of members
+    is uploaded.
+    """
+
+    def __init__(self, f, ic, sharded=False):
+        self.tensor = tensor_of(f)
+        ic = np.atleast_2d(np.asarray(ic, dtype=np.float64))
+        if ic.shape[1] != self.tensor.ndim:
+            raise ValueError("ic must have shape (n_traj, %d)" % self.tensor.ndim)
+        self.n_global = ic.shape[0]
+        self.lo, self.hi = 0, ic.shape[0]
+        dist = _dist()
+        if sharded and dist is not None:
+            self.lo, self.hi = shard_bounds(ic.shape[0], dist.get_world_size(), dist.get_rank())
+        local = _lib.f64(ic[self.lo:self.hi])
+        if local.shape[0] == 0:
+            raise ValueError("this rank received no members (fewer members than ranks)")
+        self.n_traj = local.shape[0]
+        self.n_dim = self.tensor.ndim
+        self.time = 0.
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.load().qgsb_ensemble_create(self.tensor.handle, self.n_traj, ctypes.byref(handle)))
+        self._handle = handle
+        _lib.check(_lib.load().qgsb_ensemble_upload(self._handle, _lib.dptr(local)))
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None:
+            try:
+                _lib.load().qgsb_ensemble_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def __del__(self):
+        self.close()
+
+    def integrate(self, t0, t, dt, forward=True, b=None, c=None, a=None):
+        """Advance every member from ``t0`` to ``t`` (``write_steps=0`` semantics) without leaving the device.
+        Returns the kernel time in milliseconds."""
+        if a is None and b is None and c is None:
+            b, c, a = rk4_tableau()
+        time = np.concatenate((np.arange(t0, t, dt), np.full((1,), t)))
+        steps = directed_dt(time, 1 if forward else -1)
+        b, c, a = _lib.f64(b), _lib.f64(c), _lib.f64(a)
+        ms = ctypes.c_double()
+        _lib.check(_lib.load().qgsb_ensemble_integrate(self._handle, len(steps), _lib.dptr(steps), len(b),
+                                                       _lib.dptr(a), _lib.dptr(b), _lib.dptr(c), ctypes.byref(ms)))
+        self.time = time[-1] if forward else time[0]
+        return ms.value
+
+    def states(self):
+        """This rank's members as a host array ``(n_local, n_dim)``."""
+        out = np.empty((self.n_traj, self.n_dim))
+        _lib.check(_lib.load().qgsb_ensemble_download(self._handle, _lib.dptr(out)))
+        return out
+
+    def local_sums(self):
+        s1, s2 = np.empty(self.n_dim), np.empty(self.n_dim)
+        _lib.check(_lib.load().qgsb_ensemble_moments(self._handle, _lib.dptr(s1), _lib.dptr(s2)))
+        return s1, s2
+
+    def moments(self):
+        """Ensemble mean and variance of every variable over ALL ranks' members."""
+        s1, s2 = self.local_sums()
+        mean, var, _ = combine_moments(s1, s2, self.n_traj)
+        return mean, var

