@@ -266,3 +266,28 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "member-steps/s" and line["value"] > 1e4
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_overlay_serves_hot_path_modules_and_leaves_the_rest_to_the_reference():
+    ref = os.environ.get("QGS_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "qgs")):
+        pytest.skip("reference checkout not available (GPU box)")
+    code = (
+        "import warnings; warnings.filterwarnings('ignore')\n"
+        "import qgs\n"
+        "from qgs.params.params import QgParams\n"
+        "from qgs.integrators.integrator import RungeKuttaIntegrator, RungeKuttaTglsIntegrator\n"
+        "from qgs.functions.tendencies import create_tendencies\n"
+        "from qgs.toolbox.lyapunov import LyapunovsEstimator, CovariantLyapunovsEstimator\n"
+        "from qgs.integrators.integrate import integrate_runge_kutta\n"
+        "from qgs.functions.sparse_mul import sparse_mul3\n"
+        "import qgs.functions.util as u, qgs.integrators.statistics as st\n"
+        "assert RungeKuttaIntegrator.__module__ == 'qgs_b200.integrators.integrator'\n"
+        "assert create_tendencies.__module__ == 'qgs_b200.functions.tendencies'\n"
+        "assert LyapunovsEstimator.__module__ == 'qgs_b200.toolbox.lyapunov'\n"
+        "assert QgParams.__module__ == 'qgs.params.params' and %r in u.__file__ and %r in st.__file__\n"
+        "assert st.RungeKuttaIntegrator is RungeKuttaIntegrator\n"
+        "print('overlay ok')\n" % (ref, ref))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(REPO, "overlay"), ref]))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and "overlay ok" in out.stdout, out.stderr[-2000:]
