@@ -286,7 +286,6 @@ def test_overlay_serves_hot_path_modules_and_leaves_the_rest_to_the_reference():
         "assert create_tendencies.__module__ == 'qgs_b200.functions.tendencies'\n"
         "assert LyapunovsEstimator.__module__ == 'qgs_b200.toolbox.lyapunov'\n"
         "assert QgParams.__module__ == 'qgs.params.params' and %r in u.__file__ and %r in st.__file__\n"
-        "assert st.RungeKuttaIntegrator is RungeKuttaIntegrator\n"
         "print('overlay ok')\n" % (ref, ref))
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(REPO, "overlay"), ref]))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
