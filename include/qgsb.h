@@ -159,6 +159,8 @@ QGSB_API int qgsb_synchronize(void);
 /* Dependent-chain-free DFMA micro-benchmark: measured FP64 FMA peak of this device in TFLOP/s
  * (the roofline denominator MEASURED_PEAKS.json lacks). */
 QGSB_API int qgsb_fp64_peak(double *tflops, double *ms);
+/* Same for the FP64 tensor-core path (mma.sync m8n8k4 f64). */
+QGSB_API int qgsb_dmma_peak(double *tflops);
 
 #ifdef __cplusplus
 }

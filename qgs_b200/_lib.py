@@ -70,6 +70,7 @@ _PROTOTYPES = {
     "qgsb_ensemble_ld": (ctypes.c_long, [ctypes.c_void_p]),
     "qgsb_synchronize": (ctypes.c_int, []),
     "qgsb_fp64_peak": (ctypes.c_int, [c_double_p, c_double_p]),
+    "qgsb_dmma_peak": (ctypes.c_int, [c_double_p]),
 }
 
 _lib = None
@@ -132,4 +133,10 @@ def launch_count():
 def fp64_peak():
     tf, ms = ctypes.c_double(), ctypes.c_double()
     check(load().qgsb_fp64_peak(ctypes.byref(tf), ctypes.byref(ms)))
+    return tf.value
+
+
+def dmma_peak():
+    tf = ctypes.c_double()
+    check(load().qgsb_dmma_peak(ctypes.byref(tf)))
     return tf.value

@@ -404,6 +404,29 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
     if (ssum == 12345.678) out[0] = ssum;  // never true: keeps the chains alive
 }
 
+// DMMA (mma.sync m8n8k4 f64) peak micro-benchmark: 8 independent accumulator tiles per warp
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double *out, int iters, double seed)
+{
+    double c[8][2];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        c[q][0] = seed + q;
+        c[q][1] = seed - q;
+    }
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 0.999999;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[q][0]), "+d"(c[q][1])
+                         : "d"(a), "d"(b));
+    }
+    double ssum = 0.;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ssum += c[q][0] + c[q][1];
+    if (ssum == 12345.678) out[0] = ssum;
+}
+
 }  // namespace qgsb
 
 using namespace qgsb;
@@ -573,6 +596,31 @@ int qgsb_ensemble_integrate_record(qgsb_ensemble *e, long n_steps, const double 
 
 void *qgsb_ensemble_device_ptr(qgsb_ensemble *e) { return e ? (void *)e->d_y.p : nullptr; }
 long qgsb_ensemble_ld(const qgsb_ensemble *e) { return e ? e->ld : 0; }
+
+int qgsb_dmma_peak(double *tflops)
+{
+    QGSB_API_BEGIN
+    ensure_init();
+    Context &cx = ctx();
+    DevBuf<double> d_out(1);
+    const int iters = 2048, blocks = cx.sm_count * 8, threads = 256;
+    dmma_peak_kernel<<<blocks, threads, 0, cx.stream>>>(d_out.p, 16, 1.0);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        QGSB_CUDA(cudaEventRecord(cx.ev0, cx.stream));
+        dmma_peak_kernel<<<blocks, threads, 0, cx.stream>>>(d_out.p, iters, 1.0 + rep);
+        QGSB_CUDA(cudaEventRecord(cx.ev1, cx.stream));
+        QGSB_CUDA(cudaEventSynchronize(cx.ev1));
+        float ms = 0.f;
+        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+        best = std::min(best, ms);
+    }
+    count_launch(6);
+    // one m8n8k4 mma = 8*8*4 FMA per warp
+    const double flops = 2.0 * 256.0 * 8.0 * (double)iters * (double)blocks * (threads / 32);
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    QGSB_API_END
+}
 
 int qgsb_fp64_peak(double *tflops, double *ms_out)
 {

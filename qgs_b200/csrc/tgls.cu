@@ -15,46 +15,9 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tgls_shared.cuh"
 
 namespace qgsb {
-
-constexpr int TG_THREADS = 128;
-
-struct TgParams {
-    long n_members;
-    int m;                 // tangent columns
-    int s;
-    int adjoint;
-    double inverse;
-    double a[16 * 16];
-    double b[16];
-    // --- plain TGLS integration (integrate.py:555-614) ---
-    long n_steps;
-    const double *dt;      // (n_steps)
-    long write_steps;
-    long n_records;
-    double *y;             // (N, n)     in: ic, out: end state
-    double *fm;            // (N, n, m)  in: tg_ic, out: end state
-    double *rec_y;         // (R, N, n) or null
-    double *rec_fm;        // (R, N, n, m) or null
-    // --- Benettin (lyapunov.py:471-632) ---
-    int forward;
-    long n_pre, n_rec;
-    const double *dt_macro;   // (n_pre + n_rec)
-    const long *sub_ptr;      // (n_pre + n_rec + 1)
-    const double *sub_dt;
-    const double *stored;     // forward mode: write_steps=1 trajectory, tiled SoA records; else null
-    long stored_ld;
-    const long *start_idx;    // forward mode: stored-trajectory index used by every step
-    long final_idx;
-    const double *r0;         // (N, m, m) or null
-    double *rec_exp;          // (R, N, m)
-    double *r_all;            // (N, steps, m, m) or null
-    double *q_all;            // (N, n_rec + 1, n, m) or null
-    // --- placement of the big matrices ---
-    double *scratch;          // global scratch when shared memory is too small, else null
-    size_t scratch_per_member;
-};
 
 struct TgShared {
     double *xs, *y, *Y, *K, *Jv, *rdiag, *red, *fm, *kms, *KM;
@@ -77,32 +40,6 @@ __device__ __forceinline__ TgShared carve(unsigned char *raw, const TensorView &
     S.kms = mat + (size_t)n * m;
     S.KM = mat + (size_t)2 * n * m;
     return S;
-}
-
-template <int RANK>
-__device__ __forceinline__ double f_row(const TensorView &T, int i, const double *xs)
-{
-    double acc = 0.;
-    for (int e = T.row_ptr[i]; e < T.row_ptr[i + 1]; ++e) {
-        const Entry en = T.ent[e];
-        double p = xs[en.jk & 0xffffu] * xs[en.jk >> 16];
-        if (RANK == 5) p = p * xs[en.lm & 0xffffu] * xs[en.lm >> 16];
-        acc += p * en.v;
-    }
-    return acc;
-}
-
-template <int RANK>
-__device__ __forceinline__ double jac_pos(const JacView &J, int p, const double *xs)
-{
-    double acc = 0.;
-    for (int e = J.pos_ptr[p]; e < J.pos_ptr[p + 1]; ++e) {
-        const Entry en = J.ent[e];
-        double q = xs[en.jk & 0xffffu];
-        if (RANK == 5) q = q * xs[en.jk >> 16] * xs[en.lm];
-        acc += q * en.v;
-    }
-    return acc;
 }
 
 // one explicit Runge-Kutta step of the nonlinear state only: S.y <- RK(S.y, dt)
@@ -240,8 +177,10 @@ __device__ void block_qr(int n, int m, double *A, double *W, double *rdiag, doub
     // (W is the stage-input buffer followed by the stage-derivative buffers, all free during the QR.)
     double *taus = W;
     double *wv = W + m;
+    // column dot products use 4 threads per column (rows strided by 4) and two shuffle steps
+    const int part = tid & 3, cslot = tid >> 2;           // TG_THREADS / 4 = 32 column slots per pass
     for (int j = 0; j < m; ++j) {
-        // ---- reflector for column j ----
+        // ---- reflector for column j (dgeqr2 / dlarfg) ----
         if (warp == 0) {
             double ss = 0.;
             for (int i = j + 1 + lane; i < n; i += 32) {
@@ -255,7 +194,7 @@ __device__ void block_qr(int n, int m, double *A, double *W, double *rdiag, doub
                 const double xnorm = sqrt(ss);
                 if (xnorm == 0.) {
                     red[0] = 0.;        // tau
-                    red[1] = 0.;        // scale (unused)
+                    red[1] = 0.;        // 1 / (alpha - beta)
                     red[2] = alpha;     // beta
                 } else {
                     const double beta = -copysign(hypot(alpha, xnorm), alpha);
@@ -267,46 +206,59 @@ __device__ void block_qr(int n, int m, double *A, double *W, double *rdiag, doub
         }
         __syncthreads();
         const double tj = red[0], scal = red[1], beta = red[2];
+        // ---- w_c = tau * (A[j][c] + scal * sum_{i>j} x_i A[i][c]) for the trailing columns (v = [1; scal x]) ----
+        for (int c0 = j + 1; c0 < m; c0 += TG_THREADS / 4) {
+            const int c = c0 + cslot;
+            double w = 0.;
+            if (c < m)
+                for (int i = j + 1 + part; i < n; i += 4) w += A[(size_t)i * m + j] * A[(size_t)i * m + c];
+            w += __shfl_xor_sync(0xffffffffu, w, 1);
+            w += __shfl_xor_sync(0xffffffffu, w, 2);
+            if (c < m && part == 0) wv[c] = tj * (A[(size_t)j * m + c] + scal * w);
+        }
+        __syncthreads();
+        // ---- A[:, c] -= w_c v for c > j; store v (scaled) and beta in column j ----
+        const int rows = n - j, cols = m - j;      // column slot 0 is column j itself
+        for (int q = tid; q < rows * cols; q += TG_THREADS) {
+            const int i = j + q / cols, c = j + q % cols;
+            if (c == j) {
+                if (i == j) {
+                    A[(size_t)j * m + j] = beta;
+                    rdiag[j] = beta;
+                    taus[j] = tj;
+                }
+            } else {
+                const double vi = i == j ? 1. : A[(size_t)i * m + j] * scal;
+                A[(size_t)i * m + c] -= wv[c] * vi;
+            }
+        }
+        __syncthreads();
+        // scaling of column j happens after every reader of the unscaled x is done
         if (tj != 0.)
             for (int i = j + 1 + tid; i < n; i += TG_THREADS) A[(size_t)i * m + j] *= scal;
-        __syncthreads();
-        if (tid == 0) {
-            A[(size_t)j * m + j] = beta;
-            rdiag[j] = beta;
-            taus[j] = tj;
-        }
-        // ---- apply H_j = I - tau v v^T to the trailing columns (v_j = 1) ----
-        // w_c = tau * (A[j][c] + sum_{i>j} v_i A[i][c]), one thread per trailing column
-        for (int c = j + 1 + tid; c < m; c += TG_THREADS) {
-            double w = A[(size_t)j * m + c];
-            for (int i = j + 1; i < n; ++i) w += A[(size_t)i * m + j] * A[(size_t)i * m + c];
-            wv[c] = w * tj;
-        }
-        __syncthreads();
-        const int rows = n - j, cols = m - j - 1;
-        for (int q = tid; q < rows * cols; q += TG_THREADS) {
-            const int i = j + q / cols, c = j + 1 + q % cols;
-            const double vi = i == j ? 1. : A[(size_t)i * m + j];
-            A[(size_t)i * m + c] -= wv[c] * vi;
-        }
-        __syncthreads();
+        // (the next iteration's first barrier orders this against later readers of column j: none before Q)
     }
+    __syncthreads();
     if (Rout)
         for (int q = tid; q < m * m; q += TG_THREADS) {
             const int i = q / m, c = q % m;
             Rout[q] = c >= i ? A[(size_t)i * m + c] : 0.;
         }
-    // ---- form Q = H_0 ... H_{m-1} [I; 0]   (dorg2r) in W2 = W + 2m, then copy back ----
+    // ---- form Q = H_0 ... H_{m-1} [I; 0]   (dorg2r) in W[2m..), then copy back ----
     double *Q = W + 2 * (size_t)m;
-    __syncthreads();
     for (int q = tid; q < n * m; q += TG_THREADS) Q[q] = (q / m == q % m) ? 1. : 0.;
     __syncthreads();
     for (int j = m - 1; j >= 0; --j) {
         const double tj = taus[j];
-        for (int c = j + tid; c < m; c += TG_THREADS) {
-            double w = Q[(size_t)j * m + c];
-            for (int i = j + 1; i < n; ++i) w += A[(size_t)i * m + j] * Q[(size_t)i * m + c];
-            wv[c] = w * tj;
+        // columns c < j of Q are still those of the identity below row j: only c >= j change
+        for (int c0 = j; c0 < m; c0 += TG_THREADS / 4) {
+            const int c = c0 + cslot;
+            double w = 0.;
+            if (c < m)
+                for (int i = j + 1 + part; i < n; i += 4) w += A[(size_t)i * m + j] * Q[(size_t)i * m + c];
+            w += __shfl_xor_sync(0xffffffffu, w, 1);
+            w += __shfl_xor_sync(0xffffffffu, w, 2);
+            if (c < m && part == 0) wv[c] = tj * (Q[(size_t)j * m + c] + w);
         }
         __syncthreads();
         const int rows = n - j, cols = m - j;
@@ -554,16 +506,20 @@ int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long N, const double *ic, int m
     P.fm = d_fm.p;
     P.rec_y = d_ry.p;
     P.rec_fm = d_rf.p;
-    const size_t bytes = place_matrices(t, P, scratch, 0);
     QGSB_CUDA(cudaEventRecord(cx.ev0, st));
-    if (t->view.rank == 5) {
+    if (reg_tangent_supported(t, tab, m)) {
+        launch_reg_tangent(t, P, false);
+    } else if (t->view.rank == 5) {
+        const size_t bytes = place_matrices(t, P, scratch, 0);
         set_smem_attr(tgls_kernel<5>, bytes);
         tgls_kernel<5><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
+        count_launch();
     } else {
+        const size_t bytes = place_matrices(t, P, scratch, 0);
         set_smem_attr(tgls_kernel<3>, bytes);
         tgls_kernel<3><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
+        count_launch();
     }
-    count_launch();
     QGSB_CUDA(cudaGetLastError());
     QGSB_CUDA(cudaEventRecord(cx.ev1, st));
     launch_transpose_rec(d_ry.p, d_oy.p, R, (long)N * n, time_direction == -1);
@@ -669,15 +625,19 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
         P.final_idx = steps > 0 ? idx[steps - 1] : 0;   // lyapunov.py:549: y[0] of the last pass
         QGSB_CUDA(cudaStreamSynchronize(st));           // fdt / idx host vectors must outlive the copies
     }
-    const size_t bytes = place_matrices(t, P, scratch, 0);
-    if (t->view.rank == 5) {
+    if (reg_tangent_supported(t, tab, m)) {
+        launch_reg_tangent(t, P, true);
+    } else if (t->view.rank == 5) {
+        const size_t bytes = place_matrices(t, P, scratch, 0);
         set_smem_attr(lyap_kernel<5>, bytes);
         lyap_kernel<5><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
+        count_launch();
     } else {
+        const size_t bytes = place_matrices(t, P, scratch, 0);
         set_smem_attr(lyap_kernel<3>, bytes);
         lyap_kernel<3><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
+        count_launch();
     }
-    count_launch();
     QGSB_CUDA(cudaGetLastError());
     QGSB_CUDA(cudaEventRecord(cx.ev1, st));
     launch_transpose_rec(d_ry.p, d_oy.p, R, (long)N * n, 0);

@@ -1,0 +1,87 @@
+// tgls_shared.cuh -- declarations shared by the tangent-linear kernels (tgls.cu, tgls_reg.cu).
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace qgsb {
+
+constexpr int TG_THREADS = 128;
+
+struct TgParams {
+    long n_members;
+    int m;                 // tangent columns
+    int s;
+    int adjoint;
+    double inverse;
+    double a[16 * 16];
+    double b[16];
+    // --- plain TGLS integration (integrate.py:555-614) ---
+    long n_steps;
+    const double *dt;      // (n_steps)
+    long write_steps;
+    long n_records;
+    double *y;             // (N, n)     in: ic, out: end state
+    double *fm;            // (N, n, m)  in: tg_ic, out: end state
+    double *rec_y;         // (R, N, n) or null
+    double *rec_fm;        // (R, N, n, m) or null
+    // --- Benettin (lyapunov.py:471-632) ---
+    int forward;
+    long n_pre, n_rec;
+    const double *dt_macro;   // (n_pre + n_rec)
+    const long *sub_ptr;      // (n_pre + n_rec + 1)
+    const double *sub_dt;
+    const double *stored;     // forward mode: write_steps=1 trajectory, tiled SoA records; else null
+    long stored_ld;
+    const long *start_idx;    // forward mode: stored-trajectory index used by every step
+    long final_idx;
+    const double *r0;         // (N, m, m) or null
+    double *rec_exp;          // (R, N, m)
+    double *r_all;            // (N, steps, m, m) or null
+    double *q_all;            // (N, n_rec + 1, n, m) or null
+    // --- placement of the big matrices ---
+    double *scratch;          // global scratch when shared memory is too small, else null
+    size_t scratch_per_member;
+};
+
+template <int RANK>
+__device__ __forceinline__ double f_row(const TensorView &T, int i, const double *xs)
+{
+    double acc = 0.;
+    for (int e = T.row_ptr[i]; e < T.row_ptr[i + 1]; ++e) {
+        const Entry en = T.ent[e];
+        double p = xs[en.jk & 0xffffu] * xs[en.jk >> 16];
+        if (RANK == 5) p = p * xs[en.lm & 0xffffu] * xs[en.lm >> 16];
+        acc += p * en.v;
+    }
+    return acc;
+}
+
+template <int RANK>
+__device__ __forceinline__ double jac_pos(const JacView &J, int p, const double *xs)
+{
+    double acc = 0.;
+    for (int e = J.pos_ptr[p]; e < J.pos_ptr[p + 1]; ++e) {
+        const Entry en = J.ent[e];
+        double q = xs[en.jk & 0xffffu];
+        if (RANK == 5) q = q * xs[en.jk >> 16] * xs[en.lm];
+        acc += q * en.v;
+    }
+    return acc;
+}
+
+// run-time rank dispatch (the register kernels are templated on ndim only)
+__device__ __forceinline__ double f_row_rt(const TensorView &T, int i, const double *xs)
+{
+    return T.rank == 5 ? f_row<5>(T, i, xs) : f_row<3>(T, i, xs);
+}
+
+__device__ __forceinline__ double jac_pos_rt(const JacView &J, int rank, int p, const double *xs)
+{
+    return rank == 5 ? jac_pos<5>(J, p, xs) : jac_pos<3>(J, p, xs);
+}
+
+// register-resident kernels (tgls_reg.cu)
+bool reg_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m);
+void launch_reg_tangent(const qgsb_tensor *t, const TgParams &P, bool lyap);
+
+}  // namespace qgsb

@@ -1,0 +1,9 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from qgs_b200 import _lib
+from scripts.perf_probe2 import lyap, tgls
+_lib.init(0)
+if len(sys.argv) > 1 and sys.argv[1] == "tgls":
+    tgls("maooam36", 2048, 10)
+else:
+    lyap("maooam36", 2048, 4, 16)

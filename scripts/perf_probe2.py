@@ -88,7 +88,7 @@ def cpu_lyap(name, N, n_pre, n_rec):
           (name, N, n_pre + n_rec, w, N * (n_pre + n_rec) / w, oracle.num_threads()), flush=True)
 
 
-if __name__ == "__main__":
+def main():
     _lib.init(0)
     tgls("maooam36", 8192, 50)
     tgls("maooam36", 8192, 50, m=1)
@@ -101,3 +101,8 @@ if __name__ == "__main__":
     tgls("T4", 512, 5)
     tgls("atm6x6", 256, 3, m=16)
     cpu_lyap("maooam36", 64, 10, 40)
+    print("fp64 DFMA peak %.2f TFLOP/s, DMMA (mma.sync m8n8k4) peak %.2f TFLOP/s" % (_lib.fp64_peak(), _lib.dmma_peak()))
+
+
+if __name__ == "__main__":
+    main()

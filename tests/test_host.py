@@ -178,35 +178,57 @@ def test_codegen_hash_matches_library_and_modules_exist():
     assert codegen.emit_source("m", 36, 3, cs, vs)[2] < 480
 
 
+def _eval_generated_body(src, x):
+    """Run the generated straight-line F_BODY with Python floats (fma = a*b+c)."""
+    start = src.index("#define F_BODY")
+    lines = []
+    for ln in src[start:].splitlines()[1:]:
+        if not ln.rstrip().endswith("\\") and not ln.strip():
+            break
+        lines.append(ln.rstrip().rstrip("\\"))
+        if not ln.rstrip().endswith("\\"):
+            break
+    text = " ".join(lines)
+    text = re.sub(r"\((-?0x[0-9a-f.]+p[-+]\d+)\)", lambda m: repr(float.fromhex(m.group(1))), text)
+    text = re.sub(r"K\((\d+)\)", r"K[\1]", text)
+    text = text.replace("{", ";").replace("}", ";")
+    env = {"x": x, "fma": lambda a, b, c: a * b + c, "K": {}, "t": 0., "p2": 0., "p3": 0., "p4": 0.}
+    for stmt in text.split(";"):
+        stmt = stmt.strip()
+        if not stmt or stmt.startswith("ROW_DONE") or stmt.startswith("(void)"):
+            continue
+        if stmt.startswith("double "):
+            stmt = stmt[len("double "):]
+            if "=" not in stmt:
+                continue
+            for piece in stmt.split(","):
+                exec(piece.strip(), env)
+            continue
+        exec(stmt, env)
+    return env["K"]
+
+
 def test_generated_row_code_is_the_same_polynomial():
-    """Evaluate the generated straight-line code with Python floats against the plain COO loop."""
+    """Evaluate the generated straight-line code with Python floats against the plain COO loop (row mode for the
+    rank-3 tensors and dynT, monomial-sharing mode for T4)."""
     from qgs_b200 import codegen
-    import collections
     import math
-    for name in ("rp", "maooam36", "dynT"):
+    for name in ("rp", "maooam36", "dynT", "T4"):
         z = np.load(os.path.join(GOLDEN, "tensor_%s.npz" % name))
         n = int(z["ndim"])
         cs, vs = codegen.sort_by_row(z["coo"], z["val"])
-        rows = collections.defaultdict(list)
-        for c, v in zip(cs, vs):
-            if c[0] > 0:
-                rows[int(c[0])].append((tuple(int(j) for j in c[1:] if j != 0), float(v)))
+        src, _, _ = codegen.emit_source(name, n, int(z["rank"]), cs, vs)
         rng = np.random.default_rng(5)
         x = [1.] + list(rng.standard_normal(n))
+        K = _eval_generated_body(src, x)
+        ref = np.zeros(n + 1)
+        mag = np.zeros(n + 1)
+        for c, v in zip(cs, vs):
+            term = v * math.prod(x[j] for j in c[1:])
+            ref[c[0]] += term
+            mag[c[0]] += abs(term)
         for i in range(1, n + 1):
-            out = []
-            codegen._row_code(i, rows.get(i, []), out)
-            code = out[0]
-            body = code[code.index("(void)t;") + 8:code.index("ROW_DONE")]
-            env = {"x": x, "fma": lambda a, b, c: a * b + c, "k": 0., "t": 0.}
-            for stmt in body.split(";"):
-                stmt = stmt.strip()
-                if stmt:
-                    stmt = re.sub(r"\((-?0x[0-9a-f.]+p[-+]\d+)\)", lambda m: repr(float.fromhex(m.group(1))), stmt)
-                    exec(stmt, env)
-            ref = sum(v * math.prod(x[j] for j in f) for f, v in rows.get(i, []))
-            assert abs(env["k"] - ref) <= 1e-12 * max(1., sum(abs(v * math.prod(x[j] for j in f))
-                                                             for f, v in rows.get(i, []))), (name, i)
+            assert abs(K[i] - ref[i]) <= 1e-12 * max(1., mag[i]), (name, i, K[i], ref[i])
 
 
 # ---- sharding and the statistics collective (gloo, world_size 2) ---------------------------------------------
