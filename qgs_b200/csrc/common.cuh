@@ -194,6 +194,8 @@ struct qgsb_tensor {
     qgsb::DevBuf<int> d_row_ptr, d_pos_ptr, d_pos_i, d_pos_j, d_jrow_ptr, d_jcol_ptr, d_jcol_perm;
     const qgsb::SpecKernels *spec = nullptr;
     bool use_spec = true;
+    bool jac_matches_spec = false;       // every Jacobian position of this handle has a slot in spec->jac_slot_table
+    std::vector<int> h_pos_i, h_pos_j;   // host copy of the Jacobian positions
 };
 
 struct qgsb_ensemble {

@@ -144,6 +144,20 @@ static std::map<uint64_t, const SpecKernels *> &registry()
 
 void register_spec(const SpecKernels *k) { registry()[k->hash] = k; }
 
+// the specialised tangent kernels bake in the sparsity pattern of the Jacobian tensor the module was generated
+// with; a handle created with another jcoo must not use them
+static bool jacobian_matches(const qgsb_tensor *t)
+{
+    const SpecKernels *k = t->spec;
+    if (!k || !k->tangent || !k->jac_slot_table) return false;
+    const int n = t->view.n;
+    for (size_t p = 0; p < t->h_pos_i.size(); ++p) {
+        const int i = t->h_pos_i[p], j = t->h_pos_j[p];
+        if (i < 1 || j < 1 || i > n || j > n || k->jac_slot_table[(i - 1) * n + (j - 1)] < 0) return false;
+    }
+    return true;
+}
+
 const SpecKernels *find_spec(uint64_t hash)
 {
     auto it = registry().find(hash);
@@ -544,6 +558,9 @@ int qgsb_tensor_create(int ndim, int rank, long nnz, const int32_t *coo, const d
     t->val_sorted.swap(h.val_sorted);
     t->spec = find_spec(t->hash);
     if (t->spec && (t->spec->n != ndim || t->spec->rank != rank || t->spec->nnz != (int)nnz)) t->spec = nullptr;
+    t->h_pos_i = j.pos_i;
+    t->h_pos_j = j.pos_j;
+    t->jac_matches_spec = jacobian_matches(t);
     *out = t;
     QGSB_API_END
 }
@@ -586,6 +603,7 @@ int qgsb_tensor_use_specialised(qgsb_tensor *t, int enable)
     if (enable) {  // pick up modules registered after the handle was created (qgsb_load_plugin)
         const SpecKernels *k = find_spec(t->hash);
         if (k && k->n == t->view.n && k->rank == t->view.rank && k->nnz == (int)t->nnz_in) t->spec = k;
+        t->jac_matches_spec = jacobian_matches(t);
     }
     QGSB_API_END
 }

@@ -507,7 +507,9 @@ int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long N, const double *ic, int m
     P.rec_y = d_ry.p;
     P.rec_fm = d_rf.p;
     QGSB_CUDA(cudaEventRecord(cx.ev0, st));
-    if (reg_tangent_supported(t, tab, m)) {
+    if (pack_tangent_supported(t, tab, m)) {
+        launch_pack_tangent(t, P, false);
+    } else if (reg_tangent_supported(t, tab, m)) {
         launch_reg_tangent(t, P, false);
     } else if (t->view.rank == 5) {
         const size_t bytes = place_matrices(t, P, scratch, 0);
@@ -625,7 +627,9 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
         P.final_idx = steps > 0 ? idx[steps - 1] : 0;   // lyapunov.py:549: y[0] of the last pass
         QGSB_CUDA(cudaStreamSynchronize(st));           // fdt / idx host vectors must outlive the copies
     }
-    if (reg_tangent_supported(t, tab, m)) {
+    if (pack_tangent_supported(t, tab, m)) {
+        launch_pack_tangent(t, P, true);
+    } else if (reg_tangent_supported(t, tab, m)) {
         launch_reg_tangent(t, P, true);
     } else if (t->view.rank == 5) {
         const size_t bytes = place_matrices(t, P, scratch, 0);

@@ -1,0 +1,516 @@
+// tgls_pack.cuh -- "packed" tangent-linear / Benettin kernels for small bases (ndim <= ~40).
+//
+// Same arithmetic as tgls.cu (integrate.py:555-614, lyapunov.py:471-632), laid out for the FP64 pipe:
+//
+//  * a thread owns ONE COLUMN of the n x m tangent matrix of one member in registers (ndim is a
+//    template parameter, every register index is a literal);
+//  * a block packs G = floor(256 / m) members, so all lanes of (almost) every warp carry a column --
+//    a member is not tied to a warp or a block, only to m consecutive threads;
+//  * per Runge-Kutta stage the m threads of a member evaluate the tendencies and the values of the
+//    structurally non-zero Jacobian positions of THEIR member into shared memory, then every thread
+//    computes km[:, c] = +-J @ kms[:, c] reading J as broadcast LDS.128 (two positions per load).
+//    The product is a policy: `DenseProduct` walks a dense n x n matrix (any tensor), a generated
+//    module (qgs_b200/codegen.py) supplies the same product as straight-line code over the literal
+//    position list of one tensor (MAOOAM-36: 490 positions instead of 1296);
+//  * the Benettin re-orthonormalisation is a Householder QR with LAPACK's dgeqr2 / dorg2r sign
+//    conventions (so Q, R match np.linalg.qr) WITHOUT a serial phase: the owner of column j publishes
+//    its raw column, every later column thread forms the dot product with it AND its norm (so beta,
+//    tau and the scaling are computed redundantly by everybody, no second barrier), and the explicit
+//    Q is accumulated from the published reflectors with no barrier at all.
+//
+// Only "chain" tableaux (a_ij != 0 only for j = i-1: Euler, midpoint, Heun, classic RK4) take this
+// path; the generic kernels of tgls.cu serve everything else.
+#pragma once
+#include <cmath>
+
+#include "common.cuh"
+#include "tgls_shared.cuh"
+
+namespace qgsb {
+namespace pack {
+
+constexpr int MAX_THREADS = 256;
+
+// launch geometry decided on the host
+struct Geometry {
+    int G = 0;            // members per block
+    int threads = 0;      // G * m rounded up to a warp
+    int stride = 0;       // doubles of shared memory per member
+    int jv = 0;           // doubles reserved for the Jacobian values of one member
+    size_t smem = 0;      // dynamic shared memory per block, bytes
+};
+
+__host__ __device__ inline int even(int x) { return (x + 1) & ~1; }
+
+// per-member carve-up of shared memory (offsets in doubles, all even => 16-byte aligned)
+template <int N>
+struct Carve {
+    int jv, mp, nm;
+    __host__ __device__ Carve(int jv_, int m) : jv(even(jv_)), mp(even(m)), nm(even(N * m)) {}
+    __host__ __device__ int o_jv() const { return 0; }
+    __host__ __device__ int o_xs() const { return jv; }                 // N + 2 (xs[0] = 1)
+    __host__ __device__ int o_y() const { return o_xs() + even(N + 2); }
+    __host__ __device__ int o_Y() const { return o_y() + even(N); }
+    __host__ __device__ int o_kst() const { return o_Y() + even(N); }
+    __host__ __device__ int o_yacc() const { return o_kst() + even(N); }
+    __host__ __device__ int o_rdiag() const { return o_yacc() + even(N); }
+    __host__ __device__ int o_tau() const { return o_rdiag() + mp; }
+    __host__ __device__ int o_scal() const { return o_tau() + mp; }
+    __host__ __device__ int o_fm() const { return o_scal() + mp; }
+    __host__ __device__ int o_facc() const { return o_fm() + nm; }
+    __host__ __device__ int total() const
+    {
+        int t = o_facc() + nm;
+        // members of one warp read the same literal offset of their own J: keep their bases in
+        // different bank groups (stride = 2 mod 16 doubles)
+        while (t % 16 != 2) t += 2;
+        return t;
+    }
+};
+
+template <int N>
+struct Mem {
+    double *jv, *xs, *y, *Y, *kst, *yacc, *rdiag, *tau, *scal, *fm, *facc;
+    int m;
+};
+
+template <int N>
+__device__ __forceinline__ Mem<N> carve(double *base, int jv, int m)
+{
+    const Carve<N> c(jv, m);
+    Mem<N> S;
+    S.jv = base + c.o_jv();
+    S.xs = base + c.o_xs();
+    S.y = base + c.o_y();
+    S.Y = base + c.o_Y();
+    S.kst = base + c.o_kst();
+    S.yacc = base + c.o_yacc();
+    S.rdiag = base + c.o_rdiag();
+    S.tau = base + c.o_tau();
+    S.scal = base + c.o_scal();
+    S.fm = base + c.o_fm();
+    S.facc = base + c.o_facc();
+    S.m = m;
+    return S;
+}
+
+// ---- product policies ------------------------------------------------------------------------------------------
+// A policy provides
+//   JV              doubles of shared memory per member for the Jacobian values
+//   slot(i, j)      where the value of position (i, j) (1-based) goes inside that area
+//   apply(jv, col, km)   km = (J or J^T) @ col
+template <int N, bool ADJ>
+struct DenseProduct {
+    static constexpr int JV = N * N;
+    static constexpr bool kZeroFill = true;   // structural zeros must read as 0
+    __device__ static __forceinline__ int slot(int i, int j) { return (i - 1) * N + (j - 1); }
+    __device__ static __forceinline__ void apply(const double *jv, const double (&col)[N], double (&km)[N])
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) km[i] = 0.;
+        if (!ADJ) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double2 *row = reinterpret_cast<const double2 *>(jv + i * N);
+#pragma unroll
+                for (int j = 0; j < N / 2; ++j) {
+                    const double2 v = row[j];
+                    km[i] = fma(v.x, col[2 * j], km[i]);
+                    km[i] = fma(v.y, col[2 * j + 1], km[i]);
+                }
+                if (N & 1) km[i] = fma(jv[i * N + N - 1], col[N - 1], km[i]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double2 *row = reinterpret_cast<const double2 *>(jv + j * N);
+#pragma unroll
+                for (int i = 0; i < N / 2; ++i) {
+                    const double2 v = row[i];
+                    km[2 * i] = fma(v.x, col[j], km[2 * i]);
+                    km[2 * i + 1] = fma(v.y, col[j], km[2 * i + 1]);
+                }
+                if (N & 1) km[N - 1] = fma(jv[j * N + N - 1], col[j], km[N - 1]);
+            }
+        }
+    }
+};
+
+// ---- one step of the coupled system (chain tableau) -----------------------------------------------------------------
+// col[] holds fm[:, c] on entry and on exit; S.y advances by dt.  No barrier at the end: the caller
+// synchronises before anybody reads another thread's data.
+template <int N, class Prod>
+__device__ __forceinline__ void tangent_step(const TensorView &T, const TgParams &P, const Mem<N> &S, double dt,
+                                             double (&col)[N], int c, bool live)
+{
+    const int s = P.s, m = S.m;
+    const JacView &J = T.jac;
+    double km[N];
+    for (int st = 0; st < s; ++st) {
+        const double wa_in = st > 0 ? dt * P.a[st * s + st - 1] : 0.;       // (dt a[st]) @ k   integrate.py:216
+        const double wb = dt * P.b[st];
+        const double wa_out = st + 1 < s ? dt * P.a[(st + 1) * s + st] : 0.;
+        if (live)
+            for (int r = c; r < N; r += m) S.xs[r + 1] = st > 0 ? S.y[r] + wa_in * S.kst[r] : S.y[r];
+        __syncthreads();
+        if (live) {
+            for (int r = c; r < N; r += m) {
+                const double k = f_row_rt(T, r + 1, S.xs);
+                S.kst[r] = k;
+                S.yacc[r] = st == 0 ? wb * k : S.yacc[r] + wb * k;
+            }
+            for (int p = c; p < J.npos; p += m) S.jv[Prod::slot(J.pos_i[p], J.pos_j[p])] = jac_pos_rt(J, T.rank, p, S.xs);
+        }
+        __syncthreads();
+        if (live) {
+            // km = inverse * (J or J^T) @ col        integrate.py:601-603, boundary == 0
+            Prod::apply(S.jv, col, km);
+            double *fc = S.facc + c;
+            const double *fmc = S.fm + c;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double k = P.inverse * km[i];
+                const double f = st == 0 ? wb * k : fc[i * m] + wb * k;          // fm + sum dt b_j km_j  :605-607
+                fc[i * m] = f;
+                col[i] = fmc[i * m] + wa_out * k;                                // km_s of the next stage :598-600
+            }
+        }
+    }
+    if (live) {
+        for (int r = c; r < N; r += m) S.y[r] += S.yacc[r];
+        double *fmc = S.fm + c;
+        const double *fc = S.facc + c;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            col[i] = fmc[i * m] + fc[i * m];
+            fmc[i * m] = col[i];
+        }
+    }
+}
+
+// one nonlinear step of the macro ("stored") trajectory: S.Y <- RK(S.Y, dt)
+template <int N>
+__device__ __forceinline__ void nl_step(const TensorView &T, const TgParams &P, const Mem<N> &S, double dt, int c,
+                                        bool live)
+{
+    const int s = P.s, m = S.m;
+    for (int st = 0; st < s; ++st) {
+        const double wa_in = st > 0 ? dt * P.a[st * s + st - 1] : 0.;
+        const double wb = dt * P.b[st];
+        if (live)
+            for (int r = c; r < N; r += m) S.xs[r + 1] = st > 0 ? S.Y[r] + wa_in * S.kst[r] : S.Y[r];
+        __syncthreads();
+        if (live)
+            for (int r = c; r < N; r += m) {
+                const double k = f_row_rt(T, r + 1, S.xs);
+                S.kst[r] = k;
+                S.yacc[r] = st == 0 ? wb * k : S.yacc[r] + wb * k;
+            }
+        __syncthreads();
+    }
+    if (live)
+        for (int r = c; r < N; r += m) S.Y[r] += S.yacc[r];
+    __syncthreads();
+}
+
+// Householder QR of the n x m matrix whose column c lives in col[] of thread c of the member.  On exit col[]
+// holds Q[:, c] (also stored to S.fm), S.rdiag the diagonal of R, Rout (m x m row-major, may be null) all of R.
+// The reflectors are kept column-major in the facc area: V[j * N + i] = raw x_i of step j (i >= j); their LAPACK
+// scaling 1 / (alpha - beta) is kept apart in S.scal so that nobody rewrites a published column.
+template <int N>
+__device__ __forceinline__ void qr(const Mem<N> &S, int c, bool live, double (&col)[N], double *Rout)
+{
+    static_assert(N % 2 == 0, "rows are processed in aligned pairs");
+    const int m = S.m;
+    double *V = S.facc;
+    __syncthreads();                       // every thread is done with its private facc column
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        if (j < m) {                       // uniform
+            double *x = V + j * N;
+            if (live && c == j) {
+#pragma unroll
+                for (int i = j; i < N; ++i) x[i] = col[i];
+            }
+            __syncthreads();
+            if (live && c >= j) {
+                // dlarfg + dlarf: d = x . col_c and |x|^2 over the rows below the diagonal
+                double d0 = 0., d1 = 0., n0 = 0., n1 = 0.;
+#pragma unroll
+                for (int i = (j + 1) & ~1; i < N; i += 2) {       // rows in aligned pairs: one LDS.128 each
+                    const double2 xi = *reinterpret_cast<const double2 *>(x + i);
+                    if (i > j) {
+                        d0 = fma(xi.x, col[i], d0);
+                        n0 = fma(xi.x, xi.x, n0);
+                    }
+                    d1 = fma(xi.y, col[i + 1], d1);
+                    n1 = fma(xi.y, xi.y, n1);
+                }
+                const double alpha = x[j];
+                const double xnorm = sqrt(n0 + n1);
+                double beta = alpha, tau = 0., scal = 0.;
+                if (xnorm != 0.) {
+                    beta = -copysign(hypot(alpha, xnorm), alpha);
+                    tau = (beta - alpha) / beta;
+                    scal = 1. / (alpha - beta);
+                }
+                if (c == j) {
+                    col[j] = beta;
+                    S.rdiag[j] = beta;
+                    S.tau[j] = tau;
+                    S.scal[j] = scal;
+                } else {
+                    const double w = tau * fma(d0 + d1, scal, col[j]);
+                    col[j] -= w;
+                    const double ws = -(w * scal);
+#pragma unroll
+                    for (int i = (j + 1) & ~1; i < N; i += 2) {
+                        const double2 xi = *reinterpret_cast<const double2 *>(x + i);
+                        if (i > j) col[i] = fma(ws, xi.x, col[i]);
+                        col[i + 1] = fma(ws, xi.y, col[i + 1]);
+                    }
+                }
+                if (Rout != nullptr) Rout[j * m + c] = col[j];
+            }
+        }
+    }
+    if (Rout != nullptr && live)
+        for (int i = c + 1; i < m; ++i) Rout[i * m + c] = 0.;   // strictly lower part of column c
+    __syncthreads();                       // the last reflector, tau and scal are published
+    // dorg2r: Q[:, c] = H_0 ... H_{m-1} e_c; H_j e_c = e_c for j > c
+#pragma unroll
+    for (int i = 0; i < N; ++i) col[i] = i == c ? 1. : 0.;
+#pragma unroll
+    for (int jj = 0; jj < N; ++jj) {
+        const int j = N - 1 - jj;
+        if (j < m && live && j <= c) {
+            const double *x = V + j * N;
+            double d0 = 0., d1 = 0.;
+#pragma unroll
+            for (int i = (j + 1) & ~1; i < N; i += 2) {
+                const double2 xi = *reinterpret_cast<const double2 *>(x + i);
+                if (i > j) d0 = fma(xi.x, col[i], d0);
+                d1 = fma(xi.y, col[i + 1], d1);
+            }
+            const double scal = S.scal[j];
+            const double w = S.tau[j] * fma(d0 + d1, scal, col[j]);
+            col[j] -= w;
+            const double ws = -(w * scal);
+#pragma unroll
+            for (int i = (j + 1) & ~1; i < N; i += 2) {
+                const double2 xi = *reinterpret_cast<const double2 *>(x + i);
+                if (i > j) col[i] = fma(ws, xi.x, col[i]);
+                col[i + 1] = fma(ws, xi.y, col[i + 1]);
+            }
+        }
+    }
+    if (live) {
+        double *fmc = S.fm + c;
+#pragma unroll
+        for (int i = 0; i < N; ++i) fmc[i * m] = col[i];
+    }
+}
+
+template <int N, class Prod>
+__device__ __forceinline__ void init_member(const Mem<N> &S, int c, bool live)
+{
+    if (!live) return;
+    const int m = S.m;
+    if (Prod::kZeroFill)
+        for (int q = c; q < Prod::JV; q += m) S.jv[q] = 0.;
+    for (int r = c; r < N; r += m) {
+        S.kst[r] = 0.;
+        S.yacc[r] = 0.;
+    }
+    if (c == 0) S.xs[0] = 1.;
+}
+
+// ---- plain tangent-linear integration (integrate.py:555-614) ----------------------------------------------------------
+template <int N, class Prod>
+__global__ void __launch_bounds__(MAX_THREADS, 1)
+tgls_kernel(TensorView T, const __grid_constant__ TgParams P, int G, int stride)
+{
+    extern __shared__ __align__(16) double smem_pack[];
+    const int m = P.m, t = threadIdx.x;
+    const int g = t / m, c = t - g * m;
+    const long member = (long)blockIdx.x * G + g;
+    const bool live = g < G && member < P.n_members;
+    const Mem<N> S = carve<N>(smem_pack + (size_t)(live ? g : 0) * stride, Prod::JV, m);
+    const int nm = N * m;
+    double col[N];
+    init_member<N, Prod>(S, c, live);
+    if (live)
+        for (int r = c; r < N; r += m) S.y[r] = P.y[member * N + r];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        col[i] = live ? P.fm[member * nm + i * m + c] : 0.;
+        if (live) S.fm[i * m + c] = col[i];
+    }
+    __syncthreads();
+    long iw = 0;
+    for (long ti = 0; ti < P.n_steps; ++ti) {
+        if (P.rec_y && P.write_steps > 0 && ti % P.write_steps == 0) {
+            if (live) {
+                double *ry = P.rec_y + ((size_t)iw * P.n_members + member) * N;
+                double *rf = P.rec_fm + ((size_t)iw * P.n_members + member) * nm;
+                for (int r = c; r < N; r += m) ry[r] = S.y[r];
+#pragma unroll
+                for (int i = 0; i < N; ++i) rf[i * m + c] = col[i];
+            }
+            ++iw;
+        }
+        tangent_step<N, Prod>(T, P, S, P.dt[ti], col, c, live);
+        __syncthreads();
+    }
+    if (live) {
+        if (P.rec_y) {
+            double *ry = P.rec_y + ((size_t)(P.n_records - 1) * P.n_members + member) * N;
+            double *rf = P.rec_fm + ((size_t)(P.n_records - 1) * P.n_members + member) * nm;
+            for (int r = c; r < N; r += m) ry[r] = S.y[r];
+#pragma unroll
+            for (int i = 0; i < N; ++i) rf[i * m + c] = col[i];
+        }
+        for (int r = c; r < N; r += m) P.y[member * N + r] = S.y[r];
+#pragma unroll
+        for (int i = 0; i < N; ++i) P.fm[member * nm + i * m + c] = col[i];
+    }
+}
+
+// ---- Benettin loop (lyapunov.py:471-632) ---------------------------------------------------------------------------------
+template <int N, class Prod>
+__global__ void __launch_bounds__(MAX_THREADS, 1)
+lyap_kernel(TensorView T, const __grid_constant__ TgParams P, int G, int stride)
+{
+    extern __shared__ __align__(16) double smem_pack[];
+    const int m = P.m, t = threadIdx.x;
+    const int g = t / m, c = t - g * m;
+    const long member = (long)blockIdx.x * G + g;
+    const bool live = g < G && member < P.n_members;
+    const Mem<N> S = carve<N>(smem_pack + (size_t)(live ? g : 0) * stride, Prod::JV, m);
+    const int nm = N * m;
+    const long steps = P.n_pre + P.n_rec;
+    const long R = P.n_records;
+    double col[N];
+    init_member<N, Prod>(S, c, live);
+    if (live)
+        for (int r = c; r < N; r += m) S.Y[r] = P.y[member * N + r];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        col[i] = live ? P.fm[member * nm + i * m + c] : 0.;
+        if (live) S.fm[i * m + c] = col[i];
+    }
+    if (live) S.rdiag[c] = P.r0 ? P.r0[((size_t)member * m + c) * m + c] : 0.;
+    __syncthreads();
+    const size_t sbase = (P.stored && live) ? tile_base(member, N) : 0;
+    long iw = 0;
+    double mexp = 0.;
+    for (long step = 0; step < steps; ++step) {
+        if (P.stored) {                                                   // lyapunov.py:513 / :527
+            if (live) {
+                const double *src = P.stored + (size_t)P.start_idx[step] * N * P.stored_ld + sbase;
+                for (int r = c; r < N; r += m) S.Y[r] = src[(size_t)r * TILE];
+            }
+            __syncthreads();
+        }
+        if (step >= P.n_pre) {
+            const long ti = step - P.n_pre;
+            if (live) mexp = log(fabs(S.rdiag[c])) / P.dt_macro[step];   // :611 / :531
+            if (P.q_all && live) {
+                double *qa = P.q_all + ((size_t)member * (P.n_rec + 1) + ti) * nm;
+#pragma unroll
+                for (int i = 0; i < N; ++i) qa[i * m + c] = col[i];
+            }
+            if (P.write_steps > 0 && ti % P.write_steps == 0) {
+                if (live) {
+                    const long rc = P.forward == 1 ? R - 1 - iw : iw;
+                    double *ry = P.rec_y + ((size_t)rc * P.n_members + member) * N;
+                    double *rv = P.rec_fm + ((size_t)rc * P.n_members + member) * nm;
+                    double *re = P.rec_exp + ((size_t)rc * P.n_members + member) * m;
+                    for (int r = c; r < N; r += m) ry[r] = S.Y[r];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) rv[i * m + c] = col[i];
+                    re[c] = mexp;
+                }
+                ++iw;
+            }
+        }
+        // propagate the basis over the micro steps starting from the stored point (:598-600)
+        if (live)
+            for (int r = c; r < N; r += m) S.y[r] = S.Y[r];
+        const long q0 = P.sub_ptr[step], q1 = P.sub_ptr[step + 1];
+        for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, P, S, P.sub_dt[q], col, c, live);
+        // q, r = qr(prop @ q)   (:602-604)
+        qr<N>(S, c, live, col, (P.r_all && live) ? P.r_all + ((size_t)member * steps + step) * m * m : nullptr);
+        if (P.forward == 2 || (!P.stored && q1 - q0 == 1 && P.sub_dt[q0] == P.dt_macro[step])) {
+            // Ginelli forward pass follows the micro steps; and with a single micro step of the macro length the
+            // "stored" trajectory point (:601 / :622) is bit-for-bit the state the tangent step just produced
+            if (live)
+                for (int r = c; r < N; r += m) S.Y[r] = S.y[r];
+        } else if (!P.stored) {                           // next stored-trajectory point (:601 / :622)
+            nl_step<N>(T, P, S, P.dt_macro[step], c, live);
+        }
+    }
+    if (live) {
+        if (P.stored) {
+            const double *src = P.stored + (size_t)P.final_idx * N * P.stored_ld + sbase;
+            for (int r = c; r < N; r += m) S.Y[r] = src[(size_t)r * TILE];
+        }
+        const long rc = P.forward == 1 ? 0 : R - 1;                       // :628-630 / :548-550
+        double *ry = P.rec_y + ((size_t)rc * P.n_members + member) * N;
+        double *rv = P.rec_fm + ((size_t)rc * P.n_members + member) * nm;
+        double *re = P.rec_exp + ((size_t)rc * P.n_members + member) * m;
+        for (int r = c; r < N; r += m) ry[r] = S.Y[r];
+#pragma unroll
+        for (int i = 0; i < N; ++i) rv[i * m + c] = col[i];
+        re[c] = mexp;
+        if (P.q_all) {
+            double *qa = P.q_all + ((size_t)member * (P.n_rec + 1) + P.n_rec) * nm;
+#pragma unroll
+            for (int i = 0; i < N; ++i) qa[i * m + c] = col[i];
+        }
+        for (int r = c; r < N; r += m) P.y[member * N + r] = S.Y[r];
+#pragma unroll
+        for (int i = 0; i < N; ++i) P.fm[member * nm + i * m + c] = col[i];
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+template <int N>
+inline Geometry geometry(int jv, int m, size_t smem_limit)
+{
+    Geometry geo;
+    const Carve<N> c(jv, m);
+    geo.jv = jv;
+    geo.stride = c.total();
+    const size_t per_member = (size_t)geo.stride * sizeof(double);
+    int G = MAX_THREADS / m;
+    if ((size_t)G * per_member > smem_limit) G = (int)(smem_limit / per_member);
+    geo.G = G;
+    geo.threads = G > 0 ? ((G * m + 31) / 32) * 32 : 0;
+    geo.smem = (size_t)G * per_member;
+    return geo;
+}
+
+// launches the packed kernel for one policy pair; returns cudaErrorInvalidValue when it does not fit
+template <int N, class Fwd, class Adj>
+inline cudaError_t launch(const TensorView &T, const TgParams &P, bool lyap, size_t smem_limit, cudaStream_t stream)
+{
+    static_assert(Fwd::JV == Adj::JV, "both directions of a product share one Jacobian layout");
+    if (P.m < 1 || P.m > MAX_THREADS) return cudaErrorInvalidValue;
+    const Geometry geo = geometry<N>(Fwd::JV, P.m, smem_limit);
+    if (geo.G < 1) return cudaErrorInvalidValue;
+    const unsigned blocks = (unsigned)((P.n_members + geo.G - 1) / geo.G);
+    auto go = [&](auto kernel) -> cudaError_t {
+        if (geo.smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem);
+            if (e != cudaSuccess) return e;
+        }
+        kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, geo.G, geo.stride);
+        return cudaGetLastError();
+    };
+    if (lyap) return P.adjoint ? go(lyap_kernel<N, Adj>) : go(lyap_kernel<N, Fwd>);
+    return P.adjoint ? go(tgls_kernel<N, Adj>) : go(tgls_kernel<N, Fwd>);
+}
+
+}  // namespace pack
+}  // namespace qgsb

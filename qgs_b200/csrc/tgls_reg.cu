@@ -14,6 +14,7 @@
 // path; anything else -- and any ndim without an instantiation -- runs the generic kernels of tgls.cu.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -430,6 +431,8 @@ bool reg_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m)
 {
     const char *force = getenv("QGSB_TGLS_GENERIC");
     if (force && force[0] == '1') return false;
+    const char *which = getenv("QGSB_TGLS_KERNEL");
+    if (which && !strcmp(which, "generic")) return false;
     const int n = t->view.n;
     // measured on B200: below ~16 columns the shared-memory kernel of tgls.cu is faster (the register kernel always
     // pays for the dense n x n product per column thread and for two mostly idle warps)

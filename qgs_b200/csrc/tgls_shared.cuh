@@ -80,6 +80,10 @@ __device__ __forceinline__ double jac_pos_rt(const JacView &J, int rank, int p, 
     return rank == 5 ? jac_pos<5>(J, p, xs) : jac_pos<3>(J, p, xs);
 }
 
+// packed kernels (tgls_pack.cu / tgls_pack.cuh)
+bool pack_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m);
+void launch_pack_tangent(const qgsb_tensor *t, const TgParams &P, bool lyap);
+
 // register-resident kernels (tgls_reg.cu)
 bool reg_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m);
 void launch_reg_tangent(const qgsb_tensor *t, const TgParams &P, bool lyap);
