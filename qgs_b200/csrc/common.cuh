@@ -196,6 +196,12 @@ struct qgsb_tensor {
     bool use_spec = true;
     bool jac_matches_spec = false;       // every Jacobian position of this handle has a slot in spec->jac_slot_table
     std::vector<int> h_pos_i, h_pos_j;   // host copy of the Jacobian positions
+    std::vector<qgsb::Entry> h_ent, h_jent;          // host copies of the device entry lists
+    std::vector<int> h_row_ptr, h_pos_ptr;
+    // tables of the packed tangent kernels, built on first use: [0] dense product, [1] generated product
+    struct PackCache;
+    mutable PackCache *pack_cache[2] = {nullptr, nullptr};
+    ~qgsb_tensor();
 };
 
 struct qgsb_ensemble {

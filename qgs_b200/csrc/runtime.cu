@@ -560,6 +560,10 @@ int qgsb_tensor_create(int ndim, int rank, long nnz, const int32_t *coo, const d
     if (t->spec && (t->spec->n != ndim || t->spec->rank != rank || t->spec->nnz != (int)nnz)) t->spec = nullptr;
     t->h_pos_i = j.pos_i;
     t->h_pos_j = j.pos_j;
+    t->h_ent = h.ent;
+    t->h_row_ptr = h.row_ptr;
+    t->h_jent = j.ent;
+    t->h_pos_ptr = j.pos_ptr;
     t->jac_matches_spec = jacobian_matches(t);
     *out = t;
     QGSB_API_END

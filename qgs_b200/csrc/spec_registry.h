@@ -14,6 +14,7 @@ namespace qgsb {
 
 struct TensorView;   // common.cuh
 struct TgParams;     // tgls_shared.cuh
+struct PackTables;   // tgls_shared.cuh
 
 struct SpecKernels {
     uint64_t hash;  // FNV-1a over (ndim, rank, nnz, row-sorted coo, values) -- see tensor_hash()
@@ -31,7 +32,8 @@ struct SpecKernels {
     // packed tangent-linear / Benettin kernels (tgls_pack.cuh) with the product J @ X emitted over the literal
     // list of Jacobian positions; null when the module was generated without a Jacobian tensor.
     // lyap = 0: integrate.py:555-614, 1: lyapunov.py:471-632.
-    cudaError_t (*tangent)(const TensorView &T, const TgParams &P, int lyap, size_t smem_limit, cudaStream_t stream);
+    cudaError_t (*tangent)(const TensorView &T, const TgParams &P, const PackTables &tables, int lyap,
+                           size_t smem_limit, cudaStream_t stream);
     int jac_slots;                 // doubles of shared memory holding the position values of one member
     const short *jac_slot_table;   // (n, n) row-major: slot of position (i, j), -1 where J_ij is structurally zero
 };

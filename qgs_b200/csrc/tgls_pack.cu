@@ -2,8 +2,11 @@
 //
 // A tensor with a generated module (spec_registry.h: SpecKernels::tangent) runs the product over its
 // literal Jacobian position list; every other tensor of a supported ndim runs the dense n x n product.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
+#include <vector>
 
 #include "spec_registry.h"
 #include "tgls_pack.cuh"
@@ -23,9 +26,9 @@ static int forced_kernel()
 }
 
 template <int N>
-static cudaError_t launch_dense(const TensorView &T, const TgParams &P, bool lyap)
+static cudaError_t launch_dense(const TensorView &T, const TgParams &P, const PackTables &tab, bool lyap)
 {
-    return pack::launch<N, pack::DenseProduct<N, false>, pack::DenseProduct<N, true>>(T, P, lyap, ctx().smem_optin,
+    return pack::launch<N, pack::DenseProduct<N, false>, pack::DenseProduct<N, true>>(T, P, tab, lyap, ctx().smem_optin,
                                                                                        ctx().stream);
 }
 
@@ -51,16 +54,127 @@ bool pack_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m)
     return G >= 1 && G * m >= 96;
 }
 
+}  // namespace qgsb
+
+// device copies of the ELL tables of one tensor handle
+struct qgsb_tensor::PackCache {
+    qgsb::DevBuf<qgsb::PEnt> f, j;
+    qgsb::DevBuf<unsigned short> slot;
+    qgsb::PackTables tab;
+};
+
+qgsb_tensor::~qgsb_tensor()
+{
+    delete pack_cache[0];
+    delete pack_cache[1];
+}
+
+namespace qgsb {
+
+// a list is kept in CSR form when its ELL form would be long AND mostly padding
+static bool ell_ok(int width, long count, long real)
+{
+    return width > 0 && (width <= 4 || (double)width * (double)count <= 1.5 * (double)real + 64.);
+}
+
+static const PackTables &pack_tables(const qgsb_tensor *t, bool spec)
+{
+    qgsb_tensor::PackCache *&slot = t->pack_cache[spec ? 1 : 0];
+    if (slot) return slot->tab;
+    auto *pc = new qgsb_tensor::PackCache();
+    const int n = t->view.n, rank = t->view.rank;
+    // tendency rows 1..n
+    {
+        int EF = 0;
+        long real = 0;
+        for (int r = 1; r <= n; ++r) {
+            const int len = t->h_row_ptr[r + 1] - t->h_row_ptr[r];
+            EF = std::max(EF, len);
+            real += len;
+        }
+        if (ell_ok(EF, n, real)) {
+            std::vector<PEnt> h((size_t)EF * n, PEnt{0., 0, 0, 0, 0});
+            for (int r = 1; r <= n; ++r)
+                for (int e = t->h_row_ptr[r]; e < t->h_row_ptr[r + 1]; ++e) {
+                    const Entry &en = t->h_ent[e];
+                    PEnt &o = h[(size_t)(e - t->h_row_ptr[r]) * n + (r - 1)];
+                    o.v = en.v;
+                    o.a = (unsigned short)(en.jk & 0xffffu);
+                    o.b = (unsigned short)(en.jk >> 16);
+                    o.c = rank == 5 ? (unsigned short)(en.lm & 0xffffu) : 0;
+                    o.d = rank == 5 ? (unsigned short)(en.lm >> 16) : 0;
+                }
+            pc->f.alloc(h.size());
+            QGSB_CUDA(cudaMemcpy(pc->f.p, h.data(), h.size() * sizeof(PEnt), cudaMemcpyHostToDevice));
+            pc->tab.f_ent = pc->f.p;
+            pc->tab.EF = EF;
+        }
+    }
+    // Jacobian positions, in the list order of the product policy
+    {
+        const int npos = (int)t->h_pos_i.size();
+        std::vector<int> order(npos);        // order[q] = position p served by list entry q
+        std::vector<unsigned short> slots(npos);
+        if (spec) {
+            std::vector<std::pair<int, int>> by_slot(npos);
+            for (int p = 0; p < npos; ++p)
+                by_slot[p] = {t->spec->jac_slot_table[(t->h_pos_i[p] - 1) * n + (t->h_pos_j[p] - 1)], p};
+            std::sort(by_slot.begin(), by_slot.end());
+            for (int q = 0; q < npos; ++q) {
+                order[q] = by_slot[q].second;
+                slots[q] = (unsigned short)by_slot[q].first;
+            }
+        } else {
+            for (int p = 0; p < npos; ++p) {
+                order[p] = p;
+                slots[p] = (unsigned short)((t->h_pos_i[p] - 1) * n + (t->h_pos_j[p] - 1));
+            }
+        }
+        int EJ = 0;
+        long real = 0;
+        for (int p = 0; p < npos; ++p) {
+            const int len = t->h_pos_ptr[p + 1] - t->h_pos_ptr[p];
+            EJ = std::max(EJ, len);
+            real += len;
+        }
+        if (ell_ok(EJ, npos, real)) {
+            std::vector<PEnt> h((size_t)EJ * npos, PEnt{0., 0, 0, 0, 0});
+            for (int q = 0; q < npos; ++q) {
+                const int p = order[q];
+                for (int e = t->h_pos_ptr[p]; e < t->h_pos_ptr[p + 1]; ++e) {
+                    const Entry &en = t->h_jent[e];
+                    PEnt &o = h[(size_t)(e - t->h_pos_ptr[p]) * npos + q];
+                    o.v = en.v;
+                    o.a = (unsigned short)(en.jk & 0xffffu);
+                    o.b = rank == 5 ? (unsigned short)(en.jk >> 16) : 0;
+                    o.c = rank == 5 ? (unsigned short)(en.lm & 0xffffu) : 0;
+                }
+            }
+            pc->j.alloc(h.size());
+            QGSB_CUDA(cudaMemcpy(pc->j.p, h.data(), h.size() * sizeof(PEnt), cudaMemcpyHostToDevice));
+            pc->slot.alloc(npos);
+            QGSB_CUDA(cudaMemcpy(pc->slot.p, slots.data(), npos * sizeof(unsigned short), cudaMemcpyHostToDevice));
+            pc->tab.j_ent = pc->j.p;
+            pc->tab.j_slot = pc->slot.p;
+            pc->tab.EJ = EJ;
+            pc->tab.npos = npos;
+        }
+    }
+    slot = pc;
+    return pc->tab;
+}
+
 void launch_pack_tangent(const qgsb_tensor *t, const TgParams &P, bool lyap)
 {
     cudaError_t err;
     if (spec_tangent_usable(t) && forced_kernel() != 2) {
-        err = t->spec->tangent(t->view, P, lyap ? 1 : 0, ctx().smem_optin, ctx().stream);
+        err = t->spec->tangent(t->view, P, pack_tables(t, true), lyap ? 1 : 0, ctx().smem_optin, ctx().stream);
     } else {
+        const PackTables &tab = pack_tables(t, false);
         switch (t->view.n) {
-            case 20: err = launch_dense<20>(t->view, P, lyap); break;
-            case 36: err = launch_dense<36>(t->view, P, lyap); break;
-            case 38: err = launch_dense<38>(t->view, P, lyap); break;
+            case 20: err = launch_dense<20>(t->view, P, tab, lyap); break;
+            case 36: err = launch_dense<36>(t->view, P, tab, lyap); break;
+            case 38: err = launch_dense<38>(t->view, P, tab, lyap); break;
             default: err = cudaErrorInvalidValue;
         }
     }

@@ -5,7 +5,9 @@
 //  * a thread owns ONE COLUMN of the n x m tangent matrix of one member in registers (ndim is a
 //    template parameter, every register index is a literal);
 //  * a block packs G = floor(256 / m) members, so all lanes of (almost) every warp carry a column --
-//    a member is not tied to a warp or a block, only to m consecutive threads;
+//    a member is not tied to a warp or a block, only to m consecutive threads (consecutive, so that the
+//    broadcast reads of a member's J and reflectors hit one or two addresses per warp; interleaving the
+//    members across lanes was measured 20 % slower);
 //  * per Runge-Kutta stage the m threads of a member evaluate the tendencies and the values of the
 //    structurally non-zero Jacobian positions of THEIR member into shared memory, then every thread
 //    computes km[:, c] = +-J @ kms[:, c] reading J as broadcast LDS.128 (two positions per load).
@@ -136,15 +138,99 @@ struct DenseProduct {
     }
 };
 
+// ---- tendencies and Jacobian values of one member ------------------------------------------------------------------
+// row r of f at the stage state xs (sparse_mul.py:76-81 / :153-158 with the row's entries in COO order)
+template <int N>
+__device__ __forceinline__ double f_row_tab(const TensorView &T, const PackTables &tab, int r, const double *xs)
+{
+    if (tab.f_ent == nullptr) return f_row_rt(T, r + 1, xs);
+    const PEnt *e = tab.f_ent + r;
+    double acc = 0.;
+    if (T.rank == 5) {
+#pragma unroll 2
+        for (int q = 0; q < tab.EF; ++q) {
+            const PEnt en = e[q * N];
+            acc += xs[en.a] * xs[en.b] * xs[en.c] * xs[en.d] * en.v;
+        }
+    } else {
+#pragma unroll 4
+        for (int q = 0; q < tab.EF; ++q) {
+            const PEnt en = e[q * N];
+            acc += xs[en.a] * xs[en.b] * en.v;
+        }
+    }
+    return acc;
+}
+
+// values of the Jacobian positions q = c, c + m, ... of this member (sparse_mul.py:40-44 / :113-117)
+template <int N, class Prod>
+__device__ __forceinline__ void jac_build(const TensorView &T, const PackTables &tab, const double *xs, double *jv,
+                                          int c, int m)
+{
+    const JacView &J = T.jac;
+    if (tab.j_ent == nullptr) {
+        for (int p = c; p < J.npos; p += m) jv[Prod::slot(J.pos_i[p], J.pos_j[p])] = jac_pos_rt(J, T.rank, p, xs);
+        return;
+    }
+    const int npos = tab.npos;
+    if (T.rank == 5) {
+        for (int q = c; q < npos; q += m) {
+            double acc = 0.;
+            for (int e = 0; e < tab.EJ; ++e) {
+                const PEnt en = tab.j_ent[e * npos + q];
+                acc += xs[en.a] * xs[en.b] * xs[en.c] * en.v;
+            }
+            jv[tab.j_slot[q]] = acc;
+        }
+    } else if (tab.EJ == 2) {
+#pragma unroll 2
+        for (int q = c; q < npos; q += m) {
+            const PEnt e0 = tab.j_ent[q], e1 = tab.j_ent[npos + q];
+            double acc = xs[e0.a] * e0.v;
+            acc += xs[e1.a] * e1.v;
+            jv[tab.j_slot[q]] = acc;
+        }
+    } else {
+        for (int q = c; q < npos; q += m) {
+            double acc = 0.;
+            for (int e = 0; e < tab.EJ; ++e) {
+                const PEnt en = tab.j_ent[e * npos + q];
+                acc += xs[en.a] * en.v;
+            }
+            jv[tab.j_slot[q]] = acc;
+        }
+    }
+}
+
+// copies the tables into shared memory (after the members' areas) and returns pointers to the copies
+__device__ __forceinline__ PackTables stage_tables(const PackTables &tab, double *dst, int n)
+{
+    if (tab.stage_bytes <= 0) return tab;
+    PackTables out = tab;
+    PEnt *f = reinterpret_cast<PEnt *>(dst);
+    const int nf = tab.f_ent ? tab.EF * n : 0, nj = tab.j_ent ? tab.EJ * tab.npos : 0;
+    PEnt *j = f + nf;
+    unsigned short *sl = reinterpret_cast<unsigned short *>(j + nj);
+    for (int q = threadIdx.x; q < nf; q += blockDim.x) f[q] = tab.f_ent[q];
+    for (int q = threadIdx.x; q < nj; q += blockDim.x) j[q] = tab.j_ent[q];
+    if (tab.j_ent)
+        for (int q = threadIdx.x; q < tab.npos; q += blockDim.x) sl[q] = tab.j_slot[q];
+    if (tab.f_ent) out.f_ent = f;
+    if (tab.j_ent) {
+        out.j_ent = j;
+        out.j_slot = sl;
+    }
+    return out;
+}
+
 // ---- one step of the coupled system (chain tableau) -----------------------------------------------------------------
 // col[] holds fm[:, c] on entry and on exit; S.y advances by dt.  No barrier at the end: the caller
 // synchronises before anybody reads another thread's data.
 template <int N, class Prod>
-__device__ __forceinline__ void tangent_step(const TensorView &T, const TgParams &P, const Mem<N> &S, double dt,
-                                             double (&col)[N], int c, bool live)
+__device__ __forceinline__ void tangent_step(const TensorView &T, const PackTables &tab, const TgParams &P,
+                                             const Mem<N> &S, double dt, double (&col)[N], int c, bool live)
 {
     const int s = P.s, m = S.m;
-    const JacView &J = T.jac;
     double km[N];
     for (int st = 0; st < s; ++st) {
         const double wa_in = st > 0 ? dt * P.a[st * s + st - 1] : 0.;       // (dt a[st]) @ k   integrate.py:216
@@ -155,11 +241,11 @@ __device__ __forceinline__ void tangent_step(const TensorView &T, const TgParams
         __syncthreads();
         if (live) {
             for (int r = c; r < N; r += m) {
-                const double k = f_row_rt(T, r + 1, S.xs);
+                const double k = f_row_tab<N>(T, tab, r, S.xs);
                 S.kst[r] = k;
                 S.yacc[r] = st == 0 ? wb * k : S.yacc[r] + wb * k;
             }
-            for (int p = c; p < J.npos; p += m) S.jv[Prod::slot(J.pos_i[p], J.pos_j[p])] = jac_pos_rt(J, T.rank, p, S.xs);
+            jac_build<N, Prod>(T, tab, S.xs, S.jv, c, m);
         }
         __syncthreads();
         if (live) {
@@ -190,8 +276,8 @@ __device__ __forceinline__ void tangent_step(const TensorView &T, const TgParams
 
 // one nonlinear step of the macro ("stored") trajectory: S.Y <- RK(S.Y, dt)
 template <int N>
-__device__ __forceinline__ void nl_step(const TensorView &T, const TgParams &P, const Mem<N> &S, double dt, int c,
-                                        bool live)
+__device__ __forceinline__ void nl_step(const TensorView &T, const PackTables &tab, const TgParams &P,
+                                        const Mem<N> &S, double dt, int c, bool live)
 {
     const int s = P.s, m = S.m;
     for (int st = 0; st < s; ++st) {
@@ -202,7 +288,7 @@ __device__ __forceinline__ void nl_step(const TensorView &T, const TgParams &P, 
         __syncthreads();
         if (live)
             for (int r = c; r < N; r += m) {
-                const double k = f_row_rt(T, r + 1, S.xs);
+                const double k = f_row_tab<N>(T, tab, r, S.xs);
                 S.kst[r] = k;
                 S.yacc[r] = st == 0 ? wb * k : S.yacc[r] + wb * k;
             }
@@ -211,6 +297,20 @@ __device__ __forceinline__ void nl_step(const TensorView &T, const TgParams &P, 
     if (live)
         for (int r = c; r < N; r += m) S.Y[r] += S.yacc[r];
     __syncthreads();
+}
+
+// 1 / x to within 1 ulp for normal x of moderate magnitude: hardware seed + two Newton steps, without the
+// branchy slow path of the IEEE division (the reflector scalars tolerate the last bit)
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.);
+    return fma(r, e, r);
 }
 
 // Householder QR of the n x m matrix whose column c lives in col[] of thread c of the member.  On exit col[]
@@ -229,30 +329,43 @@ __device__ __forceinline__ void qr(const Mem<N> &S, int c, bool live, double (&c
         if (j < m) {                       // uniform
             double *x = V + j * N;
             if (live && c == j) {
+                if (j & 1) x[j] = col[j];
 #pragma unroll
-                for (int i = j; i < N; ++i) x[i] = col[i];
+                for (int i = (j + 1) & ~1; i < N; i += 2)      // 16-byte stores; for even j the pair starts at row j
+                    *reinterpret_cast<double2 *>(x + i) = make_double2(col[i], col[i + 1]);
             }
             __syncthreads();
             if (live && c >= j) {
-                // dlarfg + dlarf: d = x . col_c and |x|^2 over the rows below the diagonal
-                double d0 = 0., d1 = 0., n0 = 0., n1 = 0.;
+                // dlarfg + dlarf: d = x . col_c and |x|^2 over the rows below the diagonal (4 + 4 independent chains)
+                double d0 = 0., d1 = 0., d2 = 0., d3 = 0., n0 = 0., n1 = 0., n2 = 0., n3 = 0.;
 #pragma unroll
                 for (int i = (j + 1) & ~1; i < N; i += 2) {       // rows in aligned pairs: one LDS.128 each
                     const double2 xi = *reinterpret_cast<const double2 *>(x + i);
-                    if (i > j) {
-                        d0 = fma(xi.x, col[i], d0);
-                        n0 = fma(xi.x, xi.x, n0);
+                    if ((i >> 1) & 1) {
+                        if (i > j) {
+                            d0 = fma(xi.x, col[i], d0);
+                            n0 = fma(xi.x, xi.x, n0);
+                        }
+                        d1 = fma(xi.y, col[i + 1], d1);
+                        n1 = fma(xi.y, xi.y, n1);
+                    } else {
+                        if (i > j) {
+                            d2 = fma(xi.x, col[i], d2);
+                            n2 = fma(xi.x, xi.x, n2);
+                        }
+                        d3 = fma(xi.y, col[i + 1], d3);
+                        n3 = fma(xi.y, xi.y, n3);
                     }
-                    d1 = fma(xi.y, col[i + 1], d1);
-                    n1 = fma(xi.y, xi.y, n1);
                 }
                 const double alpha = x[j];
-                const double xnorm = sqrt(n0 + n1);
+                const double nrm2 = (n0 + n1) + (n2 + n3), dot = (d0 + d1) + (d2 + d3);
                 double beta = alpha, tau = 0., scal = 0.;
-                if (xnorm != 0.) {
-                    beta = -copysign(hypot(alpha, xnorm), alpha);
-                    tau = (beta - alpha) / beta;
-                    scal = 1. / (alpha - beta);
+                if (nrm2 != 0.) {
+                    // dlapy2(alpha, xnorm) = sqrt(alpha^2 + |x|^2): the columns are O(1) here (an orthonormal
+                    // basis propagated over one step), so the unscaled form neither overflows nor underflows
+                    beta = -copysign(sqrt(fma(alpha, alpha, nrm2)), alpha);
+                    tau = (beta - alpha) * fast_rcp(beta);
+                    scal = fast_rcp(alpha - beta);
                 }
                 if (c == j) {
                     col[j] = beta;
@@ -260,7 +373,7 @@ __device__ __forceinline__ void qr(const Mem<N> &S, int c, bool live, double (&c
                     S.tau[j] = tau;
                     S.scal[j] = scal;
                 } else {
-                    const double w = tau * fma(d0 + d1, scal, col[j]);
+                    const double w = tau * fma(dot, scal, col[j]);
                     col[j] -= w;
                     const double ws = -(w * scal);
 #pragma unroll
@@ -285,15 +398,20 @@ __device__ __forceinline__ void qr(const Mem<N> &S, int c, bool live, double (&c
         const int j = N - 1 - jj;
         if (j < m && live && j <= c) {
             const double *x = V + j * N;
-            double d0 = 0., d1 = 0.;
+            double d0 = 0., d1 = 0., d2 = 0., d3 = 0.;
 #pragma unroll
             for (int i = (j + 1) & ~1; i < N; i += 2) {
                 const double2 xi = *reinterpret_cast<const double2 *>(x + i);
-                if (i > j) d0 = fma(xi.x, col[i], d0);
-                d1 = fma(xi.y, col[i + 1], d1);
+                if ((i >> 1) & 1) {
+                    if (i > j) d0 = fma(xi.x, col[i], d0);
+                    d1 = fma(xi.y, col[i + 1], d1);
+                } else {
+                    if (i > j) d2 = fma(xi.x, col[i], d2);
+                    d3 = fma(xi.y, col[i + 1], d3);
+                }
             }
             const double scal = S.scal[j];
-            const double w = S.tau[j] * fma(d0 + d1, scal, col[j]);
+            const double w = S.tau[j] * fma((d0 + d1) + (d2 + d3), scal, col[j]);
             col[j] -= w;
             const double ws = -(w * scal);
 #pragma unroll
@@ -328,9 +446,10 @@ __device__ __forceinline__ void init_member(const Mem<N> &S, int c, bool live)
 // ---- plain tangent-linear integration (integrate.py:555-614) ----------------------------------------------------------
 template <int N, class Prod>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
-tgls_kernel(TensorView T, const __grid_constant__ TgParams P, int G, int stride)
+tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride)
 {
     extern __shared__ __align__(16) double smem_pack[];
+    const PackTables tab = stage_tables(tab_g, smem_pack + (size_t)G * stride, N);
     const int m = P.m, t = threadIdx.x;
     const int g = t / m, c = t - g * m;
     const long member = (long)blockIdx.x * G + g;
@@ -348,6 +467,7 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, int G, int stride)
     }
     __syncthreads();
     long iw = 0;
+#pragma unroll 1
     for (long ti = 0; ti < P.n_steps; ++ti) {
         if (P.rec_y && P.write_steps > 0 && ti % P.write_steps == 0) {
             if (live) {
@@ -359,7 +479,7 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, int G, int stride)
             }
             ++iw;
         }
-        tangent_step<N, Prod>(T, P, S, P.dt[ti], col, c, live);
+        tangent_step<N, Prod>(T, tab, P, S, P.dt[ti], col, c, live);
         __syncthreads();
     }
     if (live) {
@@ -379,9 +499,10 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, int G, int stride)
 // ---- Benettin loop (lyapunov.py:471-632) ---------------------------------------------------------------------------------
 template <int N, class Prod>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
-lyap_kernel(TensorView T, const __grid_constant__ TgParams P, int G, int stride)
+lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride)
 {
     extern __shared__ __align__(16) double smem_pack[];
+    const PackTables tab = stage_tables(tab_g, smem_pack + (size_t)G * stride, N);
     const int m = P.m, t = threadIdx.x;
     const int g = t / m, c = t - g * m;
     const long member = (long)blockIdx.x * G + g;
@@ -404,6 +525,7 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, int G, int stride)
     const size_t sbase = (P.stored && live) ? tile_base(member, N) : 0;
     long iw = 0;
     double mexp = 0.;
+#pragma unroll 1
     for (long step = 0; step < steps; ++step) {
         if (P.stored) {                                                   // lyapunov.py:513 / :527
             if (live) {
@@ -438,7 +560,7 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, int G, int stride)
         if (live)
             for (int r = c; r < N; r += m) S.y[r] = S.Y[r];
         const long q0 = P.sub_ptr[step], q1 = P.sub_ptr[step + 1];
-        for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, P, S, P.sub_dt[q], col, c, live);
+        for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, tab, P, S, P.sub_dt[q], col, c, live);
         // q, r = qr(prop @ q)   (:602-604)
         qr<N>(S, c, live, col, (P.r_all && live) ? P.r_all + ((size_t)member * steps + step) * m * m : nullptr);
         if (P.forward == 2 || (!P.stored && q1 - q0 == 1 && P.sub_dt[q0] == P.dt_macro[step])) {
@@ -447,7 +569,7 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, int G, int stride)
             if (live)
                 for (int r = c; r < N; r += m) S.Y[r] = S.y[r];
         } else if (!P.stored) {                           // next stored-trajectory point (:601 / :622)
-            nl_step<N>(T, P, S, P.dt_macro[step], c, live);
+            nl_step<N>(T, tab, P, S, P.dt_macro[step], c, live);
         }
     }
     if (live) {
@@ -475,37 +597,53 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, int G, int stride)
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
+// table_bytes: size of the tables when staged in shared memory (0: leave them in global memory)
 template <int N>
-inline Geometry geometry(int jv, int m, size_t smem_limit)
+inline Geometry geometry(int jv, int m, size_t smem_limit, size_t table_bytes, bool *staged)
 {
     Geometry geo;
     const Carve<N> c(jv, m);
     geo.jv = jv;
     geo.stride = c.total();
     const size_t per_member = (size_t)geo.stride * sizeof(double);
-    int G = MAX_THREADS / m;
+    const int want = MAX_THREADS / m;
+    int G = want;
     if ((size_t)G * per_member > smem_limit) G = (int)(smem_limit / per_member);
+    // stage the tables only when that does not cost a member
+    *staged = table_bytes > 0 && (size_t)G * per_member + table_bytes <= smem_limit;
     geo.G = G;
     geo.threads = G > 0 ? ((G * m + 31) / 32) * 32 : 0;
-    geo.smem = (size_t)G * per_member;
+    geo.smem = (size_t)G * per_member + (*staged ? table_bytes : 0);
     return geo;
+}
+
+inline size_t table_bytes(const PackTables &tab, int n)
+{
+    size_t b = 0;
+    if (tab.f_ent) b += (size_t)tab.EF * n * sizeof(PEnt);
+    if (tab.j_ent) b += (size_t)tab.EJ * tab.npos * sizeof(PEnt) + ((size_t)tab.npos * sizeof(unsigned short) + 15) / 16 * 16;
+    return b;
 }
 
 // launches the packed kernel for one policy pair; returns cudaErrorInvalidValue when it does not fit
 template <int N, class Fwd, class Adj>
-inline cudaError_t launch(const TensorView &T, const TgParams &P, bool lyap, size_t smem_limit, cudaStream_t stream)
+inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTables &tables, bool lyap,
+                          size_t smem_limit, cudaStream_t stream)
 {
     static_assert(Fwd::JV == Adj::JV, "both directions of a product share one Jacobian layout");
     if (P.m < 1 || P.m > MAX_THREADS) return cudaErrorInvalidValue;
-    const Geometry geo = geometry<N>(Fwd::JV, P.m, smem_limit);
+    bool staged = false;
+    const Geometry geo = geometry<N>(Fwd::JV, P.m, smem_limit, table_bytes(tables, N), &staged);
     if (geo.G < 1) return cudaErrorInvalidValue;
+    PackTables tab = tables;
+    tab.stage_bytes = staged ? (int)table_bytes(tables, N) : 0;
     const unsigned blocks = (unsigned)((P.n_members + geo.G - 1) / geo.G);
     auto go = [&](auto kernel) -> cudaError_t {
         if (geo.smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem);
             if (e != cudaSuccess) return e;
         }
-        kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, geo.G, geo.stride);
+        kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, tab, geo.G, geo.stride);
         return cudaGetLastError();
     };
     if (lyap) return P.adjoint ? go(lyap_kernel<N, Adj>) : go(lyap_kernel<N, Fwd>);

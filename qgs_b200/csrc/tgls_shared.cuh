@@ -80,6 +80,27 @@ __device__ __forceinline__ double jac_pos_rt(const JacView &J, int rank, int p, 
     return rank == 5 ? jac_pos<5>(J, p, xs) : jac_pos<3>(J, p, xs);
 }
 
+// ---- tables of the packed kernels (tgls_pack.cuh) -----------------------------------------------------------------
+// ELL ("padded column") forms of the tendency rows and of the Jacobian positions: entry e of row r sits at
+// f_ent[e * n + r], entry e of list position q at j_ent[e * npos + q], so the m threads of a member read
+// consecutive 16-byte records and every thread runs the same trip count.  Padding records have v = 0 and
+// multiply x_0 = 1.  A table is absent (null) when padding would cost more than 1.5x the real entries; the
+// kernels then walk the CSR lists of TensorView.
+struct __align__(16) PEnt {
+    double v;
+    unsigned short a, b, c, d;   // factor indices into the augmented state (0 = the constant 1)
+};
+
+struct PackTables {
+    const PEnt *f_ent = nullptr;
+    int EF = 0;
+    const PEnt *j_ent = nullptr;
+    int EJ = 0;
+    int npos = 0;
+    const unsigned short *j_slot = nullptr;   // (npos) slot of list position q in the member's Jacobian area
+    int stage_bytes = 0;                      // > 0: the kernel copies the tables into shared memory first
+};
+
 // packed kernels (tgls_pack.cu / tgls_pack.cuh)
 bool pack_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m);
 void launch_pack_tangent(const qgsb_tensor *t, const TgParams &P, bool lyap);
