@@ -198,11 +198,18 @@ struct qgsb_tensor {
     std::vector<int> h_pos_i, h_pos_j;   // host copy of the Jacobian positions
     std::vector<qgsb::Entry> h_ent, h_jent;          // host copies of the device entry lists
     std::vector<int> h_row_ptr, h_pos_ptr;
+    struct G3Cache;                      // plan + tables of the large-basis RK kernel (rk.cu G3), built on first use
+    mutable G3Cache *g3_cache = nullptr;
+    mutable int g3_state = 0;            // 0 not planned, 1 ready, -1 not applicable
     // tables of the packed tangent kernels, built on first use: [0] dense product, [1] generated product
     struct PackCache;
     mutable PackCache *pack_cache[2] = {nullptr, nullptr};
     ~qgsb_tensor();
 };
+
+namespace qgsb {
+void g3_release(qgsb_tensor::G3Cache *c);
+}
 
 struct qgsb_ensemble {
     const qgsb_tensor *tensor = nullptr;

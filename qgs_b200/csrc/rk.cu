@@ -295,6 +295,164 @@ __global__ void __launch_bounds__(G2_WARPS * 32) rk_g2_kernel(TensorView T, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// G3: large bases (n > 64, rank 3, chain tableaux).  A block owns MB members (a multiple of 32) and
+// keeps only their stage state x in shared memory ([variable][member], conflict-free, ~176 KB => 96
+// members per SM for the 228-variable 6x6 model); y, the weighted stage sum and the next stage state
+// stay in the tiled-SoA arrays in global memory, where each value is touched once per stage with
+// coalesced accesses (40 n bytes per member and stage, L2 resident; the loads of a row are issued
+// before the row's terms so that their latency is covered).
+// To have enough warps in flight the rows are split into G groups of about equal entry counts and
+// thread (h, m) evaluates the rows of group h for member m: G x MB threads, all reading the same x.
+// The tensor is a 16-byte-per-entry stream walked identically by the MB threads of a group: the group
+// pulls its part through a double buffer of chunks (<= 256 entries, whole rows padded to multiples
+// of four entries) with cp.async, one chunk ahead, one named barrier per chunk, and consumes it with
+// broadcast LDS.128 in a software pipeline, four independent partial sums per row.  An entry holds
+// its value and the byte offsets of x_j / x_k in the shared state (premultiplied by MB).
+// The kernel is bound by shared-memory bandwidth: 16 bytes of x + 16/32 bytes of entry per term and member.
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) G3Entry {
+    double v;
+    uint32_t oj, ok;   // byte offsets of the x_j / x_k rows in the shared state
+};
+
+struct G3Chunk {
+    int off, count, row0, nrows;   // entries [off, off + count) = rows row0 .. row0 + nrows - 1 (0-based)
+};
+
+constexpr int G3_CHUNK = 256;               // entries per chunk
+constexpr int G3_STRIDE = G3_CHUNK + 4;     // the software pipeline reads one group of four past the end of a chunk
+constexpr int G3_RING = 2;
+constexpr int G3_MAX_GROUPS = 4;
+
+struct G3Plan {
+    int groups;
+    int chunk0[G3_MAX_GROUPS + 1];   // group h owns chunks [chunk0[h], chunk0[h + 1])
+    int row0[G3_MAX_GROUPS + 1];     // and rows [row0[h], row0[h + 1])
+};
+
+__device__ __forceinline__ void g3_fetch(G3Entry *ring, const G3Entry *__restrict__ ent, const G3Chunk *chunks,
+                                         long chunk, int per_stage, int m, int mb)
+{
+    // the chunk counter runs on across stages and steps; every stage walks the same list
+    const G3Chunk ch = chunks[chunk % per_stage];
+    G3Entry *dst = ring + (size_t)(chunk % G3_RING) * G3_STRIDE;
+    const G3Entry *src = ent + ch.off;
+    for (int e = m; e < ch.count; e += mb) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + e);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + e));
+    }
+    asm volatile("cp.async.commit_group;");
+}
+
+#define G3_X(off) (*reinterpret_cast<const double *>(xb + (off)))
+
+__global__ void __launch_bounds__(128 * G3_MAX_GROUPS)
+rk_g3_kernel(int n, int mb, int n_chunks, const __grid_constant__ G3Plan plan, const G3Entry *__restrict__ ent,
+             const G3Chunk *__restrict__ chunks_g, const int *__restrict__ rowlen_g,
+             const __grid_constant__ RkParams P, double *__restrict__ acc_g, double *__restrict__ xn_g)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, s = P.s;
+    const int h = tid / mb, m = tid - h * mb;          // row group, member inside the block
+    G3Entry *rings = reinterpret_cast<G3Entry *>(smem_raw);
+    G3Chunk *chunks_all = reinterpret_cast<G3Chunk *>(rings + (size_t)G3_STRIDE * G3_RING * plan.groups);
+    int *rowlen = reinterpret_cast<int *>(chunks_all + n_chunks);
+    unsigned char *xb = reinterpret_cast<unsigned char *>(rowlen + ((n + 3) & ~3)) + (size_t)m * 8;  // x_i at xb + i mb 8
+    const size_t rowb = (size_t)mb * 8;
+    long member = (long)blockIdx.x * mb + m;
+    const bool act = member < P.ld;                   // the whole block keeps running: it shares rings and barriers
+    if (!act) member = P.ld - 1;
+    const size_t gbase = tile_base(member, n);
+    double *yg = P.y + gbase, *ag = acc_g + gbase, *xg = xn_g + gbase;
+    G3Entry *ring = rings + (size_t)G3_STRIDE * G3_RING * h;
+    const G3Chunk *chunks = chunks_all + plan.chunk0[h];
+    const int per_stage = plan.chunk0[h + 1] - plan.chunk0[h];
+    const int r_lo = plan.row0[h], r_hi = plan.row0[h + 1];
+    for (int q = tid; q < G3_STRIDE * G3_RING * plan.groups; q += blockDim.x)
+        rings[q] = G3Entry{0., 0u, 0u};                // read-ahead lands on valid offsets
+    for (int q = tid; q < n_chunks; q += blockDim.x) chunks_all[q] = chunks_g[q];
+    for (int q = tid; q < n; q += blockDim.x) rowlen[q] = rowlen_g[q];
+    if (h == 0) *reinterpret_cast<double *>(xb) = 1.;
+    for (int i = r_lo; i < r_hi; ++i) *reinterpret_cast<double *>(xb + (size_t)(i + 1) * rowb) = yg[(size_t)i * TILE];
+    __syncthreads();
+
+    const long total = (long)per_stage * s * P.n_steps;
+    long chunk = 0;
+    if (total > 0) g3_fetch(ring, ent, chunks, 0, per_stage, m, mb);
+
+    long iw = 0;
+    for (long ti = 0; ti < P.n_steps; ++ti) {
+        const double dt = P.dt[ti];
+        if (P.rec && P.write_steps > 0 && ti % P.write_steps == 0) {       // integrate.py:210-212
+            if (act) {
+                double *r = P.rec + (size_t)iw * n * P.ld + gbase;
+                for (int i = r_lo; i < r_hi; ++i) r[(size_t)i * TILE] = yg[(size_t)i * TILE];
+            }
+            ++iw;
+        }
+        for (int st = 0; st < s; ++st) {
+            const double wb = dt * P.b[st];
+            const double wa = st + 1 < s ? dt * P.alpha[st + 1] : 0.;
+            const bool last = st + 1 == s;
+            for (int c = 0; c < per_stage; ++c, ++chunk) {
+                asm volatile("cp.async.wait_group 0;");
+                asm volatile("bar.sync %0, %1;" ::"r"(h + 1), "r"(mb));   // chunk landed for the group; chunk - 1 consumed
+                if (chunk + 1 < total) g3_fetch(ring, ent, chunks, chunk + 1, per_stage, m, mb);
+                const uint4 *pe = reinterpret_cast<const uint4 *>(ring + (size_t)(chunk % G3_RING) * G3_STRIDE);
+                const G3Chunk ch = chunks[c];
+                // software pipeline over groups of four entries: the entries of the next group are loaded while the
+                // x values of the current one are in flight (rows are padded to whole groups with zero entries)
+                uint4 c0 = pe[0], c1 = pe[1], c2 = pe[2], c3 = pe[3];
+                for (int r = 0; r < ch.nrows; ++r) {
+                    const int groups = rowlen[ch.row0 + r] >> 2;
+                    const size_t o = (size_t)(ch.row0 + r) * TILE;
+                    const double y_old = yg[o];                             // in flight while the row is summed
+                    const double a_old = st == 0 ? 0. : ag[o];
+                    double k0 = 0., k1 = 0., k2 = 0., k3 = 0.;
+#pragma unroll 2
+                    for (int g = 0; g < groups; ++g) {
+                        const double a0 = G3_X(c0.z), b0 = G3_X(c0.w), a1 = G3_X(c1.z), b1 = G3_X(c1.w);
+                        const double a2 = G3_X(c2.z), b2 = G3_X(c2.w), a3 = G3_X(c3.z), b3 = G3_X(c3.w);
+                        pe += 4;
+                        const uint4 n0 = pe[0], n1 = pe[1], n2 = pe[2], n3 = pe[3];
+                        k0 = fma(a0 * b0, __hiloint2double(c0.y, c0.x), k0);   // (a*b)*value, then +=  (sparse_mul.py:79)
+                        k1 = fma(a1 * b1, __hiloint2double(c1.y, c1.x), k1);
+                        k2 = fma(a2 * b2, __hiloint2double(c2.y, c2.x), k2);
+                        k3 = fma(a3 * b3, __hiloint2double(c3.y, c3.x), k3);
+                        c0 = n0;
+                        c1 = n1;
+                        c2 = n2;
+                        c3 = n3;
+                    }
+                    const double k = (k0 + k1) + (k2 + k3);
+                    if (act) {
+                        const double ac = a_old + wb * k;
+                        if (!last) {
+                            ag[o] = ac;
+                            xg[o] = y_old + wa * k;                         // y + (dt a[i]) @ k   integrate.py:216
+                        } else {
+                            const double yn = y_old + ac;                   // y + (dt b) @ k      integrate.py:218
+                            yg[o] = yn;
+                            xg[o] = yn;
+                        }
+                    }
+                }
+            }
+            __syncthreads();               // every group is done reading x
+            for (int i = r_lo; i < r_hi; ++i)
+                *reinterpret_cast<double *>(xb + (size_t)(i + 1) * rowb) = xg[(size_t)i * TILE];
+            __syncthreads();               // the next stage state is complete
+        }
+    }
+    asm volatile("cp.async.wait_group 0;");
+    if (P.rec && act) {                                                     // integrate.py:221
+        double *r = P.rec + (size_t)(P.n_records - 1) * n * P.ld + gbase;
+        for (int i = r_lo; i < r_hi; ++i) r[(size_t)i * TILE] = yg[(size_t)i * TILE];
+    }
+}
+#undef G3_X
+
+// ------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------
 template <typename K>
@@ -365,6 +523,121 @@ static void launch_g2(const qgsb_tensor *t, RkParams &P)
     QGSB_CUDA(cudaGetLastError());
 }
 
+static bool g3_enabled()
+{
+    const char *e = getenv("QGSB_RK_LARGE");     // "g2": force the warp-per-member kernel (A/B measurements)
+    return !(e && !strcmp(e, "g2"));
+}
+
+// the host side of the plan, cached in the tensor handle
+struct G3Host {
+    G3Plan plan;
+    int mb = 0, n_chunks = 0;
+    DevBuf<G3Entry> ent;
+    DevBuf<int> meta;      // chunk list (4 ints each), then the padded row lengths
+    size_t smem = 0;
+};
+
+}  // namespace qgsb
+
+struct qgsb_tensor::G3Cache : qgsb::G3Host {};
+
+namespace qgsb {
+
+void g3_release(qgsb_tensor::G3Cache *c) { delete c; }
+
+// rows -> groups of about equal (padded) entry counts -> chunks of whole rows
+static bool g3_prepare(const qgsb_tensor *t)
+{
+    const int n = t->view.n;
+    std::vector<int> rowlen(n);
+    long total = 0;
+    for (int i = 1; i <= n; ++i) {
+        rowlen[i - 1] = (t->h_row_ptr[i + 1] - t->h_row_ptr[i] + 3) & ~3;
+        if (rowlen[i - 1] > G3_CHUNK) return false;
+        total += rowlen[i - 1];
+    }
+    if (total == 0) return false;
+    auto *c = new qgsb_tensor::G3Cache();
+    G3Plan &plan = c->plan;
+    const int G = (int)std::min<long>(G3_MAX_GROUPS, std::max<long>(1, total / 2048));
+    plan.groups = G;
+    std::vector<G3Chunk> chunks;
+    int row = 0;
+    long done = 0;
+    int off = 0;
+    for (int h = 0; h < G; ++h) {
+        plan.chunk0[h] = (int)chunks.size();
+        plan.row0[h] = row;
+        const long target = total * (h + 1) / G;
+        G3Chunk cur{off, 0, row, 0};
+        while (row < n && (h == G - 1 || done + rowlen[row] / 2 < target)) {
+            if (cur.count + rowlen[row] > G3_CHUNK) {
+                chunks.push_back(cur);
+                cur = G3Chunk{off, 0, row, 0};
+            }
+            cur.count += rowlen[row];
+            cur.nrows += 1;
+            off += rowlen[row];
+            done += rowlen[row];
+            ++row;
+        }
+        if (cur.nrows > 0 || chunks.size() == (size_t)plan.chunk0[h]) chunks.push_back(cur);
+    }
+    plan.chunk0[G] = (int)chunks.size();
+    plan.row0[G] = n;
+    c->n_chunks = (int)chunks.size();
+    const size_t fixed = sizeof(G3Entry) * G3_STRIDE * G3_RING * G + sizeof(G3Chunk) * chunks.size() +
+                         sizeof(int) * (size_t)((n + 3) & ~3);
+    const size_t limit = ctx().smem_optin;
+    if (fixed + 32 * 8 * (size_t)(n + 1) > limit) {
+        delete c;
+        return false;
+    }
+    const int mb = (int)std::min<size_t>(128, (limit - fixed) / (8 * (size_t)(n + 1))) & ~31;
+    c->mb = mb;
+    c->smem = fixed + (size_t)(n + 1) * 8 * mb;
+    std::vector<G3Entry> h;
+    h.reserve(total);
+    for (int i = 1; i <= n; ++i) {
+        for (int e = t->h_row_ptr[i]; e < t->h_row_ptr[i + 1]; ++e)
+            h.push_back(G3Entry{t->h_ent[e].v, (uint32_t)((t->h_ent[e].jk & 0xffffu) * (uint32_t)mb * 8u),
+                                (uint32_t)((t->h_ent[e].jk >> 16) * (uint32_t)mb * 8u)});
+        while (h.size() & 3) h.push_back(G3Entry{0., 0u, 0u});       // + 0 * x_0 * x_0
+    }
+    std::vector<int> meta(chunks.size() * 4 + rowlen.size());
+    memcpy(meta.data(), chunks.data(), chunks.size() * sizeof(G3Chunk));
+    memcpy(meta.data() + chunks.size() * 4, rowlen.data(), rowlen.size() * sizeof(int));
+    c->ent.alloc(h.size());
+    QGSB_CUDA(cudaMemcpy(c->ent.p, h.data(), h.size() * sizeof(G3Entry), cudaMemcpyHostToDevice));
+    c->meta.alloc(meta.size());
+    QGSB_CUDA(cudaMemcpy(c->meta.p, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice));
+    t->g3_cache = c;
+    return true;
+}
+
+static bool launch_g3(const qgsb_tensor *t, RkParams &P)
+{
+    const int n = t->view.n;
+    if (t->g3_state < 0) return false;
+    if (t->g3_state == 0) {
+        t->g3_state = -1;
+        if (!g3_prepare(t)) return false;
+        t->g3_state = 1;
+    }
+    const qgsb_tensor::G3Cache *c = t->g3_cache;
+    PoolBuf<double> d_acc((size_t)n * P.ld), d_xn((size_t)n * P.ld);
+    set_smem(rk_g3_kernel, c->smem);
+    const unsigned grid = (unsigned)((P.ld + c->mb - 1) / c->mb);
+    rk_g3_kernel<<<grid, c->mb * c->plan.groups, c->smem, ctx().stream>>>(
+        n, c->mb, c->n_chunks, c->plan, c->ent.p, reinterpret_cast<const G3Chunk *>(c->meta.p),
+        c->meta.p + (size_t)c->n_chunks * 4, P, d_acc.p, d_xn.p);
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+    // the scratch arrays go back to the pool here; every user of the pool runs on the same stream
+    return true;
+}
+
 void rk_advance(const qgsb_tensor *t, double *d_y, long ld, long N, long n_steps, const double *d_dt,
                 const Tableau &tab, long write_steps, long R, double *d_rec)
 {
@@ -377,6 +650,7 @@ void rk_advance(const qgsb_tensor *t, double *d_y, long ld, long N, long n_steps
     RkParams P;
     fill_params(P, tab, d_y, ld, N, n_steps, d_dt, write_steps, R, d_rec);
     const int n = t->view.n;
+    if (n > QGSB_G1_MAX_NDIM && t->view.rank == 3 && tab.chain && g3_enabled() && launch_g3(t, P)) return;
     if (n <= QGSB_G1_MAX_NDIM) {
         const size_t per_thread = tab.chain ? (size_t)(4 * n + 2) : (size_t)(2 * n + 1) + (size_t)tab.s * n;
         if (per_thread * 8 * 64 + 4096 <= ctx().smem_optin) return launch_g1<64>(t, P);

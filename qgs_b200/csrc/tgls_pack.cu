@@ -67,6 +67,7 @@ qgsb_tensor::~qgsb_tensor()
 {
     delete pack_cache[0];
     delete pack_cache[1];
+    qgsb::g3_release(g3_cache);
 }
 
 namespace qgsb {
