@@ -151,6 +151,15 @@ QGSB_API int qgsb_ensemble_integrate_record(qgsb_ensemble *e, long n_steps, cons
 /* Sum and sum of squares over members for every variable (ensemble statistics; NCCL all-reduce of
  * these 2n doubles is done by the caller across ranks). */
 QGSB_API int qgsb_ensemble_moments(qgsb_ensemble *e, double *sum /* (n) */, double *sumsq /* (n) */);
+/* Integrate the resident ensemble and return, for every record of integrate.py:190-221 (n_records of them), the
+ * per-variable sum and sum of squares over the members -- the ensemble statistics of
+ * qgs/integrators/statistics.py:33-66 (TrajectoriesStatistics.compute_stats with the identity and the square as
+ * functions) without materialising the (n_traj, n_dim, n_records) trajectories on the host.  The ensemble ends at
+ * the final state, like qgsb_ensemble_integrate. */
+QGSB_API int qgsb_ensemble_integrate_moments(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                                             const double *b, const double *c, long write_steps, long n_records,
+                                             double *sum /* host (R, n) */, double *sumsq /* host (R, n) */,
+                                             double *device_ms);
 QGSB_API void *qgsb_ensemble_device_ptr(qgsb_ensemble *e);
 QGSB_API long qgsb_ensemble_ld(const qgsb_ensemble *e);
 QGSB_API int qgsb_synchronize(void);

@@ -66,6 +66,9 @@ _PROTOTYPES = {
                                                       c_double_p, c_double_p, c_double_p, ctypes.c_long,
                                                       ctypes.c_long, ctypes.c_void_p, c_double_p]),
     "qgsb_ensemble_moments": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p]),
+    "qgsb_ensemble_integrate_moments": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_long, c_double_p, ctypes.c_int,
+                                                       c_double_p, c_double_p, c_double_p, ctypes.c_long,
+                                                       ctypes.c_long, c_double_p, c_double_p, c_double_p]),
     "qgsb_ensemble_device_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),
     "qgsb_ensemble_ld": (ctypes.c_long, [ctypes.c_void_p]),
     "qgsb_synchronize": (ctypes.c_int, []),

@@ -12,6 +12,9 @@ void launch_soa_to_aos(const double *d_in, double *d_out, long N, int n, long ld
 // (R, rows, ld) member-minor records -> (N, rows, R) API layout
 void launch_rec_to_api(const double *d_in, double *d_out, long N, long rows, long R, long ld, int flip);
 
+// sums and sums of squares per variable of R tiled records (R, n, ld) over the first N members -> (R, n) each
+void launch_record_moments(const double *d_rec, long R, long N, int n, long ld, double *d_sum, double *d_sumsq);
+
 inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
 
 // Butcher tableau checked and reduced on the host

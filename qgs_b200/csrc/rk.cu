@@ -868,6 +868,59 @@ int qgsb_ensemble_integrate_record(qgsb_ensemble *e, long n_steps, const double 
     QGSB_API_END
 }
 
+// Ensemble statistics without the (N, n, R) dump of TrajectoriesStatistics.compute_stats
+// (qgs/integrators/statistics.py:33-66): integrate, keep the records of a bounded number of write steps in HBM,
+// reduce them to per-record sums on the device, continue.  Record semantics are those of integrate.py:190-221.
+int qgsb_ensemble_integrate_moments(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                                    const double *b, const double *c, long write_steps, long R, double *sum,
+                                    double *sumsq, double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(e && sum && sumsq, "null argument");
+    QGSB_REQUIRE(n_steps >= 0 && write_steps >= 0, "negative step count");
+    QGSB_REQUIRE(n_steps == 0 || dt != nullptr, "null dt array");
+    QGSB_REQUIRE(R == records_for(n_steps, write_steps), "n_records %ld inconsistent with %ld steps / write_steps %ld",
+                 R, n_steps, write_steps);
+    ensure_init();
+    Context &cx = ctx();
+    cudaStream_t st = cx.stream;
+    const Tableau tab = make_tableau(s, a, b);
+    const int n = e->tensor->view.n;
+    const long ld = e->ld;
+    PoolBuf<double> d_dt(std::max<long>(n_steps, 1)), d_sum((size_t)R * n), d_sq((size_t)R * n);
+    if (n_steps) d_dt.upload(dt, n_steps, st);
+    QGSB_CUDA(cudaEventRecord(cx.ev0, st));
+    if (write_steps == 0 || R == 1) {
+        rk_advance(e->tensor, e->d_y.p, ld, e->N, n_steps, d_dt.p, tab, 0, 1, nullptr);
+        launch_record_moments(e->d_y.p, 1, e->N, n, ld, d_sum.p, d_sq.p);
+    } else {
+        // regular records r = 0 .. R-2 are the states before step r * write_steps; record R-1 is the final state
+        const size_t rec_bytes = (size_t)n * ld * sizeof(double);
+        const long budget = std::max<long>(2, (long)(std::min<size_t>(cx.total_mem / 8, (size_t)8 << 30) / rec_bytes));
+        const long per_chunk = std::min<long>(R - 1, budget - 1);
+        PoolBuf<double> d_rec((size_t)(per_chunk + 1) * n * ld);
+        for (long r0 = 0; r0 < R - 1; r0 += per_chunk) {
+            const long r1 = std::min(R - 1, r0 + per_chunk);
+            const long step0 = r0 * write_steps, step1 = std::min(n_steps, r1 * write_steps);
+            const long steps = step1 - step0, rc = records_for(steps, write_steps);
+            rk_advance(e->tensor, e->d_y.p, ld, e->N, steps, d_dt.p + step0, tab, write_steps, rc, d_rec.p);
+            launch_record_moments(d_rec.p, r1 - r0, e->N, n, ld, d_sum.p + (size_t)r0 * n, d_sq.p + (size_t)r0 * n);
+        }
+        launch_record_moments(e->d_y.p, 1, e->N, n, ld, d_sum.p + (size_t)(R - 1) * n, d_sq.p + (size_t)(R - 1) * n);
+    }
+    QGSB_CUDA(cudaEventRecord(cx.ev1, st));
+    d_sum.download(sum, (size_t)R * n, st);
+    d_sq.download(sumsq, (size_t)R * n, st);
+    QGSB_CUDA(cudaStreamSynchronize(st));
+    if (device_ms) {
+        float ms = 0.f;
+        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+        *device_ms = ms;
+    }
+    QGSB_API_END
+}
+
 void *qgsb_ensemble_device_ptr(qgsb_ensemble *e) { return e ? (void *)e->d_y.p : nullptr; }
 long qgsb_ensemble_ld(const qgsb_ensemble *e) { return e ? e->ld : 0; }
 

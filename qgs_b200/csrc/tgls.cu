@@ -388,6 +388,73 @@ static void launch_transpose_rec(const double *d_in, double *d_out, long R, long
     QGSB_CUDA(cudaGetLastError());
 }
 
+// per-variable sum and sum of squares over members (ensemble statistics), deterministic two-stage reduction:
+// block (i, r, p) sums variable i of record r over its slice of the members, the second kernel adds the slices
+// in a fixed order.  Padding members (>= N) are skipped: they are integrated too and do not stay zero.
+__global__ void moments_partial_kernel(const double *__restrict__ rec, long N, int n, long ld, int parts,
+                                       double *__restrict__ partial)
+{
+    const int i = blockIdx.x, r = blockIdx.y, p = blockIdx.z;
+    const double *y = rec + (size_t)r * n * ld;
+    const long per = (N + parts - 1) / parts;
+    const long lo = (long)p * per, hi = min(N, lo + per);
+    double s1 = 0., s2 = 0.;
+    for (long mbr = lo + threadIdx.x; mbr < hi; mbr += blockDim.x) {
+        const double v = y[tile_base(mbr, n) + (size_t)i * TILE];
+        s1 += v;
+        s2 = fma(v, v, s2);
+    }
+    __shared__ double sh1[256], sh2[256];
+    sh1[threadIdx.x] = s1;
+    sh2[threadIdx.x] = s2;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh1[threadIdx.x] += sh1[threadIdx.x + o];
+            sh2[threadIdx.x] += sh2[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double *out = partial + ((size_t)r * n + i) * 2 * parts;
+        out[p] = sh1[0];
+        out[parts + p] = sh2[0];
+    }
+}
+
+__global__ void moments_final_kernel(const double *__restrict__ partial, long count, int parts, double *__restrict__ sum,
+                                     double *__restrict__ sumsq)
+{
+    const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;   // (record, variable) pair
+    if (q >= count) return;
+    const double *in = partial + (size_t)q * 2 * parts;
+    double s1 = 0., s2 = 0.;
+    for (int p = 0; p < parts; ++p) {
+        s1 += in[p];
+        s2 += in[parts + p];
+    }
+    sum[q] = s1;
+    sumsq[q] = s2;
+}
+
+// sums of R records (R, n, ld tiled) -> device arrays sum, sumsq (R, n)
+void launch_record_moments(const double *d_rec, long R, long N, int n, long ld, double *d_sum, double *d_sumsq)
+{
+    if (R <= 0) return;
+    const int parts = (int)std::max<long>(1, std::min<long>(64, N / 4096));
+    PoolBuf<double> partial((size_t)R * n * 2 * parts);
+    for (long r0 = 0; r0 < R; r0 += 65535) {
+        const long rc = std::min<long>(65535, R - r0);
+        dim3 grid((unsigned)n, (unsigned)rc, (unsigned)parts);
+        moments_partial_kernel<<<grid, 256, 0, ctx().stream>>>(d_rec + (size_t)r0 * n * ld, N, n, ld, parts,
+                                                              partial.p + (size_t)r0 * n * 2 * parts);
+    }
+    const long count = R * n;
+    moments_final_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx().stream>>>(partial.p, count, parts, d_sum, d_sumsq);
+    count_launch(2);
+    QGSB_CUDA(cudaGetLastError());
+}
+
 // per-variable sum and sum of squares over members (ensemble statistics)
 __global__ void moments_kernel(const double *__restrict__ y, long N, int n, double *__restrict__ out)
 {
@@ -667,15 +734,11 @@ int qgsb_ensemble_moments(qgsb_ensemble *e, double *sum, double *sumsq)
     QGSB_REQUIRE(e && sum && sumsq, "null argument");
     ensure_init();
     const int n = e->tensor->view.n;
-    DevBuf<double> d_out((size_t)2 * n);
-    moments_kernel<<<n, 256, 0, ctx().stream>>>(e->d_y.p, e->N, n, d_out.p);
-    count_launch();
-    QGSB_CUDA(cudaGetLastError());
-    std::vector<double> h((size_t)2 * n);
-    d_out.download(h.data(), (size_t)2 * n, ctx().stream);
+    PoolBuf<double> d_out((size_t)2 * n);
+    launch_record_moments(e->d_y.p, 1, e->N, n, e->ld, d_out.p, d_out.p + n);
+    d_out.download(sum, n, ctx().stream);
+    QGSB_CUDA(cudaMemcpyAsync(sumsq, d_out.p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx().stream));
     QGSB_CUDA(cudaStreamSynchronize(ctx().stream));
-    memcpy(sum, h.data(), sizeof(double) * n);
-    memcpy(sumsq, h.data() + n, sizeof(double) * n);
     QGSB_API_END
 }
 

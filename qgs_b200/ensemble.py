@@ -131,6 +131,50 @@ class DeviceEnsemble(object):
         self.time = time[-1] if forward else time[0]
         return ms.value
 
+    def integrate_moments(self, t0, t, dt, forward=True, write_steps=1, b=None, c=None, a=None):
+        """Advance every member from ``t0`` to ``t`` and return ``(time, mean, var)`` of the ensemble at every
+        record the reference would write (integrate.py:190-221, integrator.py:397-424): ``mean`` and ``var`` have
+        shape ``(n_records, n_dim)`` and cover ALL ranks' members.  This is what
+        ``TrajectoriesStatistics.compute_stats`` (qgs/integrators/statistics.py:33-66) yields for the functions
+        ``x`` and ``x**2``, but the ``(n_traj, n_dim, n_records)`` trajectories never leave the device: records
+        are reduced in HBM and only ``2 * n_records * n_dim`` sums reach the host (and the all-reduce)."""
+        if a is None and b is None and c is None:
+            b, c, a = rk4_tableau()
+        time = np.concatenate((np.arange(t0, t, dt), np.full((1,), t)))
+        steps = directed_dt(time, 1 if forward else -1)
+        n_steps = len(steps)
+        ws = int(write_steps)
+        # returned time vector: integrator.py:409-424 (for write_steps == 0 the reference returns time[-1] in both
+        # directions)
+        if ws > 0 and forward:
+            rec_time = time[::ws]
+            if rec_time[-1] != time[-1]:
+                rec_time = np.concatenate((rec_time, time[-1:]))
+        elif ws > 0:
+            rec_time = time[::-ws][::-1]
+            if rec_time[0] != time[0]:
+                rec_time = np.concatenate((time[:1], rec_time))
+        else:
+            rec_time = time[-1:]
+        R = len(rec_time)
+        b, c, a = _lib.f64(b), _lib.f64(c), _lib.f64(a)
+        s1, s2 = np.empty((R, self.n_dim)), np.empty((R, self.n_dim))
+        ms = ctypes.c_double()
+        _lib.check(_lib.load().qgsb_ensemble_integrate_moments(self._handle, n_steps, _lib.dptr(steps), len(b),
+                                                               _lib.dptr(a), _lib.dptr(b), _lib.dptr(c), ws, R,
+                                                               _lib.dptr(s1), _lib.dptr(s2), ctypes.byref(ms)))
+        self.time = time[-1] if forward else time[0]
+        self.last_ms = ms.value
+        packed = np.concatenate((s1.ravel(), s2.ravel(), [float(self.n_traj)]))
+        tot = all_reduce_sums(packed)
+        count = tot[-1]
+        mean = tot[:R * self.n_dim].reshape(R, self.n_dim) / count
+        var = np.maximum(tot[R * self.n_dim:-1].reshape(R, self.n_dim) / count - mean * mean, 0.)
+        if not forward and ws > 0:
+            # the kernel records in integration order; the reference returns the record axis in increasing time
+            mean, var = mean[::-1], var[::-1]
+        return rec_time, mean, var
+
     def states(self):
         """This rank's members as a host array ``(n_local, n_dim)``."""
         out = np.empty((self.n_traj, self.n_dim))

@@ -308,3 +308,50 @@ def test_long_run_climatology_matches_oracle_statistically():
     assert np.sum(z > 4.) <= 1, z
     ratio = g.std(axis=0) / np.maximum(o.std(axis=0), 1e-12)
     assert np.all((ratio > 0.6) & (ratio < 1.6)), ratio
+
+
+# ---- f-2: ensemble statistics without the trajectory dump (statistics.py:33-66) ----------------------------------------
+@pytest.mark.parametrize("ws,forward", [(1, True), (7, True), (0, True), (5, False)])
+def test_record_moments_match_the_trajectory_dump(ws, forward):
+    """mean / variance per record from the device reduction == numpy over the (N, n, R) trajectories that the
+    reference's TrajectoriesStatistics would average (ragged last record, write_steps=0, backward runs)."""
+    from qgs_b200.ensemble import DeviceEnsemble
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator
+    f, Df, T = model("maooam36")
+    rng = np.random.default_rng(5)
+    ic = rng.random((1000, 36)) * 0.01           # not a multiple of the 128-member tile: padding must not leak in
+    integ = RungeKuttaIntegrator()
+    integ.set_func(f)
+    integ.integrate(0., 3.3, 0.1, ic=ic, forward=forward, write_steps=ws)
+    time, traj = integ.get_trajectories()
+    traj = traj.reshape(1000, 36, -1)
+    ens = DeviceEnsemble(f, ic)
+    t2, mean, var = ens.integrate_moments(0., 3.3, 0.1, forward=forward, write_steps=ws)
+    assert np.allclose(np.atleast_1d(time), t2)
+    assert mean.shape == (traj.shape[2], 36)
+    assert np.allclose(mean, traj.mean(axis=0).T, rtol=1e-12, atol=1e-16)
+    assert np.allclose(var, traj.var(axis=0).T, rtol=1e-8, atol=1e-18)
+    # the resident state is the end state of the run
+    end = traj[:, :, -1] if forward else traj[:, :, 0]
+    assert rel(ens.states(), end) < 1e-13
+
+
+def test_trajectories_statistics_class_matches_reference_semantics():
+    """TrajectoriesStatistics.compute_stats (chunked, host functions) and compute_moments (device) agree."""
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator
+    from qgs_b200.integrators.statistics import TrajectoriesStatistics
+    f, Df, T = model("rp")
+    rng = np.random.default_rng(6)
+    ic = rng.random((300, 20)) * 0.1
+    integ = RungeKuttaIntegrator()
+    integ.set_func(f)
+    st = TrajectoriesStatistics()
+    st.set_integrator(integ)
+    st.set_func_list([lambda x: x, lambda x: x ** 2])
+    st.compute_stats(0., 2., 0.1, ic=ic, write_steps=4, num=3)       # 3 chunks of 100 members
+    chunked = st.get_stats()
+    assert chunked.shape == (2, 20, 6)
+    time, mean, var = st.compute_moments(0., 2., 0.1, ic=ic, write_steps=4)
+    assert time.shape == (6,)
+    assert np.allclose(st.get_stats(), chunked, rtol=1e-11, atol=1e-15)   # equal chunk sizes: mean of means == mean
+    assert np.allclose(var, chunked[1] - chunked[0] ** 2, rtol=1e-6, atol=1e-14)
