@@ -132,6 +132,23 @@ QGSB_API int qgsb_lyap_benettin(const qgsb_tensor *t, long n_traj, const double 
                        double *rec_traj, double *rec_exp, double *rec_vec,
                        double *r_all, double *q_all, double *device_ms);
 
+/* Covariant Lyapunov vectors, method of Ginelli et al. -- replaces _compute_clv_gin_jit
+ * (qgs/toolbox/lyapunov.py:1174-1288) with solve_triangular_matrix / normalize_matrix_columns
+ * (qgs/functions/util.py:56-98).  Forward Benettin pass over n_pre (t0..ta), n_time (ta..tb) and n_after (tb..tc)
+ * steps (dt_macro / sub_ptr / sub_dt as for qgsb_lyap_benettin, n_pre + n_time + n_after steps) that keeps every Q
+ * and R of [ta, tc] in HBM, then the backward recursion A <- normalise(R^-1 A + noise_pert * diag(noise)) from tc
+ * to ta starting from am0.  Records follow the time vector ta..tb: n_records of them, the last written first.
+ * am0: host (N, m, m) upper triangular with unit columns; noise: host (N, n_time + n_after, m) or NULL when
+ * noise_pert == 0; dte: host (n_time + 1) step lengths used for the local exponents.  Members are processed in
+ * batches sized to the device memory. */
+QGSB_API int qgsb_clv_ginelli(const qgsb_tensor *t, long n_traj, const double *ic, int n_vec, const double *q0,
+                              const double *r0, long n_pre, long n_time, long n_after, const double *dt_macro,
+                              const long *sub_ptr, const double *sub_dt, int s, const double *a, const double *b,
+                              const double *c, long write_steps, double noise_pert, const double *am0,
+                              const double *noise, const double *dte, long n_records,
+                              double *rec_traj /* (N, n, R) */, double *rec_exp /* (N, m, R) */,
+                              double *rec_vec /* (N, n, m, R) */, double *device_ms);
+
 /* ---- device-resident ensemble (state stays in HBM between calls) ---------
  * State layout in HBM: tiled structure of arrays -- members in tiles of 128, variable i of member m at
  * (m / 128) * (n * 128) + i * 128 + m % 128; ld = n_traj rounded up to 128. */

@@ -269,3 +269,54 @@ def compute_forward_lyap(T, time, posttime, mdt, ic, n_vec, write_steps, adjoint
     final_idx = start[-1] if len(start) > n_pre else 0
     return _lyap(T, ttraj, start, subs, dts, n_pre, final_idx, True, n_vec, write_steps, len(time),
                  adjoint, inverse, b, c, a, q0, r0)
+
+
+# ---- Ginelli backward recursion (numpy restatement) -------------------------------------------------------
+def solve_triangular_matrix(a, b):
+    """qgs/functions/util.py:78-98: column i of x solves the leading (i+1) x (i+1) block."""
+    x = np.zeros_like(a)
+    for i in range(2, a.shape[0] + 1):
+        x[:i, i - 1] = np.linalg.solve(a[:i, :i], b[:i, i - 1])
+    x[0, 0] = b[0, 0] / a[0, 0]
+    return x
+
+
+def normalize_matrix_columns(a):
+    """qgs/functions/util.py:56-75."""
+    an = np.zeros_like(a)
+    norm = np.zeros(a.shape[0])
+    for i in range(a.shape[1]):
+        norm[i] = np.linalg.norm(a[:, i], 2)
+        an[:, i] = a[:, i] / norm[i]
+    return an, norm
+
+
+def clv_ginelli_backward(tmp_traj, tmp_vec, tmp_R, am, noise, noise_pert, tw, tew, write_steps, dte, n_records):
+    """Parts four and five of ``_compute_clv_gin_jit`` (qgs/toolbox/lyapunov.py:1252-1286) for ONE trajectory,
+    with the random start matrix ``am`` and the per-step diagonal ``noise (tew, n_vec)`` passed in instead of
+    drawn from numba's generator.  ``tmp_traj (tw+1, n)``, ``tmp_vec (tw+1, n, m)``, ``tmp_R (tew, m, m)``."""
+    n_dim, n_vec = tmp_vec.shape[1], tmp_vec.shape[2]
+    recorded_traj = np.zeros((n_dim, n_records))
+    recorded_exp = np.zeros((n_vec, n_records))
+    recorded_vec = np.zeros((n_dim, n_vec, n_records))
+    for ti in range(tew - 1, tw, -1):
+        am_new = solve_triangular_matrix(tmp_R[ti], am)
+        for i in range(n_vec):
+            am_new[i, i] += (noise[ti, i] if noise is not None else 0.) * noise_pert
+        am, norm = normalize_matrix_columns(am_new)
+    iw = 1
+    mloc_exp = np.ones(n_vec)
+    for ti in range(tw, -1, -1):
+        am_new = solve_triangular_matrix(tmp_R[ti], am)
+        for i in range(n_vec):
+            am_new[i, i] += (noise[ti, i] if noise is not None else 0.) * noise_pert
+        am, mloc_exp = normalize_matrix_columns(am_new)
+        if write_steps > 0 and np.mod(tw - ti, write_steps) == 0:
+            recorded_traj[:, -iw] = tmp_traj[ti]
+            recorded_exp[:, -iw] = -np.log(np.abs(mloc_exp)) / dte[ti]
+            recorded_vec[:, :, -iw] = tmp_vec[ti] @ am
+            iw += 1
+    recorded_traj[:, 0] = tmp_traj[0]
+    recorded_exp[:, 0] = -np.log(np.abs(mloc_exp)) / dte[0]
+    recorded_vec[:, :, 0] = tmp_vec[0] @ am
+    return recorded_traj, recorded_exp, recorded_vec

@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __
         __syncthreads();
         for (long q = P.sub_ptr[step]; q < P.sub_ptr[step + 1]; ++q) tg_step<RANK>(T, P, S, P.sub_dt[q]);
         // q_new = prop @ q ; q, r = qr(q_new)   (:602-604) -- fm already holds prop @ q by linearity
-        block_qr(n, m, S.fm, S.kms, S.rdiag, S.red, P.r_all ? P.r_all + ((size_t)member * steps + step) * m * m : nullptr);
+        block_qr(n, m, S.fm, S.kms, S.rdiag, S.red, (P.r_all && step >= P.r_first) ? P.r_all + ((size_t)member * (steps - P.r_first) + (step - P.r_first)) * m * m : nullptr);
         // next point of the stored trajectory (:601 / :622): one nonlinear step of length dt_macro
         if (P.forward == 2) {
             // Ginelli forward pass (lyapunov.py:1212-1218): the trajectory follows the micro-steps
@@ -528,6 +528,39 @@ static void set_smem_attr(K kernel, size_t bytes)
         QGSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
+// picks the Benettin kernel for a filled parameter block (device pointers)
+void benettin_dispatch(const qgsb_tensor *t, const Tableau &tab, TgParams &P, DevBuf<double> &scratch)
+{
+    const int m = P.m;
+    cudaStream_t st = ctx().stream;
+    if (pack_tangent_supported(t, tab, m)) {
+        launch_pack_tangent(t, P, true);
+    } else if (reg_tangent_supported(t, tab, m)) {
+        launch_reg_tangent(t, P, true);
+    } else if (t->view.rank == 5) {
+        const size_t bytes = place_matrices(t, P, scratch, 0);
+        set_smem_attr(lyap_kernel<5>, bytes);
+        lyap_kernel<5><<<(unsigned)P.n_members, TG_THREADS, bytes, st>>>(t->view, P);
+        count_launch();
+    } else {
+        const size_t bytes = place_matrices(t, P, scratch, 0);
+        set_smem_attr(lyap_kernel<3>, bytes);
+        lyap_kernel<3><<<(unsigned)P.n_members, TG_THREADS, bytes, st>>>(t->view, P);
+        count_launch();
+    }
+    QGSB_CUDA(cudaGetLastError());
+}
+
+void benettin_fill_common(TgParams &P, const Tableau &tab, long N, int m, int adjoint, double inverse)
+{
+    fill_common(P, tab, N, m, adjoint, inverse);
+}
+
+void launch_transpose_records(const double *d_in, double *d_out, long R, long inner, int flip)
+{
+    launch_transpose_rec(d_in, d_out, R, inner, flip);
+}
+
 }  // namespace qgsb
 
 using namespace qgsb;
@@ -694,21 +727,7 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
         P.final_idx = steps > 0 ? idx[steps - 1] : 0;   // lyapunov.py:549: y[0] of the last pass
         QGSB_CUDA(cudaStreamSynchronize(st));           // fdt / idx host vectors must outlive the copies
     }
-    if (pack_tangent_supported(t, tab, m)) {
-        launch_pack_tangent(t, P, true);
-    } else if (reg_tangent_supported(t, tab, m)) {
-        launch_reg_tangent(t, P, true);
-    } else if (t->view.rank == 5) {
-        const size_t bytes = place_matrices(t, P, scratch, 0);
-        set_smem_attr(lyap_kernel<5>, bytes);
-        lyap_kernel<5><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
-        count_launch();
-    } else {
-        const size_t bytes = place_matrices(t, P, scratch, 0);
-        set_smem_attr(lyap_kernel<3>, bytes);
-        lyap_kernel<3><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
-        count_launch();
-    }
+    benettin_dispatch(t, tab, P, scratch);
     QGSB_CUDA(cudaGetLastError());
     QGSB_CUDA(cudaEventRecord(cx.ev1, st));
     launch_transpose_rec(d_ry.p, d_oy.p, R, (long)N * n, 0);

@@ -562,7 +562,7 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
         const long q0 = P.sub_ptr[step], q1 = P.sub_ptr[step + 1];
         for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, tab, P, S, P.sub_dt[q], col, c, live);
         // q, r = qr(prop @ q)   (:602-604)
-        qr<N>(S, c, live, col, (P.r_all && live) ? P.r_all + ((size_t)member * steps + step) * m * m : nullptr);
+        qr<N>(S, c, live, col, (P.r_all && live && step >= P.r_first) ? P.r_all + ((size_t)member * (steps - P.r_first) + (step - P.r_first)) * m * m : nullptr);
         if (P.forward == 2 || (!P.stored && q1 - q0 == 1 && P.sub_dt[q0] == P.dt_macro[step])) {
             // Ginelli forward pass follows the micro steps; and with a single micro step of the macro length the
             // "stored" trajectory point (:601 / :622) is bit-for-bit the state the tangent step just produced

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(RT) lyap_reg_kernel(TensorView T, const __grid
         for (long q = P.sub_ptr[step]; q < P.sub_ptr[step + 1]; ++q)
             reg_tangent_step<N, ADJ>(T, P, S, P.sub_dt[q], col, active);
         // q, r = qr(prop @ q)   (:602-604)
-        reg_qr<N>(S, m, col, active, P.r_all ? P.r_all + ((size_t)member * steps + step) * m * m : nullptr);
+        reg_qr<N>(S, m, col, active, (P.r_all && step >= P.r_first) ? P.r_all + ((size_t)member * (steps - P.r_first) + (step - P.r_first)) * m * m : nullptr);
         if (P.forward == 2) {                             // Ginelli forward pass: follow the micro steps
             if (tid < N) S.Y[tid] = S.y[tid];
             __syncthreads();

@@ -36,7 +36,8 @@ struct TgParams {
     long final_idx;
     const double *r0;         // (N, m, m) or null
     double *rec_exp;          // (R, N, m)
-    double *r_all;            // (N, steps, m, m) or null
+    double *r_all;            // (N, steps - r_first, m, m) or null: R of every step >= r_first
+    long r_first;
     double *q_all;            // (N, n_rec + 1, n, m) or null
     // --- placement of the big matrices ---
     double *scratch;          // global scratch when shared memory is too small, else null
@@ -100,6 +101,11 @@ struct PackTables {
     const unsigned short *j_slot = nullptr;   // (npos) slot of list position q in the member's Jacobian area
     int stage_bytes = 0;                      // > 0: the kernel copies the tables into shared memory first
 };
+
+// Benettin plumbing shared with clv.cu (tgls.cu)
+void benettin_dispatch(const qgsb_tensor *t, const Tableau &tab, TgParams &P, DevBuf<double> &scratch);
+void benettin_fill_common(TgParams &P, const Tableau &tab, long N, int m, int adjoint, double inverse);
+void launch_transpose_records(const double *d_in, double *d_out, long R, long inner, int flip);
 
 // packed kernels (tgls_pack.cu / tgls_pack.cuh)
 bool pack_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m);

@@ -80,6 +80,41 @@ def benettin(f, fjac, ic, mode, n_vec, q0, r0, pre_times, rec_times, mdt, write_
     return rec_traj, rec_exp, rec_vec
 
 
+def ginelli(f, fjac, ic, n_vec, q0, r0, am0, noise, noise_pert, pretime, time, aftertime, mdt, write_steps, b, c, a):
+    """Run ``qgsb_clv_ginelli``: the whole of ``_compute_clv_gin_jit`` (lyapunov.py:1174-1288) on the device --
+    forward Benettin pass over ``pretime``, ``time`` and ``aftertime`` keeping every ``Q`` and ``R`` in HBM, then
+    the backward recursion ``A <- normalise(R^-1 A)`` from ``tc`` to ``ta``.  ``am0 (N, m, m)`` are the start
+    matrices of the recursion, ``noise (N, tew, m)`` the diagonal perturbations (``None`` when ``noise_pert`` is 0).
+    Returns ``traj (N,n,R), exp (N,m,R), vec (N,n,m,R)`` for the records of ``time``."""
+    tensor = tensor_of(f)
+    if tensor_of(fjac, "fjac") is not tensor:
+        raise ValueError("f and fjac must come from the same create_tendencies() call")
+    if len(aftertime) < 2:
+        raise ValueError("the Ginelli method needs tc > tb")
+    ic = _lib.f64(ic)
+    N, n = ic.shape
+    m = int(n_vec)
+    rec_times = np.concatenate((time[:-1], aftertime))
+    ptr_a, sub_a = _subtimes(pretime, mdt, False)
+    ptr_b, sub_b = _subtimes(rec_times, mdt, False)
+    sub_ptr = np.ascontiguousarray(np.concatenate((ptr_a, ptr_b[1:] + ptr_a[-1])), dtype=np.int64)
+    sub_dt = np.ascontiguousarray(np.concatenate((sub_a, sub_b)))
+    dt_macro = np.ascontiguousarray(np.concatenate((np.diff(pretime), np.diff(rec_times))), dtype=np.float64)
+    dte = np.ascontiguousarray(np.concatenate((np.diff(time), np.full((1,), aftertime[1] - aftertime[0]))))
+    R = n_records_of(time, write_steps)
+    b, c, a = _lib.f64(b), _lib.f64(c), _lib.f64(a)
+    q0, am0 = _lib.f64(q0), _lib.f64(am0)
+    r0 = None if r0 is None else _lib.f64(r0)
+    noise = None if noise is None else _lib.f64(noise)
+    rec_traj, rec_exp, rec_vec = np.empty((N, n, R)), np.empty((N, m, R)), np.empty((N, n, m, R))
+    _lib.check(_lib.load().qgsb_clv_ginelli(
+        tensor.handle, N, _lib.dptr(ic), m, _lib.dptr(q0), _lib.dptr(r0), len(pretime) - 1, len(time) - 1,
+        len(aftertime) - 1, _lib.dptr(dt_macro), sub_ptr.ctypes.data_as(_lib.c_long_p), _lib.dptr(sub_dt), len(b),
+        _lib.dptr(a), _lib.dptr(b), _lib.dptr(c), int(write_steps), float(noise_pert), _lib.dptr(am0),
+        _lib.dptr(noise), _lib.dptr(dte), R, _lib.dptr(rec_traj), _lib.dptr(rec_exp), _lib.dptr(rec_vec), None))
+    return rec_traj, rec_exp, rec_vec
+
+
 def _random_basis(n_traj, n_dim, n_vec, normal=False):
     """qr(random((n_dim, n_vec))) per member (lyapunov.py:592-593; randn for Ginelli, :1200)."""
     q0 = np.empty((n_traj, n_dim, n_vec))
@@ -234,8 +269,8 @@ class LyapProcess(object):
 class CovariantLyapunovsEstimator(_EstimatorBase):
     """Covariant Lyapunov vectors (reference: lyapunov.py:635-1092).
 
-    ``method`` 0: Ginelli et al. (forward Benettin pass on the GPU storing every ``R``, backward
-    triangular solves on the host); ``method`` 1: intersection of the BLV and FLV subspaces (both
+    ``method`` 0: Ginelli et al. (forward Benettin pass storing every ``Q`` and ``R`` in HBM and the backward
+    triangular recursion, both on the GPU: ``qgsb_clv_ginelli``); ``method`` 1: intersection of the BLV and FLV subspaces (both
     Benettin passes on the GPU, SVDs on the host).
     """
 
@@ -287,52 +322,16 @@ class CovariantLyapunovsEstimator(_EstimatorBase):
     # ---- method 0: Ginelli et al., lyapunov.py:1174-1288 ---------------------------------------------
     def _ginelli(self, mdt):
         n_traj, n_dim, n_vec = self.n_traj, self.n_dim, self.n_vec
-        time, aftertime = self._time, self._aftertime
-        tw = len(time) - 1
-        tew = len(time) + len(aftertime) - 2
+        tew = len(self._time) + len(self._aftertime) - 2
         q0, r0 = _random_basis(n_traj, n_dim, n_vec, normal=True)
-        rec_times = np.concatenate((time[:-1], aftertime))
-        # parts 1-3: convergence, then Benettin steps storing the basis (ta..tb) and every R (ta..tc)
-        traj, _, vec, r_all = benettin(self.func, self.func_jac, self.ic, 2, n_vec, q0, r0, self._pretime, rec_times,
-                                       mdt, 1, False, 1., self.b, self.c, self.a, want_r=True)
-        n_pre = len(self._pretime) - 1
-        tmp_R_all = r_all[:, n_pre:]                        # (N, tew, m, m)
-        n_records = self.n_records
-        write_steps = self.write_steps
-        self._recorded_vec = np.zeros((n_traj, n_dim, n_vec, n_records))
-        self._recorded_traj = np.zeros((n_traj, n_dim, n_records))
-        self._recorded_exp = np.zeros((n_traj, n_vec, n_records))
-        dte = np.concatenate((np.diff(time), np.full((1,), aftertime[1] - aftertime[0])))
-        for i_traj in range(n_traj):
-            tmp_R = tmp_R_all[i_traj]
-            tmp_traj = traj[i_traj, :, :tw + 1].T            # (tw+1, n)
-            tmp_vec = np.moveaxis(vec[i_traj, :, :, :tw + 1], 2, 0)   # (tw+1, n, m)
-            # part 4: backward to tb
-            qr = np.linalg.qr(np.random.randn(n_dim, n_vec))
-            am, norm = normalize_matrix_columns(qr[1])
-            for ti in range(tew - 1, tw, -1):
-                am_new = solve_triangular_matrix(tmp_R[ti], am)
-                noise = np.random.randn(n_dim)
-                for i in range(n_vec):
-                    am_new[i, i] += noise[i] * self.noise_pert
-                am, norm = normalize_matrix_columns(am_new)
-            # part 5: backward from tb to ta, saving
-            iw = 1
-            mloc_exp = np.ones(n_vec)
-            for ti in range(tw, -1, -1):
-                am_new = solve_triangular_matrix(tmp_R[ti], am)
-                noise = np.random.randn(n_vec)
-                for i in range(n_vec):
-                    am_new[i, i] += noise[i] * self.noise_pert
-                am, mloc_exp = normalize_matrix_columns(am_new)
-                if write_steps > 0 and np.mod(tw - ti, write_steps) == 0:
-                    self._recorded_traj[i_traj, :, -iw] = tmp_traj[ti]
-                    self._recorded_exp[i_traj, :, -iw] = -np.log(np.abs(mloc_exp[:n_vec])) / dte[ti]
-                    self._recorded_vec[i_traj, :, :, -iw] = tmp_vec[ti] @ am
-                    iw += 1
-            self._recorded_traj[i_traj, :, 0] = tmp_traj[0]
-            self._recorded_exp[i_traj, :, 0] = -np.log(np.abs(mloc_exp[:n_vec])) / dte[0]
-            self._recorded_vec[i_traj, :, :, 0] = tmp_vec[0] @ am
+        # start of the backward recursion (lyapunov.py:1254-1255) and the diagonal noise of every step (:1260, :1271)
+        am0 = np.empty((n_traj, n_vec, n_vec))
+        for i in range(n_traj):
+            am0[i], _ = normalize_matrix_columns(np.linalg.qr(np.random.randn(n_dim, n_vec))[1])
+        noise = np.random.randn(n_traj, tew, n_vec) if self.noise_pert != 0. else None
+        res = ginelli(self.func, self.func_jac, self.ic, n_vec, q0, r0, am0, noise, self.noise_pert, self._pretime,
+                      self._time, self._aftertime, mdt, self.write_steps, self.b, self.c, self.a)
+        self._recorded_traj, self._recorded_exp, self._recorded_vec = res
 
     # ---- method 1: subspace intersection, lyapunov.py:1292-1329 ----------------------------------------
     def _subspaces(self, mdt, backward_vectors, forward_vectors):

@@ -355,3 +355,43 @@ def test_trajectories_statistics_class_matches_reference_semantics():
     assert time.shape == (6,)
     assert np.allclose(st.get_stats(), chunked, rtol=1e-11, atol=1e-15)   # equal chunk sizes: mean of means == mean
     assert np.allclose(var, chunked[1] - chunked[0] ** 2, rtol=1e-6, atol=1e-14)
+
+
+# ---- f-3: Ginelli backward recursion on the device (lyapunov.py:1252-1286) ------------------------------------------------
+@pytest.mark.parametrize("name,n_vec,ws,noise_pert", [("maooam36", 36, 3, 0.), ("rp", 20, 1, 1e-3), ("maooam36", 36, 0, 0.)])
+def test_ginelli_on_device_matches_the_host_recursion(name, n_vec, ws, noise_pert):
+    """qgsb_clv_ginelli == (forward Benettin pass with every Q, R pulled to the host) + the numpy restatement of
+    the reference's backward recursion, for the same start matrices and noise."""
+    import oracle
+    from qgs_b200.toolbox.lyapunov import benettin, ginelli, n_records_of
+    f, Df, T = model(name)
+    n = f.ndim
+    b, c, a = oracle.rk4_tableau()
+    rng = np.random.default_rng(11)
+    N = 5
+    ic = rng.random((N, n)) * (0.01 if name == "maooam36" else 0.1)
+    pretime = np.concatenate((np.arange(0., 1., 0.1), [1.]))
+    time = np.concatenate((np.arange(1., 3.05, 0.1), [3.05]))          # ragged last step
+    aftertime = np.concatenate((np.arange(3.05, 4.5, 0.1), [4.5]))
+    tw, tew = len(time) - 1, len(time) + len(aftertime) - 2
+    q0 = np.stack([np.linalg.qr(rng.standard_normal((n, n_vec)))[0] for _ in range(N)])
+    am0 = np.stack([oracle.normalize_matrix_columns(np.linalg.qr(rng.standard_normal((n, n_vec)))[1])[0]
+                    for _ in range(N)])
+    noise = rng.standard_normal((N, tew, n_vec)) if noise_pert else None
+    gt, ge, gv = ginelli(f, Df, ic, n_vec, q0, None, am0, noise, noise_pert, pretime, time, aftertime, 0.1, ws,
+                         b, c, a)
+    rec_times = np.concatenate((time[:-1], aftertime))
+    traj, _, vec, r_all = benettin(f, Df, ic, 2, n_vec, q0, None, pretime, rec_times, 0.1, 1, False, 1., b, c, a,
+                                   want_r=True)
+    R = n_records_of(time, ws)
+    dte = np.concatenate((np.diff(time), [aftertime[1] - aftertime[0]]))
+    for i in range(N):
+        tmp_R = r_all[i, len(pretime) - 1:]
+        tmp_traj = traj[i, :, :tw + 1].T
+        tmp_vec = np.moveaxis(vec[i, :, :, :tw + 1], 2, 0)
+        ot, oe, ov = oracle.clv_ginelli_backward(tmp_traj, tmp_vec, tmp_R, am0[i], None if noise is None else noise[i],
+                                                 noise_pert, tw, tew, ws, dte, R)
+        assert gt.shape[1:] == ot.shape
+        assert rel(gt[i], ot) < 1e-13
+        assert rel(gv[i], ov) < 1e-9, (i, rel(gv[i], ov))
+        assert np.max(np.abs(ge[i] - oe)) < 1e-9 * max(1., np.max(np.abs(oe)))
