@@ -24,6 +24,7 @@
 // path; the generic kernels of tgls.cu serve everything else.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tgls_shared.cuh"
@@ -183,7 +184,7 @@ __device__ __forceinline__ void jac_build(const TensorView &T, const PackTables 
             jv[tab.j_slot[q]] = acc;
         }
     } else if (tab.EJ == 2) {
-#pragma unroll 2
+#pragma unroll 4
         for (int q = c; q < npos; q += m) {
             const PEnt e0 = tab.j_ent[q], e1 = tab.j_ent[npos + q];
             double acc = xs[e0.a] * e0.v;
@@ -499,7 +500,7 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
 // ---- Benettin loop (lyapunov.py:471-632) ---------------------------------------------------------------------------------
 template <int N, class Prod>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
-lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride)
+lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride, int qr_remap)
 {
     extern __shared__ __align__(16) double smem_pack[];
     const PackTables tab = stage_tables(tab_g, smem_pack + (size_t)G * stride, N);
@@ -511,6 +512,15 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
     const int nm = N * m;
     const long steps = P.n_pre + P.n_rec;
     const long R = P.n_records;
+    // For the QR the columns are dealt out a second way, member index fastest: a warp then holds the same few
+    // columns of all the members, so the warps whose columns are already finished skip a reflector altogether
+    // (with the consecutive layout every warp has live columns until the very end).  The tangent steps keep the
+    // consecutive layout, whose broadcast reads of J hit one or two addresses per warp.
+    const bool remap = qr_remap != 0;
+    const int cq = remap ? t / G : c, gq = remap ? t - cq * G : g;
+    const long memberq = (long)blockIdx.x * G + gq;
+    const bool liveq = remap ? (cq < m && memberq < P.n_members) : live;
+    const Mem<N> Sq = carve<N>(smem_pack + (size_t)(liveq ? gq : 0) * stride, Prod::JV, m);
     double col[N];
     init_member<N, Prod>(S, c, live);
     if (live)
@@ -562,7 +572,25 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
         const long q0 = P.sub_ptr[step], q1 = P.sub_ptr[step + 1];
         for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, tab, P, S, P.sub_dt[q], col, c, live);
         // q, r = qr(prop @ q)   (:602-604)
-        qr<N>(S, c, live, col, (P.r_all && live && step >= P.r_first) ? P.r_all + ((size_t)member * (steps - P.r_first) + (step - P.r_first)) * m * m : nullptr);
+        {
+            double *Rout = (P.r_all && liveq && step >= P.r_first)
+                               ? P.r_all + ((size_t)memberq * (steps - P.r_first) + (step - P.r_first)) * m * m : nullptr;
+            if (remap) {                     // hand the columns over through the fm area (tangent_step left them there)
+                __syncthreads();
+                if (liveq) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) col[i] = Sq.fm[i * m + cq];
+                }
+            }
+            qr<N>(Sq, cq, liveq, col, Rout);
+            if (remap) {
+                __syncthreads();
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) col[i] = S.fm[i * m + c];
+                }
+            }
+        }
         if (P.forward == 2 || (!P.stored && q1 - q0 == 1 && P.sub_dt[q0] == P.dt_macro[step])) {
             // Ginelli forward pass follows the micro steps; and with a single micro step of the macro length the
             // "stored" trajectory point (:601 / :622) is bit-for-bit the state the tangent step just produced
@@ -646,7 +674,17 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
         kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, tab, geo.G, geo.stride);
         return cudaGetLastError();
     };
-    if (lyap) return P.adjoint ? go(lyap_kernel<N, Adj>) : go(lyap_kernel<N, Fwd>);
+    auto go_lyap = [&](auto kernel) -> cudaError_t {
+        if (geo.smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem);
+            if (e != cudaSuccess) return e;
+        }
+        const char *env = getenv("QGSB_QR_REMAP");
+        const int remap = env ? (env[0] != '0') : 1;
+        kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, tab, geo.G, geo.stride, remap);
+        return cudaGetLastError();
+    };
+    if (lyap) return P.adjoint ? go_lyap(lyap_kernel<N, Adj>) : go_lyap(lyap_kernel<N, Fwd>);
     return P.adjoint ? go(tgls_kernel<N, Adj>) : go(tgls_kernel<N, Fwd>);
 }
 
