@@ -15,11 +15,12 @@ STEPS_PER_LAUNCH classic-RK4 time steps of dt = 0.1 with write_steps = 0 -- one 
             are inside the timed region, every step.
   roofline  FP64: algorithmic flops (4132 per member-step) / launch time against the
             DFMA peak measured on this device in this run (MEASURED_PEAKS.json has no FP64 entry).
-  cpu_baseline  the CPU oracle port (oracle/qgs_oracle.c, all host threads) on a bounded sample.
+  cpu_baseline  the UNMODIFIED reference (numba + its multiprocessing pool, all host cores) from the git-ignored
+            baseline/_ref install on a bounded sample; the C oracle port (oracle/qgs_oracle.c, all host threads) is
+            reported next to it as cpu_port, and replaces it (kind "port") when baseline/_ref or numba is missing.
 
---impl reference times the CPU implementation of the path (the oracle port of the reference's
-_integrate_runge_kutta_jit + worker pool; the Python reference itself cannot travel to the GPU box).
-Under torchrun rank 0 alone runs it.
+--impl reference times the reference's own CPU implementation of the path: RungeKuttaIntegrator from
+baseline/_ref through its public API (else the oracle port).  Under torchrun rank 0 alone runs it.
 """
 import argparse
 import json
@@ -147,16 +148,105 @@ def cpu_rate(target_seconds=12.0):
                       % (members, STEPS_PER_LAUNCH, cores, wall)}, members, wall
 
 
+REF_DIR = os.path.join(REPO, "baseline", "_ref")
+
+
+class ReferenceNumba(object):
+    """The UNMODIFIED reference (pip-installed from /root/reference into the git-ignored baseline/_ref, see
+    DESIGN.md section 6) on its own stock path: QgParams of qgs_maooam.py:78-92 -> create_tendencies ->
+    RungeKuttaIntegrator(num_threads = host cores).integrate(..., write_steps=0) -> get_trajectories().
+    pydata `sparse` / `pebble`, which the reference imports while it BUILDS the tensor, are absent from the image;
+    qgs_b200.compat provides stand-ins for that setup step only -- f, the RK4 loop and the worker pool are the
+    reference's numba / multiprocessing code."""
+
+    def __init__(self):
+        if not os.path.isdir(os.path.join(REF_DIR, "qgs")):
+            raise RuntimeError("baseline/_ref/qgs is not installed")
+        import warnings
+        warnings.filterwarnings("ignore")
+        from qgs_b200 import compat
+        compat.install()
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import numba  # noqa: F401  (fail early when the reference's JIT is missing)
+        from qgs.params.params import QgParams
+        from qgs.functions.tendencies import create_tendencies
+        from qgs.integrators.integrator import RungeKuttaIntegrator
+        import qgs
+        if os.path.abspath(os.path.dirname(qgs.__file__)) != os.path.abspath(os.path.join(REF_DIR, "qgs")):
+            raise RuntimeError("qgs resolved to %s, not to baseline/_ref" % qgs.__file__)
+        p = QgParams()
+        p.set_atmospheric_channel_fourier_modes(2, 2)
+        p.set_oceanic_basin_fourier_modes(2, 4)
+        p.set_params({'kd': 0.0290, 'kdp': 0.0290, 'n': 1.5, 'r': 1.e-7, 'h': 136.5, 'd': 1.1e-7})
+        p.atemperature_params.set_params({'eps': 0.7, 'T0': 289.3, 'hlambda': 15.06, })
+        p.gotemperature_params.set_params({'gamma': 5.6e8, 'T0': 301.46})
+        p.atemperature_params.set_insolation(103.3333, 0)
+        p.gotemperature_params.set_insolation(310., 0)
+        f, Df = create_tendencies(p)
+        self.cores = os.cpu_count() or 1
+        self.integrator = RungeKuttaIntegrator(num_threads=self.cores)
+        self.integrator.set_func(f)
+        # every worker JIT-compiles the integrator on its first trajectory
+        self.run(4 * self.cores, 10)
+
+    def run(self, members, steps):
+        ic = initial_conditions(0, members)
+        t0 = time.perf_counter()
+        self.integrator.integrate(0., steps * DT, DT, ic=ic, write_steps=0)
+        self.integrator.get_trajectories()
+        return time.perf_counter() - t0
+
+    def rate(self, target_seconds):
+        wall = self.run(8 * self.cores, STEPS_PER_LAUNCH)
+        est = 8 * self.cores * STEPS_PER_LAUNCH / wall
+        members = int(min(max(est * target_seconds / STEPS_PER_LAUNCH // self.cores * self.cores, self.cores), 1 << 16))
+        wall = self.run(members, STEPS_PER_LAUNCH)
+        return {"value": members * STEPS_PER_LAUNCH / wall, "unit": UNIT, "cores": self.cores, "kind": "reference",
+                "sample": "%d members x %d RK4 steps (write_steps=0), unmodified qgs RungeKuttaIntegrator (numba + %d "
+                          "worker processes) from baseline/_ref, %.1f s wall" % (members, STEPS_PER_LAUNCH, self.cores,
+                                                                               wall)}, members, wall
+
+    def close(self):
+        try:
+            self.integrator.terminate()
+        except Exception:
+            pass
+
+
+def reference_or_port(target_seconds):
+    """(baseline dict, members, wall): the reference's numba path when baseline/_ref can run here, else the C port."""
+    if os.environ.get("QGSB_BENCH_CPU", "") != "port":
+        ref = None
+        try:
+            ref = ReferenceNumba()
+            return ref.rate(target_seconds)
+        except Exception as exc:  # missing install / numba: say so and use the port
+            sys.stderr.write("reference numba path unavailable (%s); timing the C port instead\n" % (exc,))
+        finally:
+            if ref is not None:
+                ref.close()
+    return cpu_rate(target_seconds)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     rates, walls = [], []
     base = None
+    ref = None
+    if os.environ.get("QGSB_BENCH_CPU", "") != "port":
+        try:
+            ref = ReferenceNumba()
+        except Exception as exc:
+            sys.stderr.write("reference numba path unavailable (%s); timing the C port instead\n" % (exc,))
     for i in range(args.warmup + args.steps):
-        base, members, wall = cpu_rate(target_seconds=6.0)
+        base, members, wall = ref.rate(6.0) if ref is not None else cpu_rate(target_seconds=6.0)
         if i >= args.warmup:
             rates.append(base["value"])
             walls.append(wall)
+    if ref is not None:
+        ref.close()
     value = float(np.mean(rates))
     base["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -276,7 +366,10 @@ def run_ours(args, rank, world, local_rank):
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except (ValueError, OSError):
                 traffic = None
-        base, _, _ = cpu_rate()
+        base, _, _ = reference_or_port(10.0)
+        port = None
+        if base.get("kind") == "reference":
+            port, _, _ = cpu_rate(6.0)      # the C oracle port as a second data point (it is faster than numba)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -286,7 +379,7 @@ def run_ours(args, rank, world, local_rank):
                              "peak_source": "DFMA micro-benchmark measured on this device in this run "
                                             "(qgsb_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                              "flops_per_member_step": FLOPS_PER_MEMBER_STEP, "kernel": "rk_chain_kernel (maooam36)"},
-                "cpu_baseline": base,
+                "cpu_baseline": base, "cpu_port": port,
                 "e2e": {"value": member_steps / e2e_s, "unit": UNIT,
                         "h2d_bytes_per_step": members * NDIM * 8 + n_steps * 8,
                         "d2h_bytes_per_step": members * NDIM * 8,

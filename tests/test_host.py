@@ -280,7 +280,7 @@ def test_sharded_moments_and_gather_gloo_world_size_2(tmp_path):
 def test_bench_reference_arm_contract():
     """--impl reference prints one JSON line with the contract's keys (bounded CPU sample)."""
     import json
-    env = dict(os.environ, QGSB_BENCH_CPU_SECONDS="0.5")
+    env = dict(os.environ, QGSB_BENCH_CPU_SECONDS="0.5", QGSB_BENCH_CPU="port")     # the port leg: fast and always there
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr
@@ -313,3 +313,32 @@ def test_overlay_serves_hot_path_modules_and_leaves_the_rest_to_the_reference():
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(REPO, "overlay"), ref]))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and "overlay ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_reference_arm_runs_the_installed_reference_and_agrees_with_the_oracle():
+    """bench.py --impl reference drives the UNMODIFIED reference from baseline/_ref (numba f + RK4 + worker pool);
+    the same object integrates a few members here and must agree with the C oracle -- a live pin of the oracle."""
+    import importlib.util
+    ref_dir = os.path.join(REPO, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "qgs")) or importlib.util.find_spec("numba") is None:
+        pytest.skip("baseline/_ref is not installed (python -m pip install --no-index --no-build-isolation --no-deps "
+                    "--target baseline/_ref /root/reference)")
+    code = (
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "os.cpu_count = lambda: 2\n"
+        "import bench, oracle\n"
+        "ref = bench.ReferenceNumba()\n"
+        "ic = bench.initial_conditions(0, 6)\n"
+        "ref.integrator.integrate(0., 5., 0.1, ic=ic, write_steps=5)\n"
+        "t, traj = ref.integrator.get_trajectories()\n"
+        "ref.close()\n"
+        "T = oracle.Tensor.from_npz(bench.TENSOR)\n"
+        "b, c, a = oracle.rk4_tableau()\n"
+        "tv = np.concatenate((np.arange(0., 5., 0.1), [5.]))\n"
+        "o = oracle.integrate_runge_kutta_jit(T, tv, ic, 1, 5, b, c, a)\n"
+        "err = np.max(np.abs(traj - o)) / np.max(np.abs(o))\n"
+        "assert traj.shape == o.shape and err < 1e-13, err\n"
+        "print('reference arm ok', err)\n" % REPO)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=REPO)
+    assert out.returncode == 0 and "reference arm ok" in out.stdout, out.stderr[-3000:]
