@@ -122,7 +122,8 @@ QGSB_API int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long n_traj, const dou
  * q0 (N, n, n_vec), r0 (N, n_vec, n_vec) or NULL: the start basis (the reference draws
  * qr(random((n_dim, n_vec))), lyapunov.py:592-593, on the host side).
  * rec_* follow _compute_*_lyap_traj_jit's return values: traj (N, n, R), exp (N, n_vec, R),
- * vec (N, n, n_vec, R).  r_all (N, n_steps_total, n_vec, n_vec) or NULL stores every R factor and
+ * vec (N, n, n_vec, R); rec_vec may be NULL when only the exponents are wanted (no vector records are kept
+ * or copied).  r_all (N, n_steps_total, n_vec, n_vec) or NULL stores every R factor and
  * q_all (N, n_rec + 1, n, n_vec) or NULL the basis at every recorded-phase point (Ginelli, :1220-1250). */
 QGSB_API int qgsb_lyap_benettin(const qgsb_tensor *t, long n_traj, const double *ic, int forward, int n_vec,
                        const double *q0, const double *r0, long n_pre, long n_rec,

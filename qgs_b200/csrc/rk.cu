@@ -738,16 +738,68 @@ int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_ste
     const long ld = round_up(N, TILE);
     PoolBuf<double> d_ic((size_t)N * n), d_y((size_t)n * ld), d_dt(std::max<long>(n_steps, 1));
     PoolBuf<double> d_rec, d_out((size_t)N * n * R);
-    d_ic.upload(ic, (size_t)N * n, st);
     if (n_steps) d_dt.upload(dt, n_steps, st);
-    launch_aos_to_soa(d_ic.p, d_y.p, N, n, ld);
     if (R == 1) {
-        // write_steps == 0 (or a single time point): only the end state is returned (integrate.py:221)
+        // write_steps == 0 (or a single time point): only the end state is returned (integrate.py:221).
+        // Large ensembles go through in chunks of whole waves of thread blocks so that the upload of chunk k+1
+        // and the download of chunk k-1 overlap the integration of chunk k (two copy streams, pinned host
+        // buffers make the copies truly asynchronous; members are independent, so the results are unchanged).
+        const long chunk = (long)cx.sm_count * 2 * TILE * 4;
+        if (N >= 2 * chunk) {
+            static cudaStream_t s_in = nullptr, s_out = nullptr;
+            if (!s_in) {
+                QGSB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+                QGSB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+            }
+            const long n_chunks = (N + chunk - 1) / chunk;
+            std::vector<cudaEvent_t> up(n_chunks), done(n_chunks);
+            for (long k = 0; k < n_chunks; ++k) {
+                QGSB_CUDA(cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming));
+                QGSB_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+            }
+            QGSB_CUDA(cudaStreamSynchronize(st));      // d_dt upload and earlier work on the pool buffers
+            for (long k = 0; k < n_chunks; ++k) {
+                const long m0 = k * chunk, nk = std::min(chunk, N - m0);
+                QGSB_CUDA(cudaMemcpyAsync(d_ic.p + (size_t)m0 * n, ic + (size_t)m0 * n, sizeof(double) * nk * n,
+                                          cudaMemcpyHostToDevice, s_in));
+                QGSB_CUDA(cudaEventRecord(up[k], s_in));
+            }
+            QGSB_CUDA(cudaEventRecord(cx.ev0, st));
+            for (long k = 0; k < n_chunks; ++k) {
+                const long m0 = k * chunk, nk = std::min(chunk, N - m0), ldk = round_up(nk, TILE);
+                double *yk = d_y.p + (size_t)m0 * n;   // chunk starts on a tile boundary: its tiles are contiguous
+                QGSB_CUDA(cudaStreamWaitEvent(st, up[k], 0));
+                launch_aos_to_soa(d_ic.p + (size_t)m0 * n, yk, nk, n, ldk);
+                rk_advance(t, yk, ldk, nk, n_steps, d_dt.p, tab, 0, 1, nullptr);
+                launch_soa_to_aos(yk, d_out.p + (size_t)m0 * n, nk, n, ldk);
+                QGSB_CUDA(cudaEventRecord(done[k], st));
+                QGSB_CUDA(cudaStreamWaitEvent(s_out, done[k], 0));
+                QGSB_CUDA(cudaMemcpyAsync(traj + (size_t)m0 * n, d_out.p + (size_t)m0 * n, sizeof(double) * nk * n,
+                                          cudaMemcpyDeviceToHost, s_out));
+            }
+            QGSB_CUDA(cudaEventRecord(cx.ev1, st));
+            QGSB_CUDA(cudaStreamSynchronize(s_out));
+            QGSB_CUDA(cudaStreamSynchronize(st));
+            for (long k = 0; k < n_chunks; ++k) {
+                cudaEventDestroy(up[k]);
+                cudaEventDestroy(done[k]);
+            }
+            if (device_ms) {
+                float ms = 0.f;
+                QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+                *device_ms = ms;
+            }
+            return 0;
+        }
+        d_ic.upload(ic, (size_t)N * n, st);
+        launch_aos_to_soa(d_ic.p, d_y.p, N, n, ld);
         QGSB_CUDA(cudaEventRecord(cx.ev0, st));
         rk_advance(t, d_y.p, ld, N, n_steps, d_dt.p, tab, 0, 1, nullptr);
         QGSB_CUDA(cudaEventRecord(cx.ev1, st));
         launch_soa_to_aos(d_y.p, d_out.p, N, n, ld);
     } else {
+        d_ic.upload(ic, (size_t)N * n, st);
+        launch_aos_to_soa(d_ic.p, d_y.p, N, n, ld);
         d_rec.alloc((size_t)R * n * ld);
         QGSB_CUDA(cudaEventRecord(cx.ev0, st));
         rk_advance(t, d_y.p, ld, N, n_steps, d_dt.p, tab, write_steps, R, d_rec.p);

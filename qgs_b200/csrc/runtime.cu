@@ -722,8 +722,20 @@ int qgsb_tendencies(const qgsb_tensor *t, long N, const double *x, double *out)
     ensure_init();
     cudaStream_t s = ctx().stream;
     const int n = t->view.n;
-    DevBuf<double> d_x((size_t)N * n), d_out((size_t)N * n);
+    PoolBuf<double> d_x((size_t)N * n), d_out((size_t)N * n);
     d_x.upload(x, (size_t)N * n, s);
+    if (t->spec && t->use_spec && t->spec->tendencies && N >= 512) {
+        // batches: the generated straight-line kernel (state in registers) on the tiled layout
+        const long ld = round_up(N, TILE);
+        PoolBuf<double> d_xs((size_t)n * ld), d_os((size_t)n * ld);
+        launch_aos_to_soa(d_x.p, d_xs.p, N, n, ld);
+        QGSB_CUDA(t->spec->tendencies(d_xs.p, d_os.p, ld, N, s));
+        count_launch();
+        launch_soa_to_aos(d_os.p, d_out.p, N, n, ld);
+        d_out.download(out, (size_t)N * n, s);
+        QGSB_CUDA(cudaStreamSynchronize(s));
+        return 0;
+    }
     const long total = N * n;
     const int threads = 128;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);

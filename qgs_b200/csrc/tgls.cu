@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __
                 double *rv = P.rec_fm + ((size_t)col * P.n_members + member) * nm;
                 double *re = P.rec_exp + ((size_t)col * P.n_members + member) * m;
                 for (int r = tid; r < n; r += TG_THREADS) ry[r] = S.Y[r];
-                for (int q = tid; q < nm; q += TG_THREADS) rv[q] = S.fm[q];
+                if (P.rec_fm)
+                    for (int q = tid; q < nm; q += TG_THREADS) rv[q] = S.fm[q];
                 if (tid < m) re[tid] = mexp;
                 ++iw;
             }
@@ -349,7 +350,8 @@ __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __
         double *rv = P.rec_fm + ((size_t)col * P.n_members + member) * nm;
         double *re = P.rec_exp + ((size_t)col * P.n_members + member) * m;
         for (int r = tid; r < n; r += TG_THREADS) ry[r] = S.Y[r];
-        for (int q = tid; q < nm; q += TG_THREADS) rv[q] = S.fm[q];
+        if (P.rec_fm)
+            for (int q = tid; q < nm; q += TG_THREADS) rv[q] = S.fm[q];
         if (tid < m) re[tid] = mexp;
         if (P.q_all) {
             double *qa = P.q_all + ((size_t)member * (P.n_rec + 1) + P.n_rec) * nm;
@@ -645,7 +647,7 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
 {
     (void)c;
     QGSB_API_BEGIN
-    QGSB_REQUIRE(t && ic && q0 && dt_macro && sub_ptr && sub_dt && rec_traj && rec_exp && rec_vec, "null argument");
+    QGSB_REQUIRE(t && ic && q0 && dt_macro && sub_ptr && sub_dt && rec_traj && rec_exp, "null argument");
     QGSB_REQUIRE(N >= 1, "need at least one trajectory");
     QGSB_REQUIRE(forward >= 0 && forward <= 2, "mode must be 0 (BLV), 1 (FLV) or 2 (BLV following the micro-steps)");
     QGSB_REQUIRE(n_vec >= 1 && n_vec <= t->view.n, "n_vec must be in 1..n_dim");
@@ -669,8 +671,9 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
     DevBuf<double> d_y((size_t)N * n), d_q((size_t)N * nm), d_dtm(std::max<long>(steps, 1)), d_sub(std::max<long>(n_sub, 1));
     DevBuf<long> d_ptr(steps + 1), d_idx(std::max<long>(steps, 1));
     DevBuf<double> d_r0, d_rall, d_qall, d_stored, d_ys, scratch;
-    DevBuf<double> d_ry((size_t)R * N * n), d_rv((size_t)R * N * nm), d_re((size_t)R * N * m);
-    DevBuf<double> d_oy((size_t)R * N * n), d_ov((size_t)R * N * nm), d_oe((size_t)R * N * m);
+    // rec_vec == NULL: the vectors are not recorded (spectrum-only runs skip 8 n m bytes per member and record)
+    DevBuf<double> d_ry((size_t)R * N * n), d_rv(rec_vec ? (size_t)R * N * nm : 0), d_re((size_t)R * N * m);
+    DevBuf<double> d_oy((size_t)R * N * n), d_ov(rec_vec ? (size_t)R * N * nm : 0), d_oe((size_t)R * N * m);
     d_y.upload(ic, (size_t)N * n, st);
     d_q.upload(q0, (size_t)N * nm, st);
     if (steps) d_dtm.upload(dt_macro, steps, st);
@@ -689,7 +692,7 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
     P.y = d_y.p;
     P.fm = d_q.p;
     P.rec_y = d_ry.p;
-    P.rec_fm = d_rv.p;
+    P.rec_fm = rec_vec ? d_rv.p : nullptr;
     P.rec_exp = d_re.p;
     if (r0) {
         d_r0.alloc((size_t)N * m * m);
@@ -731,10 +734,10 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
     QGSB_CUDA(cudaGetLastError());
     QGSB_CUDA(cudaEventRecord(cx.ev1, st));
     launch_transpose_rec(d_ry.p, d_oy.p, R, (long)N * n, 0);
-    launch_transpose_rec(d_rv.p, d_ov.p, R, (long)N * (long)nm, 0);
+    if (rec_vec) launch_transpose_rec(d_rv.p, d_ov.p, R, (long)N * (long)nm, 0);
     launch_transpose_rec(d_re.p, d_oe.p, R, (long)N * m, 0);
     d_oy.download(rec_traj, (size_t)R * N * n, st);
-    d_ov.download(rec_vec, (size_t)R * N * nm, st);
+    if (rec_vec) d_ov.download(rec_vec, (size_t)R * N * nm, st);
     d_oe.download(rec_exp, (size_t)R * N * m, st);
     if (r_all) d_rall.download(r_all, (size_t)N * steps * m * m, st);
     if (q_all) d_qall.download(q_all, (size_t)N * (n_rec + 1) * nm, st);

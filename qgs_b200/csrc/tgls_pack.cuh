@@ -559,8 +559,10 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
                     double *rv = P.rec_fm + ((size_t)rc * P.n_members + member) * nm;
                     double *re = P.rec_exp + ((size_t)rc * P.n_members + member) * m;
                     for (int r = c; r < N; r += m) ry[r] = S.Y[r];
+                    if (P.rec_fm) {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) rv[i * m + c] = col[i];
+                        for (int i = 0; i < N; ++i) rv[i * m + c] = col[i];
+                    }
                     re[c] = mexp;
                 }
                 ++iw;
@@ -610,8 +612,10 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
         double *rv = P.rec_fm + ((size_t)rc * P.n_members + member) * nm;
         double *re = P.rec_exp + ((size_t)rc * P.n_members + member) * m;
         for (int r = c; r < N; r += m) ry[r] = S.Y[r];
+        if (P.rec_fm) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) rv[i * m + c] = col[i];
+            for (int i = 0; i < N; ++i) rv[i * m + c] = col[i];
+        }
         re[c] = mexp;
         if (P.q_all) {
             double *qa = P.q_all + ((size_t)member * (P.n_rec + 1) + P.n_rec) * nm;

@@ -349,8 +349,10 @@ __global__ void __launch_bounds__(RT) lyap_reg_kernel(TensorView T, const __grid
                 double *re = P.rec_exp + ((size_t)c * P.n_members + member) * m;
                 if (tid < N) ry[tid] = S.Y[tid];
                 if (active) {
+                    if (P.rec_fm) {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) rv[i * m + tid] = col[i];
+                        for (int i = 0; i < N; ++i) rv[i * m + tid] = col[i];
+                    }
                     re[tid] = mexp;
                 }
                 ++iw;
@@ -382,8 +384,10 @@ __global__ void __launch_bounds__(RT) lyap_reg_kernel(TensorView T, const __grid
         double *re = P.rec_exp + ((size_t)c * P.n_members + member) * m;
         if (tid < N) ry[tid] = S.Y[tid];
         if (active) {
+            if (P.rec_fm) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) rv[i * m + tid] = col[i];
+                for (int i = 0; i < N; ++i) rv[i * m + tid] = col[i];
+            }
             re[tid] = mexp;
             if (P.q_all) {
                 double *qa = P.q_all + ((size_t)member * (P.n_rec + 1) + P.n_rec) * nm;

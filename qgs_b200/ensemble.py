@@ -191,3 +191,50 @@ class DeviceEnsemble(object):
         s1, s2 = self.local_sums()
         mean, var, _ = combine_moments(s1, s2, self.n_traj)
         return mean, var
+
+
+def spectrum_from_local_exponents(local_exp, n_global=None):
+    """Ensemble- and time-mean Lyapunov spectrum with its standard error from the local exponents
+    ``(n_local, n_vec, n_records)`` of THIS rank's members (``LyapunovsEstimator.get_lyapunovs()[2]``); the
+    partial sums of all ranks are combined with one all-reduce of ``2 * n_vec + 1`` doubles.  The standard error
+    is over members (each member's time mean is one sample)."""
+    local_exp = np.asarray(local_exp, dtype=np.float64)
+    if local_exp.ndim == 2:
+        local_exp = local_exp[None]
+    per_member = local_exp.mean(axis=2)                       # (n_local, n_vec)
+    packed = np.concatenate((per_member.sum(axis=0), (per_member ** 2).sum(axis=0), [float(per_member.shape[0])]))
+    tot = all_reduce_sums(packed)
+    m = local_exp.shape[1]
+    count = tot[-1]
+    mean = tot[:m] / count
+    var = np.maximum(tot[m:2 * m] / count - mean * mean, 0.)
+    sem = np.sqrt(var / max(count - 1., 1.))
+    if n_global is not None and int(round(count)) != int(n_global):
+        raise RuntimeError("spectrum combined %d members, expected %d" % (int(round(count)), int(n_global)))
+    return mean, sem
+
+
+def sharded_lyapunov_spectrum(f, Df, ic, t0, tw, t, dt, mdt, n_vec=None, write_steps=1, forward=False):
+    """Lyapunov spectrum of an ensemble sharded over the ranks of the current ``torch.distributed`` group
+    (BASELINE.json config "MAOOAM-36 Lyapunov spectrum ..., 8-GPU sharded ensemble").  Every rank runs
+    ``LyapunovsEstimator.compute_lyapunovs`` (lyapunov.py:232-358) on ITS block of ``ic`` -- members are
+    independent and carry their own basis, so nothing is exchanged during the Benettin loop -- and the
+    member/time-mean exponents are combined at the end.  Returns ``(mean, standard_error, local_result)`` where
+    ``local_result`` is this rank's ``get_lyapunovs()`` tuple."""
+    from qgs_b200.toolbox.lyapunov import LyapunovsEstimator
+    ic = np.atleast_2d(np.asarray(ic, dtype=np.float64))
+    dist = _dist()
+    world, rank = (dist.get_world_size(), dist.get_rank()) if dist is not None else (1, 0)
+    lo, hi = shard_bounds(ic.shape[0], world, rank)
+    if hi <= lo:
+        raise ValueError("this rank received no members (fewer members than ranks)")
+    est = LyapunovsEstimator()
+    est.set_func(f, Df)
+    est.compute_lyapunovs(t0, tw, t, dt, mdt, ic=ic[lo:hi], write_steps=write_steps, n_vec=n_vec, forward=forward,
+                          vectors=False)
+    res = est.get_lyapunovs()
+    exps = np.asarray(res[2])
+    m = est.n_vec
+    exps = exps.reshape(hi - lo, m, -1)
+    mean, sem = spectrum_from_local_exponents(exps, ic.shape[0])
+    return mean, sem, res

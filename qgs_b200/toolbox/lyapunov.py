@@ -45,7 +45,7 @@ def _subtimes(times, mdt, backward=False):
 
 
 def benettin(f, fjac, ic, mode, n_vec, q0, r0, pre_times, rec_times, mdt, write_steps, adjoint, inverse, b, c, a,
-             want_r=False):
+             want_r=False, want_vectors=True):
     """Run ``qgsb_lyap_benettin``.  ``pre_times`` / ``rec_times`` are the directed time vectors of the
     convergence phase and of the recorded phase.  mode 0: BLV, 1: FLV, 2: BLV whose trajectory follows the
     micro-steps (Ginelli forward pass).  Returns ``traj (N,n,R), exp (N,m,R), vec (N,n,m,R)[, r_all]``."""
@@ -68,7 +68,7 @@ def benettin(f, fjac, ic, mode, n_vec, q0, r0, pre_times, rec_times, mdt, write_
     r0 = None if r0 is None else _lib.f64(r0)
     rec_traj = np.empty((N, n, R))
     rec_exp = np.empty((N, m, R))
-    rec_vec = np.empty((N, n, m, R))
+    rec_vec = np.empty((N, n, m, R)) if want_vectors else None
     r_all = np.empty((N, n_pre + n_rec, m, m)) if want_r else None
     _lib.check(_lib.load().qgsb_lyap_benettin(
         tensor.handle, N, _lib.dptr(ic), int(mode), m, _lib.dptr(q0), _lib.dptr(r0), n_pre, n_rec,
@@ -116,13 +116,11 @@ def ginelli(f, fjac, ic, n_vec, q0, r0, am0, noise, noise_pert, pretime, time, a
 
 
 def _random_basis(n_traj, n_dim, n_vec, normal=False):
-    """qr(random((n_dim, n_vec))) per member (lyapunov.py:592-593; randn for Ginelli, :1200)."""
-    q0 = np.empty((n_traj, n_dim, n_vec))
-    r0 = np.empty((n_traj, n_vec, n_vec))
-    for i in range(n_traj):
-        draw = np.random.randn(n_dim, n_vec) if normal else np.random.random((n_dim, n_vec))
-        q0[i], r0[i] = np.linalg.qr(draw)
-    return q0, r0
+    """qr(random((n_dim, n_vec))) per member (lyapunov.py:592-593; randn for Ginelli, :1200) -- drawn and
+    factorised for the whole ensemble at once (stacked LAPACK calls instead of a Python loop)."""
+    draw = np.random.randn(n_traj, n_dim, n_vec) if normal else np.random.random((n_traj, n_dim, n_vec))
+    q0, r0 = np.linalg.qr(draw)
+    return np.ascontiguousarray(q0), np.ascontiguousarray(r0)
 
 
 class _EstimatorBase(object):
@@ -201,7 +199,8 @@ class _EstimatorBase(object):
                 time = np.concatenate((tt[::self.write_steps], np.full((1,), tt[-1])))
         else:
             time = tt[-1]
-        return time, np.squeeze(self._recorded_traj), np.squeeze(self._recorded_exp), np.squeeze(vec)
+        return (time, np.squeeze(self._recorded_traj), np.squeeze(self._recorded_exp),
+                None if vec is None else np.squeeze(vec))
 
 
 class LyapunovsEstimator(_EstimatorBase):
@@ -215,9 +214,11 @@ class LyapunovsEstimator(_EstimatorBase):
         self._inverse = 1.
 
     def compute_lyapunovs(self, t0, tw, t, dt, mdt, ic=None, write_steps=1, n_vec=None, forward=False, adjoint=False,
-                          inverse=False):
+                          inverse=False, vectors=True):
         """Estimate the BLVs between ``tw`` and ``t`` (``forward=False``) or the FLVs between ``t0`` and ``tw``
-        (``forward=True``) -- lyapunov.py:232-358.  Results via :meth:`get_lyapunovs`."""
+        (``forward=True``) -- lyapunov.py:232-358.  Results via :meth:`get_lyapunovs`.  ``vectors=False`` (an
+        extension) keeps only the trajectory and the local exponents: no ``(n_traj, n_dim, n_vec, n_records)`` array
+        is recorded or copied, and ``get_lyapunovs`` returns ``None`` for the vectors."""
         if self.func is None or self.func_jac is None:
             print('No function to integrate defined!')
             return 0
@@ -244,13 +245,13 @@ class LyapunovsEstimator(_EstimatorBase):
         if not forward:
             self.n_records = n_records_of(self._time, write_steps)
             res = benettin(self.func, self.func_jac, self.ic, 0, self.n_vec, q0, r0, self._pretime, self._time, mdt,
-                           write_steps, adjoint, self._inverse, self.b, self.c, self.a)
+                           write_steps, adjoint, self._inverse, self.b, self.c, self.a, want_vectors=vectors)
         else:
             self.n_records = n_records_of(self._pretime, write_steps)
             # walk back over posttime (= self._time) first, then over time (= self._pretime): lyapunov.py:509-546
             res = benettin(self.func, self.func_jac, self.ic, 1, self.n_vec, q0, r0, self._time[::-1].copy(),
                            self._pretime[::-1].copy(), mdt, write_steps, adjoint, self._inverse, self.b, self.c,
-                           self.a)
+                           self.a, want_vectors=vectors)
         self._recorded_traj, self._recorded_exp, self._recorded_vec = res
 
     def get_lyapunovs(self):

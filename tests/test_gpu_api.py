@@ -395,3 +395,36 @@ def test_ginelli_on_device_matches_the_host_recursion(name, n_vec, ws, noise_per
         assert rel(gt[i], ot) < 1e-13
         assert rel(gv[i], ov) < 1e-9, (i, rel(gv[i], ov))
         assert np.max(np.abs(ge[i] - oe)) < 1e-9 * max(1., np.max(np.abs(oe)))
+
+
+def test_pipelined_host_buffer_path_is_bitwise_the_resident_path():
+    """qgsb_rk_integrate overlaps the copies of large ensembles with the integration by going through in chunks of
+    whole waves; members are independent, so this must not change a bit (and ragged sizes must work)."""
+    from qgs_b200.ensemble import DeviceEnsemble
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator
+    f, Df, T = model("maooam36")
+    N = 2 * 148 * 2 * 128 * 4 + 12345          # two full chunks and a ragged third
+    ic = np.random.default_rng(8).random((N, 36)) * 0.01
+    integ = RungeKuttaIntegrator()
+    integ.set_func(f)
+    integ.integrate(0., 2., 0.1, ic=ic, write_steps=0)
+    t, x = integ.get_trajectories()
+    ens = DeviceEnsemble(f, ic)
+    ens.integrate(0., 2., 0.1)
+    assert x.shape == (N, 36) and np.array_equal(x, ens.states())
+
+
+def test_exponents_only_run_equals_the_full_run():
+    """compute_lyapunovs(vectors=False) skips the vector records; trajectory and exponents are unchanged."""
+    from qgs_b200.toolbox.lyapunov import LyapunovsEstimator
+    f, Df, T = model("maooam36")
+    ic = np.random.default_rng(3).random((9, 36)) * 0.01
+    out = []
+    for vectors in (True, False):
+        np.random.seed(77)
+        est = LyapunovsEstimator()
+        est.set_func(f, Df)
+        est.compute_lyapunovs(0., 1., 3., 0.1, 0.1, ic=ic, write_steps=4, n_vec=12, vectors=vectors)
+        out.append(est.get_lyapunovs())
+    assert out[1][3] is None and out[0][3].shape == (9, 36, 12, 6)
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])

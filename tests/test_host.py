@@ -247,7 +247,7 @@ import os, sys
 import numpy as np
 import torch.distributed as dist
 sys.path.insert(0, %(repo)r)
-from qgs_b200.ensemble import shard_bounds, combine_moments, gather_states
+from qgs_b200.ensemble import shard_bounds, combine_moments, gather_states, spectrum_from_local_exponents
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
 states = np.random.default_rng(0).standard_normal((1001, 36))
@@ -259,6 +259,12 @@ assert np.allclose(mean, states.mean(axis=0), rtol=1e-12, atol=1e-14)
 assert np.allclose(var, states.var(axis=0), rtol=1e-10)
 full = gather_states(mine)
 assert np.array_equal(full, states)
+# Lyapunov spectrum of a sharded ensemble: member/time means combined over the ranks
+exps = np.random.default_rng(1).standard_normal((1001, 5, 7)) + np.arange(5)[None, :, None]
+spec, sem = spectrum_from_local_exponents(exps[lo:hi], 1001)
+per_member = exps.mean(axis=2)
+assert np.allclose(spec, per_member.mean(axis=0), rtol=1e-12)
+assert np.allclose(sem, per_member.std(axis=0) / np.sqrt(1000.), rtol=1e-9)
 dist.barrier()
 dist.destroy_process_group()
 print("rank %%d ok" %% rank)
