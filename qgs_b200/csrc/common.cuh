@@ -60,6 +60,7 @@ struct Context {
     size_t smem_optin = 0;  // max dynamic shared memory per block
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the pipelined host-buffer paths
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long launches = 0;
 };
@@ -216,4 +217,5 @@ struct qgsb_ensemble {
     long N = 0, ld = 0;
     qgsb::DevBuf<double> d_y;        // (n, ld)
     qgsb::DevBuf<double> d_stage;    // scratch for AoS <-> SoA staging (N * n)
+    qgsb::DevBuf<double> d_dt;       // step lengths of the launch in flight
 };

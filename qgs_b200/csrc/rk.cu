@@ -746,11 +746,7 @@ int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_ste
         // buffers make the copies truly asynchronous; members are independent, so the results are unchanged).
         const long chunk = (long)cx.sm_count * 2 * TILE * 4;
         if (N >= 2 * chunk) {
-            static cudaStream_t s_in = nullptr, s_out = nullptr;
-            if (!s_in) {
-                QGSB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-                QGSB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-            }
+            cudaStream_t s_in = cx.copy_in, s_out = cx.copy_out;
             const long n_chunks = (N + chunk - 1) / chunk;
             std::vector<cudaEvent_t> up(n_chunks), done(n_chunks);
             for (long k = 0; k < n_chunks; ++k) {
@@ -880,8 +876,8 @@ static void ensemble_run(qgsb_ensemble *e, long n_steps, const double *dt, int s
     ensure_init();
     Context &cx = ctx();
     const Tableau tab = make_tableau(s, a, b);
-    // dt staging buffer lives with the context so the launch can stay asynchronous
-    static DevBuf<double> d_dt;
+    // dt staging buffer lives with the ensemble so the launch can stay asynchronous
+    DevBuf<double> &d_dt = e->d_dt;
     if (d_dt.n < (size_t)std::max<long>(n_steps, 1)) {
         QGSB_CUDA(cudaStreamSynchronize(cx.stream));
         d_dt.alloc(std::max<long>(n_steps, 1));

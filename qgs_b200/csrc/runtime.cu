@@ -45,7 +45,12 @@ static void init_device(int device)
     QGSB_REQUIRE(device < count, "device %d requested but only %d visible", device, count);
     if (c.ready && c.device == device) return;
     if (c.ready) {
+        cudaSetDevice(c.device);
+        cudaStreamSynchronize(c.stream);
+        pool_trim();                       // the scratch pool belongs to the device we are leaving
         cudaStreamDestroy(c.own_stream);
+        cudaStreamDestroy(c.copy_in);
+        cudaStreamDestroy(c.copy_out);
         cudaEventDestroy(c.ev0);
         cudaEventDestroy(c.ev1);
         c.ready = false;
@@ -61,6 +66,8 @@ static void init_device(int device)
     c.smem_optin = p.sharedMemPerBlockOptin;
     QGSB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
+    QGSB_CUDA(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking));
+    QGSB_CUDA(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking));
     QGSB_CUDA(cudaEventCreate(&c.ev0));
     QGSB_CUDA(cudaEventCreate(&c.ev1));
     c.ready = true;
@@ -465,6 +472,9 @@ void qgsb_shutdown(void)
     cudaStreamSynchronize(c.stream);
     pool_trim();
     cudaStreamDestroy(c.own_stream);
+    cudaStreamDestroy(c.copy_in);
+    cudaStreamDestroy(c.copy_out);
+    c.copy_in = c.copy_out = nullptr;
     cudaEventDestroy(c.ev0);
     cudaEventDestroy(c.ev1);
     c.own_stream = c.stream = nullptr;
