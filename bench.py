@@ -272,9 +272,19 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout when the first communicator comes up: keep stdout for the one
+        # JSON line by pointing fd 1 at stderr until the group exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     _lib.init(local_rank)
     lib = _lib.load()
 
@@ -381,8 +391,8 @@ def run_ours(args, rank, world, local_rank):
                              "flops_per_member_step": FLOPS_PER_MEMBER_STEP, "kernel": "rk_chain_kernel (maooam36)"},
                 "cpu_baseline": base, "cpu_port": port,
                 "e2e": {"value": member_steps / e2e_s, "unit": UNIT,
-                        "h2d_bytes_per_step": members * NDIM * 8 + n_steps * 8,
-                        "d2h_bytes_per_step": members * NDIM * 8,
+                        "h2d_bytes_per_step": world * (members * NDIM * 8 + n_steps * 8),
+                        "d2h_bytes_per_step": world * members * NDIM * 8,
                         "call": "qgsb_rk_integrate (C ABI behind RungeKuttaIntegrator.integrate), pinned host buffers"},
                 "gpu_launches": int(n_launches), "clocks": clocks,
                 "wall_s_timed_region": wall_s, "ensemble_mean_finite": finite}
