@@ -59,7 +59,6 @@ bool pack_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m)
 // device copies of the ELL tables of one tensor handle
 struct qgsb_tensor::PackCache {
     qgsb::DevBuf<qgsb::PEnt> f, j;
-    qgsb::DevBuf<unsigned short> slot;
     qgsb::PackTables tab;
 };
 
@@ -100,10 +99,10 @@ static const PackTables &pack_tables(const qgsb_tensor *t, bool spec)
                     const Entry &en = t->h_ent[e];
                     PEnt &o = h[(size_t)(e - t->h_row_ptr[r]) * n + (r - 1)];
                     o.v = en.v;
-                    o.a = (unsigned short)(en.jk & 0xffffu);
-                    o.b = (unsigned short)(en.jk >> 16);
-                    o.c = rank == 5 ? (unsigned short)(en.lm & 0xffffu) : 0;
-                    o.d = rank == 5 ? (unsigned short)(en.lm >> 16) : 0;
+                    o.a = (unsigned short)(8 * (en.jk & 0xffffu));
+                    o.b = (unsigned short)(8 * (en.jk >> 16));
+                    o.c = rank == 5 ? (unsigned short)(8 * (en.lm & 0xffffu)) : 0;
+                    o.d = rank == 5 ? (unsigned short)(8 * (en.lm >> 16)) : 0;
                 }
             pc->f.alloc(h.size());
             QGSB_CUDA(cudaMemcpy(pc->f.p, h.data(), h.size() * sizeof(PEnt), cudaMemcpyHostToDevice));
@@ -146,17 +145,15 @@ static const PackTables &pack_tables(const qgsb_tensor *t, bool spec)
                     const Entry &en = t->h_jent[e];
                     PEnt &o = h[(size_t)(e - t->h_pos_ptr[p]) * npos + q];
                     o.v = en.v;
-                    o.a = (unsigned short)(en.jk & 0xffffu);
-                    o.b = rank == 5 ? (unsigned short)(en.jk >> 16) : 0;
-                    o.c = rank == 5 ? (unsigned short)(en.lm & 0xffffu) : 0;
+                    o.a = (unsigned short)(8 * (en.jk & 0xffffu));
+                    o.b = rank == 5 ? (unsigned short)(8 * (en.jk >> 16)) : 0;
+                    o.c = rank == 5 ? (unsigned short)(8 * (en.lm & 0xffffu)) : 0;
                 }
+                h[q].d = (unsigned short)(8 * slots[q]);      // entry 0 of the position carries its slot
             }
             pc->j.alloc(h.size());
             QGSB_CUDA(cudaMemcpy(pc->j.p, h.data(), h.size() * sizeof(PEnt), cudaMemcpyHostToDevice));
-            pc->slot.alloc(npos);
-            QGSB_CUDA(cudaMemcpy(pc->slot.p, slots.data(), npos * sizeof(unsigned short), cudaMemcpyHostToDevice));
             pc->tab.j_ent = pc->j.p;
-            pc->tab.j_slot = pc->slot.p;
             pc->tab.EJ = EJ;
             pc->tab.npos = npos;
         }

@@ -140,24 +140,38 @@ struct DenseProduct {
 };
 
 // ---- tendencies and Jacobian values of one member ------------------------------------------------------------------
+// The ELL tables live in shared memory (ShTab: plain shared pointers, so every access below is an LDS); their index
+// fields are BYTE offsets into the augmented stage state, and entry 0 of a Jacobian position carries the byte offset
+// of its slot in the member's Jacobian area.
+struct ShTab {
+    const PEnt *f = nullptr;   // (EF, N)
+    const PEnt *j = nullptr;   // (EJ, npos)
+    int EF = 0, EJ = 0, npos = 0;
+};
+
+__device__ __forceinline__ double at(const double *base, unsigned off)
+{
+    return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + off);
+}
+
 // row r of f at the stage state xs (sparse_mul.py:76-81 / :153-158 with the row's entries in COO order)
 template <int N>
-__device__ __forceinline__ double f_row_tab(const TensorView &T, const PackTables &tab, int r, const double *xs)
+__device__ __forceinline__ double f_row_tab(const TensorView &T, const ShTab &tab, int r, const double *xs)
 {
-    if (tab.f_ent == nullptr) return f_row_rt(T, r + 1, xs);
-    const PEnt *e = tab.f_ent + r;
+    if (tab.f == nullptr) return f_row_rt(T, r + 1, xs);
+    const PEnt *e = tab.f + r;
     double acc = 0.;
     if (T.rank == 5) {
 #pragma unroll 2
         for (int q = 0; q < tab.EF; ++q) {
             const PEnt en = e[q * N];
-            acc += xs[en.a] * xs[en.b] * xs[en.c] * xs[en.d] * en.v;
+            acc += at(xs, en.a) * at(xs, en.b) * at(xs, en.c) * at(xs, en.d) * en.v;
         }
     } else {
-#pragma unroll 4
+#pragma unroll 5
         for (int q = 0; q < tab.EF; ++q) {
             const PEnt en = e[q * N];
-            acc += xs[en.a] * xs[en.b] * en.v;
+            acc += at(xs, en.a) * at(xs, en.b) * en.v;
         }
     }
     return acc;
@@ -165,61 +179,64 @@ __device__ __forceinline__ double f_row_tab(const TensorView &T, const PackTable
 
 // values of the Jacobian positions q = c, c + m, ... of this member (sparse_mul.py:40-44 / :113-117)
 template <int N, class Prod>
-__device__ __forceinline__ void jac_build(const TensorView &T, const PackTables &tab, const double *xs, double *jv,
-                                          int c, int m)
+__device__ __forceinline__ void jac_build(const TensorView &T, const ShTab &tab, const double *xs, double *jv, int c,
+                                          int m)
 {
     const JacView &J = T.jac;
-    if (tab.j_ent == nullptr) {
+    if (tab.j == nullptr) {
         for (int p = c; p < J.npos; p += m) jv[Prod::slot(J.pos_i[p], J.pos_j[p])] = jac_pos_rt(J, T.rank, p, xs);
         return;
     }
     const int npos = tab.npos;
+    char *jvb = reinterpret_cast<char *>(jv);
     if (T.rank == 5) {
         for (int q = c; q < npos; q += m) {
+            const unsigned slot = tab.j[q].d;
             double acc = 0.;
             for (int e = 0; e < tab.EJ; ++e) {
-                const PEnt en = tab.j_ent[e * npos + q];
-                acc += xs[en.a] * xs[en.b] * xs[en.c] * en.v;
+                const PEnt en = tab.j[e * npos + q];
+                acc += at(xs, en.a) * at(xs, en.b) * at(xs, en.c) * en.v;
             }
-            jv[tab.j_slot[q]] = acc;
+            *reinterpret_cast<double *>(jvb + slot) = acc;
         }
     } else if (tab.EJ == 2) {
 #pragma unroll 4
         for (int q = c; q < npos; q += m) {
-            const PEnt e0 = tab.j_ent[q], e1 = tab.j_ent[npos + q];
-            double acc = xs[e0.a] * e0.v;
-            acc += xs[e1.a] * e1.v;
-            jv[tab.j_slot[q]] = acc;
+            const PEnt e0 = tab.j[q], e1 = tab.j[npos + q];
+            double acc = at(xs, e0.a) * e0.v;
+            acc += at(xs, e1.a) * e1.v;
+            *reinterpret_cast<double *>(jvb + e0.d) = acc;
         }
     } else {
         for (int q = c; q < npos; q += m) {
+            const unsigned slot = tab.j[q].d;
             double acc = 0.;
             for (int e = 0; e < tab.EJ; ++e) {
-                const PEnt en = tab.j_ent[e * npos + q];
-                acc += xs[en.a] * en.v;
+                const PEnt en = tab.j[e * npos + q];
+                acc += at(xs, en.a) * en.v;
             }
-            jv[tab.j_slot[q]] = acc;
+            *reinterpret_cast<double *>(jvb + slot) = acc;
         }
     }
 }
 
-// copies the tables into shared memory (after the members' areas) and returns pointers to the copies
-__device__ __forceinline__ PackTables stage_tables(const PackTables &tab, double *dst, int n)
+// copies the tables into shared memory (after the members' areas)
+__device__ __forceinline__ ShTab stage_tables(const PackTables &tab, double *dst, int n)
 {
-    if (tab.stage_bytes <= 0) return tab;
-    PackTables out = tab;
+    ShTab out;
     PEnt *f = reinterpret_cast<PEnt *>(dst);
     const int nf = tab.f_ent ? tab.EF * n : 0, nj = tab.j_ent ? tab.EJ * tab.npos : 0;
     PEnt *j = f + nf;
-    unsigned short *sl = reinterpret_cast<unsigned short *>(j + nj);
     for (int q = threadIdx.x; q < nf; q += blockDim.x) f[q] = tab.f_ent[q];
     for (int q = threadIdx.x; q < nj; q += blockDim.x) j[q] = tab.j_ent[q];
-    if (tab.j_ent)
-        for (int q = threadIdx.x; q < tab.npos; q += blockDim.x) sl[q] = tab.j_slot[q];
-    if (tab.f_ent) out.f_ent = f;
+    if (tab.f_ent) {
+        out.f = f;
+        out.EF = tab.EF;
+    }
     if (tab.j_ent) {
-        out.j_ent = j;
-        out.j_slot = sl;
+        out.j = j;
+        out.EJ = tab.EJ;
+        out.npos = tab.npos;
     }
     return out;
 }
@@ -228,7 +245,7 @@ __device__ __forceinline__ PackTables stage_tables(const PackTables &tab, double
 // col[] holds fm[:, c] on entry and on exit; S.y advances by dt.  No barrier at the end: the caller
 // synchronises before anybody reads another thread's data.
 template <int N, class Prod>
-__device__ __forceinline__ void tangent_step(const TensorView &T, const PackTables &tab, const TgParams &P,
+__device__ __forceinline__ void tangent_step(const TensorView &T, const ShTab &tab, const TgParams &P,
                                              const Mem<N> &S, double dt, double (&col)[N], int c, bool live)
 {
     const int s = P.s, m = S.m;
@@ -277,7 +294,7 @@ __device__ __forceinline__ void tangent_step(const TensorView &T, const PackTabl
 
 // one nonlinear step of the macro ("stored") trajectory: S.Y <- RK(S.Y, dt)
 template <int N>
-__device__ __forceinline__ void nl_step(const TensorView &T, const PackTables &tab, const TgParams &P,
+__device__ __forceinline__ void nl_step(const TensorView &T, const ShTab &tab, const TgParams &P,
                                         const Mem<N> &S, double dt, int c, bool live)
 {
     const int s = P.s, m = S.m;
@@ -450,7 +467,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
 tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride)
 {
     extern __shared__ __align__(16) double smem_pack[];
-    const PackTables tab = stage_tables(tab_g, smem_pack + (size_t)G * stride, N);
+    const ShTab tab = stage_tables(tab_g, smem_pack + (size_t)G * stride, N);
     const int m = P.m, t = threadIdx.x;
     const int g = t / m, c = t - g * m;
     const long member = (long)blockIdx.x * G + g;
@@ -503,7 +520,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
 lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride, int qr_remap)
 {
     extern __shared__ __align__(16) double smem_pack[];
-    const PackTables tab = stage_tables(tab_g, smem_pack + (size_t)G * stride, N);
+    const ShTab tab = stage_tables(tab_g, smem_pack + (size_t)G * stride, N);
     const int m = P.m, t = threadIdx.x;
     const int g = t / m, c = t - g * m;
     const long member = (long)blockIdx.x * G + g;
@@ -629,23 +646,21 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
-// table_bytes: size of the tables when staged in shared memory (0: leave them in global memory)
+// table_bytes: size of the ELL tables, which are always staged in shared memory behind the members' areas
 template <int N>
-inline Geometry geometry(int jv, int m, size_t smem_limit, size_t table_bytes, bool *staged)
+inline Geometry geometry(int jv, int m, size_t smem_limit, size_t table_bytes)
 {
     Geometry geo;
     const Carve<N> c(jv, m);
     geo.jv = jv;
     geo.stride = c.total();
     const size_t per_member = (size_t)geo.stride * sizeof(double);
-    const int want = MAX_THREADS / m;
-    int G = want;
-    if ((size_t)G * per_member > smem_limit) G = (int)(smem_limit / per_member);
-    // stage the tables only when that does not cost a member
-    *staged = table_bytes > 0 && (size_t)G * per_member + table_bytes <= smem_limit;
+    int G = MAX_THREADS / m;
+    if (table_bytes >= smem_limit) G = 0;
+    else if ((size_t)G * per_member + table_bytes > smem_limit) G = (int)((smem_limit - table_bytes) / per_member);
     geo.G = G;
     geo.threads = G > 0 ? ((G * m + 31) / 32) * 32 : 0;
-    geo.smem = (size_t)G * per_member + (*staged ? table_bytes : 0);
+    geo.smem = (size_t)G * per_member + table_bytes;
     return geo;
 }
 
@@ -653,7 +668,7 @@ inline size_t table_bytes(const PackTables &tab, int n)
 {
     size_t b = 0;
     if (tab.f_ent) b += (size_t)tab.EF * n * sizeof(PEnt);
-    if (tab.j_ent) b += (size_t)tab.EJ * tab.npos * sizeof(PEnt) + ((size_t)tab.npos * sizeof(unsigned short) + 15) / 16 * 16;
+    if (tab.j_ent) b += (size_t)tab.EJ * tab.npos * sizeof(PEnt);
     return b;
 }
 
@@ -664,11 +679,9 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
 {
     static_assert(Fwd::JV == Adj::JV, "both directions of a product share one Jacobian layout");
     if (P.m < 1 || P.m > MAX_THREADS) return cudaErrorInvalidValue;
-    bool staged = false;
-    const Geometry geo = geometry<N>(Fwd::JV, P.m, smem_limit, table_bytes(tables, N), &staged);
+    const Geometry geo = geometry<N>(Fwd::JV, P.m, smem_limit, table_bytes(tables, N));
     if (geo.G < 1) return cudaErrorInvalidValue;
-    PackTables tab = tables;
-    tab.stage_bytes = staged ? (int)table_bytes(tables, N) : 0;
+    const PackTables &tab = tables;
     const unsigned blocks = (unsigned)((P.n_members + geo.G - 1) / geo.G);
     auto go = [&](auto kernel) -> cudaError_t {
         if (geo.smem > 48 * 1024) {

@@ -89,17 +89,16 @@ __device__ __forceinline__ double jac_pos_rt(const JacView &J, int rank, int p, 
 // kernels then walk the CSR lists of TensorView.
 struct __align__(16) PEnt {
     double v;
-    unsigned short a, b, c, d;   // factor indices into the augmented state (0 = the constant 1)
+    unsigned short a, b, c, d;   // BYTE offsets (8 * index) of the factors in the augmented state (0 = the constant 1);
+                                 // Jacobian tables: d of entry 0 = byte offset of the position's slot
 };
 
 struct PackTables {
-    const PEnt *f_ent = nullptr;
+    const PEnt *f_ent = nullptr;   // device, (EF, n)
     int EF = 0;
-    const PEnt *j_ent = nullptr;
+    const PEnt *j_ent = nullptr;   // device, (EJ, npos)
     int EJ = 0;
     int npos = 0;
-    const unsigned short *j_slot = nullptr;   // (npos) slot of list position q in the member's Jacobian area
-    int stage_bytes = 0;                      // > 0: the kernel copies the tables into shared memory first
 };
 
 // Benettin plumbing shared with clv.cu (tgls.cu)
