@@ -199,6 +199,7 @@ struct qgsb_tensor {
     std::vector<int> h_pos_i, h_pos_j;   // host copy of the Jacobian positions
     std::vector<qgsb::Entry> h_ent, h_jent;          // host copies of the device entry lists
     std::vector<int> h_row_ptr, h_pos_ptr;
+    mutable qgsb::DevBuf<int> d_wide;    // row-to-warp assignment of the wide RK kernel (rk.cu), built on first use
     struct G3Cache;                      // plan + tables of the large-basis RK kernel (rk.cu G3), built on first use
     mutable G3Cache *g3_cache = nullptr;
     mutable int g3_state = 0;            // 0 not planned, 1 ready, -1 not applicable

@@ -6,10 +6,12 @@
 // into shared memory and reused for every evaluation of f.
 #include <algorithm>
 #include <cmath>
+#include <numeric>
 
 #include "common.cuh"
 #include "kernels.cuh"
 #include "spec_registry.h"
+#include "tgls_shared.cuh"
 
 namespace qgsb {
 
@@ -453,6 +455,195 @@ rk_g3_kernel(int n, int mb, int n_chunks, const __grid_constant__ G3Plan plan, c
 #undef G3_X
 
 // ------------------------------------------------------------------------------------------------
+// Rows kernel: the latency regime (few members, many steps -- the reference's example scripts integrate ONE
+// trajectory, qgs_maooam.py:100-117).  The throughput kernels give a member to one thread, which then walks all n
+// rows one after the other (3 us per MAOOAM-36 step however few members there are).  Here a block owns one member
+// and thread r owns ROW r: y_r and the weighted stage sum stay in its registers, the stage state is exchanged
+// through a double buffer in shared memory (one barrier per stage), and the row is summed from the ELL table
+// (staged in shared memory) with two independent partial sums.  Chain tableaux, ELL-able tensors.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rows_at(const double *base, unsigned off)
+{
+    return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + off);
+}
+
+// EFU = entries per row rounded up (template, so the row's entries live in registers for the whole integration and
+// the sums are fully unrolled: per stage a thread issues its 2 EFU independent loads of x back to back)
+template <int RANK, int EFU>
+__global__ void __launch_bounds__(256) rk_rows_kernel(int n, const PEnt *__restrict__ f_ent, int EF,
+                                                      const __grid_constant__ RkParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int r = threadIdx.x, s = P.s;
+    const long member = blockIdx.x;
+    double *cur = reinterpret_cast<double *>(smem_raw);          // (n + 1), [0] = 1
+    double *nxt = cur + ((n + 2) & ~1);
+    const bool act = r < n;
+    const size_t g = tile_base(member, n) + (size_t)(act ? r : 0) * TILE;
+    double y = act ? P.y[g] : 0., acc = 0.;
+    // this row's entries: value and the byte offsets of its factors
+    double v[EFU];
+    unsigned ab[EFU], cd[RANK == 5 ? EFU : 1];
+#pragma unroll
+    for (int q = 0; q < EFU; ++q) {
+        PEnt e = {0., 0, 0, 0, 0};
+        if (act && q < EF) e = f_ent[(size_t)q * n + r];
+        v[q] = e.v;
+        ab[q] = (unsigned)e.a | ((unsigned)e.b << 16);
+        if (RANK == 5) cd[q] = (unsigned)e.c | ((unsigned)e.d << 16);
+    }
+    if (r == 0) {
+        cur[0] = 1.;
+        nxt[0] = 1.;
+    }
+    if (act) cur[r + 1] = y;
+    __syncthreads();
+    long iw = 0;
+    for (long ti = 0; ti < P.n_steps; ++ti) {
+        const double dt = P.dt[ti];
+        if (P.rec && P.write_steps > 0 && ti % P.write_steps == 0) {       // integrate.py:210-212
+            if (act) P.rec[(size_t)iw * n * P.ld + g] = y;
+            ++iw;
+        }
+        for (int st = 0; st < s; ++st) {
+            double p[EFU];
+#pragma unroll
+            for (int q = 0; q < EFU; ++q) {
+                p[q] = rows_at(cur, ab[q] & 0xffffu) * rows_at(cur, ab[q] >> 16);
+                if (RANK == 5) p[q] = p[q] * rows_at(cur, cd[q] & 0xffffu) * rows_at(cur, cd[q] >> 16);
+            }
+            double k0 = 0., k1 = 0., k2 = 0., k3 = 0.;
+#pragma unroll
+            for (int q = 0; q < EFU; q += 4) {
+                k0 = fma(p[q], v[q], k0);                                   // (a*b)*value, then +=  (sparse_mul.py:79)
+                if (q + 1 < EFU) k1 = fma(p[q + 1], v[q + 1], k1);
+                if (q + 2 < EFU) k2 = fma(p[q + 2], v[q + 2], k2);
+                if (q + 3 < EFU) k3 = fma(p[q + 3], v[q + 3], k3);
+            }
+            const double k = (k0 + k1) + (k2 + k3);
+            const double wb = dt * P.b[st];
+            acc = st == 0 ? wb * k : acc + wb * k;
+            if (st + 1 < s) {
+                if (act) nxt[r + 1] = y + (dt * P.alpha[st + 1]) * k;       // y + (dt a[i]) @ k   integrate.py:216
+            } else {
+                y += acc;                                                   // y + (dt b) @ k      integrate.py:218
+                if (act) nxt[r + 1] = y;
+            }
+            __syncthreads();
+            double *t = cur;
+            cur = nxt;
+            nxt = t;
+        }
+    }
+    if (act) {
+        if (P.rec) P.rec[(size_t)(P.n_records - 1) * n * P.ld + g] = y;     // integrate.py:221
+        P.y[g] = y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wide kernel: the latency regime for large bases (a handful of trajectories of the 228-variable model).  One
+// 1024-thread block owns one member; its 32 warps share the rows (assigned on the host by decreasing length so
+// that every warp streams about the same number of entries), a warp's lanes stride over a row's entries
+// (coalesced 512-byte reads of the tensor stream from L2) and reduce the row with a fixed shuffle tree, lane 0
+// finishes the row.  The stage state is a double buffer in shared memory, one barrier per stage.
+// 6x6, one member: 47 us per step, where the thread-per-member kernels need 1 ms and one CPU core of the reference
+// 360 us; ncu: the random gathers of x_j, x_k from shared memory dominate (bank conflicts: short-scoreboard and MIO
+// stalls, shared-memory wavefronts at 56 % of peak), then the tensor stream from L2.
+// ------------------------------------------------------------------------------------------------
+constexpr int WIDE_WARPS = 32;
+
+template <int RANK>
+__global__ void __launch_bounds__(WIDE_WARPS * 32) rk_wide_kernel(TensorView T, const int *__restrict__ warp_ptr,
+                                                                   const int *__restrict__ warp_rows,
+                                                                   const __grid_constant__ RkParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = T.n, s = P.s, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long member = blockIdx.x;
+    double *cur = reinterpret_cast<double *>(smem_raw);          // (n + 1), [0] = 1
+    double *nxt = cur + ((n + 2) & ~1);
+    double *ys = nxt + ((n + 2) & ~1);                           // (n)
+    double *accs = ys + ((n + 1) & ~1);                          // (n)
+    int *rinfo = reinterpret_cast<int *>(accs + ((n + 1) & ~1));  // (n, 3): row, first entry, end -- in warp order
+    const size_t gbase = tile_base(member, n);
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double v = P.y[gbase + (size_t)i * TILE];
+        ys[i] = v;
+        cur[i + 1] = v;
+        const int row = warp_rows[i];
+        rinfo[3 * i] = row;
+        rinfo[3 * i + 1] = T.row_ptr[row];
+        rinfo[3 * i + 2] = T.row_ptr[row + 1];
+    }
+    if (tid == 0) {
+        cur[0] = 1.;
+        nxt[0] = 1.;
+    }
+    __syncthreads();
+    const int r0 = warp_ptr[warp], r1 = warp_ptr[warp + 1];
+    long iw = 0;
+    for (long ti = 0; ti < P.n_steps; ++ti) {
+        const double dt = P.dt[ti];
+        if (P.rec && P.write_steps > 0 && ti % P.write_steps == 0) {       // integrate.py:210-212
+            double *rp = P.rec + (size_t)iw * n * P.ld + gbase;
+            for (int i = tid; i < n; i += blockDim.x) rp[(size_t)i * TILE] = ys[i];
+            ++iw;
+        }
+        for (int st = 0; st < s; ++st) {
+            const double wb = dt * P.b[st];
+            const double wa = st + 1 < s ? dt * P.alpha[st + 1] : 0.;
+            const bool last = st + 1 == s;
+            for (int q = r0; q < r1; ++q) {
+                const int i = rinfo[3 * q], e1 = rinfo[3 * q + 2];          // 1-based row
+                double k0 = 0., k1 = 0.;
+                // 128 entries of the row are requested at once (4 independent 16-byte loads per lane)
+                for (int e = rinfo[3 * q + 1] + lane; e < e1; e += 128) {
+                    Entry en[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        en[u].v = 0.;
+                        en[u].jk = 0u;
+                        en[u].lm = 0u;
+                        if (e + 32 * u < e1) en[u] = T.ent[e + 32 * u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        double p = cur[en[u].jk & 0xffffu] * cur[en[u].jk >> 16];
+                        if (RANK == 5) p = p * cur[en[u].lm & 0xffffu] * cur[en[u].lm >> 16];
+                        if (u & 1) k1 = fma(p, en[u].v, k1);                // (a*b)*value, then +=  (sparse_mul.py:79)
+                        else k0 = fma(p, en[u].v, k0);
+                    }
+                }
+                double k = k0 + k1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+                if (lane == 0) {
+                    const double ac = st == 0 ? wb * k : accs[i - 1] + wb * k;
+                    if (!last) {
+                        accs[i - 1] = ac;
+                        nxt[i] = ys[i - 1] + wa * k;                        // y + (dt a[i]) @ k   integrate.py:216
+                    } else {
+                        const double yn = ys[i - 1] + ac;                   // y + (dt b) @ k      integrate.py:218
+                        ys[i - 1] = yn;
+                        nxt[i] = yn;
+                    }
+                }
+            }
+            __syncthreads();
+            double *t = cur;
+            cur = nxt;
+            nxt = t;
+        }
+    }
+    if (P.rec) {                                                            // integrate.py:221
+        double *rp = P.rec + (size_t)(P.n_records - 1) * n * P.ld + gbase;
+        for (int i = tid; i < n; i += blockDim.x) rp[(size_t)i * TILE] = ys[i];
+    }
+    for (int i = tid; i < n; i += blockDim.x) P.y[gbase + (size_t)i * TILE] = ys[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------
 template <typename K>
@@ -638,9 +829,85 @@ static bool launch_g3(const qgsb_tensor *t, RkParams &P)
     return true;
 }
 
+// members below which a block per member (thread per row) beats a thread per member; measured on B200 for
+// MAOOAM-36: 0.5 us per step against 3 us, and a full wave of row blocks costs about one thread-per-member step
+static long rows_threshold()
+{
+    const char *e = getenv("QGSB_RK_ROWS_MAX");     // A/B measurements: 0 disables the rows kernel
+    return e ? atol(e) : 2048;
+}
+
+template <int RANK, int EFU>
+static void launch_rows_efu(int n, const PackTables &pt, RkParams &P)
+{
+    const size_t bytes = 2 * (size_t)((n + 2) & ~1) * sizeof(double);
+    const int threads = (n + 31) / 32 * 32;
+    rk_rows_kernel<RANK, EFU><<<(unsigned)P.n_members, threads, bytes, ctx().stream>>>(n, pt.f_ent, pt.EF, P);
+}
+
+static bool launch_rows(const qgsb_tensor *t, RkParams &P)
+{
+    const int n = t->view.n;
+    if (n > 256) return false;                      // larger bases: one thread per row is too coarse
+    const PackTables &pt = pack_tables(t, false);
+    if (pt.f_ent == nullptr || pt.EF > 64) return false;
+    const bool r5 = t->view.rank == 5;
+    if (pt.EF <= 8) r5 ? launch_rows_efu<5, 8>(n, pt, P) : launch_rows_efu<3, 8>(n, pt, P);
+    else if (pt.EF <= 16) r5 ? launch_rows_efu<5, 16>(n, pt, P) : launch_rows_efu<3, 16>(n, pt, P);
+    else if (pt.EF <= 32) r5 ? launch_rows_efu<5, 32>(n, pt, P) : launch_rows_efu<3, 32>(n, pt, P);
+    else r5 ? launch_rows_efu<5, 64>(n, pt, P) : launch_rows_efu<3, 64>(n, pt, P);
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+    return true;
+}
+
+// rows of a tensor dealt to WIDE_WARPS warps, longest first onto the least loaded warp
+static bool launch_wide(const qgsb_tensor *t, RkParams &P)
+{
+    const int n = t->view.n;
+    const size_t bytes = (2 * (size_t)((n + 2) & ~1) + 2 * (size_t)((n + 1) & ~1)) * sizeof(double) +
+                         3 * (size_t)n * sizeof(int);
+    if (bytes > ctx().smem_optin) return false;
+    if (t->d_wide.n == 0) {
+        std::vector<int> order(n), load(WIDE_WARPS, 0);
+        std::iota(order.begin(), order.end(), 1);
+        auto len = [&](int i) { return t->h_row_ptr[i + 1] - t->h_row_ptr[i]; };
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return len(x) > len(y); });
+        std::vector<std::vector<int>> rows(WIDE_WARPS);
+        for (int i : order) {
+            const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            rows[w].push_back(i);
+            load[w] += len(i) + 8;                     // + the fixed cost of finishing a row
+        }
+        std::vector<int> flat(WIDE_WARPS + 1, 0);
+        for (int w = 0; w < WIDE_WARPS; ++w) flat[w + 1] = flat[w] + (int)rows[w].size();
+        for (int w = 0; w < WIDE_WARPS; ++w) flat.insert(flat.end(), rows[w].begin(), rows[w].end());
+        t->d_wide.alloc(flat.size());
+        QGSB_CUDA(cudaMemcpy(t->d_wide.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    const int *warp_ptr = t->d_wide.p, *warp_rows = t->d_wide.p + WIDE_WARPS + 1;
+    if (t->view.rank == 5) {
+        set_smem(rk_wide_kernel<5>, bytes);
+        rk_wide_kernel<5><<<(unsigned)P.n_members, WIDE_WARPS * 32, bytes, ctx().stream>>>(t->view, warp_ptr, warp_rows, P);
+    } else {
+        set_smem(rk_wide_kernel<3>, bytes);
+        rk_wide_kernel<3><<<(unsigned)P.n_members, WIDE_WARPS * 32, bytes, ctx().stream>>>(t->view, warp_ptr, warp_rows, P);
+    }
+    count_launch();
+    QGSB_CUDA(cudaGetLastError());
+    return true;
+}
+
 void rk_advance(const qgsb_tensor *t, double *d_y, long ld, long N, long n_steps, const double *d_dt,
                 const Tableau &tab, long write_steps, long R, double *d_rec)
 {
+    if (tab.chain && N <= rows_threshold() && n_steps > 0) {
+        RkParams P;
+        fill_params(P, tab, d_y, ld, N, n_steps, d_dt, write_steps, R, d_rec);
+        if (launch_rows(t, P)) return;
+        // many entries per row (large bases, T4): a block of 32 warps per member
+        if (t->view.nnz >= 4096 && launch_wide(t, P)) return;
+    }
     if (t->spec && t->use_spec && tab.chain && tab.s <= 8 && t->spec->rk_chain) {
         QGSB_CUDA(t->spec->rk_chain(d_y, ld, N, n_steps, d_dt, tab.s, tab.alpha.data(), tab.b.data(), write_steps, R,
                                     d_rec, ctx().sm_count, ctx().stream));

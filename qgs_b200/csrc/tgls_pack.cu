@@ -77,7 +77,7 @@ static bool ell_ok(int width, long count, long real)
     return width > 0 && (width <= 4 || (double)width * (double)count <= 1.5 * (double)real + 64.);
 }
 
-static const PackTables &pack_tables(const qgsb_tensor *t, bool spec)
+const PackTables &pack_tables(const qgsb_tensor *t, bool spec)
 {
     qgsb_tensor::PackCache *&slot = t->pack_cache[spec ? 1 : 0];
     if (slot) return slot->tab;

@@ -101,6 +101,10 @@ struct PackTables {
     int npos = 0;
 };
 
+// ELL tables of a tensor handle, built on first use and cached in it (tgls_pack.cu); spec: Jacobian positions in the
+// slot order of the handle's generated module instead of the dense n x n layout
+const PackTables &pack_tables(const qgsb_tensor *t, bool spec);
+
 // Benettin plumbing shared with clv.cu (tgls.cu)
 void benettin_dispatch(const qgsb_tensor *t, const Tableau &tab, TgParams &P, DevBuf<double> &scratch);
 void benettin_fill_common(TgParams &P, const Tableau &tab, long N, int m, int adjoint, double inverse);

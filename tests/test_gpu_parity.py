@@ -118,9 +118,17 @@ def test_rk_trajectories_vs_golden(name, specialise):
     if specialise and f.tensor.kernel_kind != 2:
         pytest.skip("no specialised kernel for this tensor")
     b, c, a = rk4()
-    for tag, (direction, ws) in RK_CASES.items():
-        got = _integrate_runge_kutta_jit(f, g["rk_time"], g["ic"], direction, ws, b, c, a)
-        assert rel(got, g["rk_" + tag]) < 1e-10, tag
+    # few members take the block-per-member "rows" kernel by default; QGSB_RK_ROWS_MAX=0 sends the same members
+    # through the throughput kernels (tensor-specialised / thread per member / large basis), so both are checked
+    for rows_max in ("0", "2048"):
+        os.environ["QGSB_RK_ROWS_MAX"] = rows_max
+        try:
+            for tag, (direction, ws) in RK_CASES.items():
+                got = _integrate_runge_kutta_jit(f, g["rk_time"], g["ic"], direction, ws, b, c, a)
+                assert rel(got, g["rk_" + tag]) < 1e-10, (tag, rows_max)
+        finally:
+            del os.environ["QGSB_RK_ROWS_MAX"]
+    os.environ["QGSB_RK_ROWS_MAX"] = "0"        # the generic-tableau cases below: throughput kernels
     # generic tableaux on a ragged time vector: Kutta 3/8 (not a chain) and Heun (2 stages, backward)
     c38 = np.array([0., 1. / 3, 2. / 3, 1.])
     b38 = np.array([1. / 8, 3. / 8, 3. / 8, 1. / 8])
@@ -129,6 +137,9 @@ def test_rk_trajectories_vs_golden(name, specialise):
     assert rel(got, g["rk38"]) < 1e-10
     ch, bh, ah = np.array([0., 1.]), np.array([0.5, 0.5]), np.array([[0., 0.], [1., 0.]])
     got = _integrate_runge_kutta_jit(f, g["rk38_time"], g["ic"], -1, 2, bh, ch, ah)
+    assert rel(got, g["rkheun"]) < 1e-10
+    del os.environ["QGSB_RK_ROWS_MAX"]
+    got = _integrate_runge_kutta_jit(f, g["rk38_time"], g["ic"], -1, 2, bh, ch, ah)      # Heun on the rows kernel
     assert rel(got, g["rkheun"]) < 1e-10
 
 
