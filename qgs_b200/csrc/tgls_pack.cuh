@@ -23,6 +23,7 @@
 // Only "chain" tableaux (a_ij != 0 only for j = i-1: Euler, midpoint, Heun, classic RK4) take this
 // path; the generic kernels of tgls.cu serve everything else.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -656,6 +657,7 @@ inline Geometry geometry(int jv, int m, size_t smem_limit, size_t table_bytes)
     geo.stride = c.total();
     const size_t per_member = (size_t)geo.stride * sizeof(double);
     int G = MAX_THREADS / m;
+    if (const char *env = getenv("QGSB_PACK_G")) G = std::max(1, std::min(G, atoi(env)));   // A/B measurements
     if (table_bytes >= smem_limit) G = 0;
     else if ((size_t)G * per_member + table_bytes > smem_limit) G = (int)((smem_limit - table_bytes) / per_member);
     geo.G = G;
