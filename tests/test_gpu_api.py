@@ -428,3 +428,40 @@ def test_exponents_only_run_equals_the_full_run():
         out.append(est.get_lyapunovs())
     assert out[1][3] is None and out[0][3].shape == (9, 36, 12, 6)
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+
+
+# ---- callers pinned against outputs of the UNMODIFIED reference (tests/golden/make_golden_extra.py) ---------------------------
+@pytest.mark.parametrize("tag", ["plain", "noise"])
+def test_ginelli_clvs_against_the_reference_itself(tag):
+    """qgsb_clv_ginelli fed the very draws the reference took from numba's generator (start basis, start matrix of
+    the backward recursion, diagonal noise) reproduces _compute_clv_gin_jit (lyapunov.py:1174-1288)."""
+    import oracle
+    from qgs_b200.toolbox.lyapunov import ginelli
+    f, Df, T = model("rp")
+    g = np.load(os.path.join(GOLDEN, "golden_extra_rp.npz"))
+    b, c, a = oracle.rk4_tableau()
+    ws, noise_pert = int(g["clv_%s_meta" % tag][0]), float(g["clv_%s_meta" % tag][1])
+    q0, _ = np.linalg.qr(g["clv_%s_q_draw" % tag])
+    am0, _ = oracle.normalize_matrix_columns(np.linalg.qr(g["clv_%s_a_draw" % tag])[1])
+    noise = g["clv_%s_noise" % tag][None] if noise_pert else None
+    traj, exps, vecs = ginelli(f, Df, g["clv_ic"], 20, q0[None], None, am0[None], noise, noise_pert,
+                               g["clv_pretime"], g["clv_time"], g["clv_aftertime"], 0.1, ws, b, c, a)
+    assert rel(traj, g["clv_%s_traj" % tag]) < 1e-12
+    assert rel(vecs, g["clv_%s_vec" % tag]) < 1e-8
+    assert np.max(np.abs(exps - g["clv_%s_exp" % tag])) < 1e-8 * max(1., np.max(np.abs(g["clv_%s_exp" % tag])))
+
+
+def test_trajectories_statistics_against_the_reference_itself():
+    """TrajectoriesStatistics.compute_stats (statistics.py:33-66, 3 blocks of 4/4/5 members) on the CUDA integrator
+    == the reference class on the reference's worker pool."""
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator
+    from qgs_b200.integrators.statistics import TrajectoriesStatistics
+    f, Df, T = model("rp")
+    g = np.load(os.path.join(GOLDEN, "golden_extra_rp.npz"))
+    integ = RungeKuttaIntegrator()
+    integ.set_func(f)
+    st = TrajectoriesStatistics()
+    st.set_integrator(integ)
+    st.set_func_list([lambda x: x, lambda x: x ** 2])
+    st.compute_stats(0., 1.25, 0.1, ic=g["stats_ic"], write_steps=4, num=3)
+    assert rel(st.get_stats(), g["stats_mean_func"]) < 1e-12
