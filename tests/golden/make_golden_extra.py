@@ -5,6 +5,7 @@
   method, with and without the diagonal noise.  Its random start matrices and noise come from numba's generator; that
   generator is seeded from inside a jitted function and the very same draws are taken again, in the same order, and
   stored (``q_draw``, ``a_draw``, ``noise``), so that the device path can be fed identical inputs;
+* ``qgs.toolbox.lyapunov._compute_clv_sub_jit`` (lyapunov.py:1292-1329) -- CLVs by subspace intersection, same seeding trick;
 * ``qgs.integrators.statistics.TrajectoriesStatistics.compute_stats`` (statistics.py:33-66) on top of the reference's
   own ``RungeKuttaIntegrator`` worker pool.
 
@@ -48,6 +49,11 @@ def _randn1(n):
     return np.random.randn(n)
 
 
+@njit
+def _random2(n, m):
+    return np.random.random((n, m))
+
+
 def main():
     z = np.load(os.path.join(HERE, "tensor_rp.npz"))
     n = int(z["ndim"])
@@ -79,6 +85,15 @@ def main():
         out["clv_%s_q_draw" % tag], out["clv_%s_a_draw" % tag] = q_draw, a_draw
         out["clv_%s_noise" % tag] = noise[::-1].copy()                 # indexed by ti
         out["clv_%s_traj" % tag], out["clv_%s_exp" % tag], out["clv_%s_vec" % tag] = rt, re, rv
+
+    # ---- CLVs by subspace intersection (lyapunov.py:1292-1329): the FLV pass draws its start basis first, then the BLV pass
+    _seed(999)
+    f_draw = _random2(n, n)
+    b_draw = _random2(n, n)
+    _seed(999)
+    rt, re, rv, bvec, fvec = ref_lyap._compute_clv_sub_jit(f, Df, pretime, time, aftertime, 0.1, ic, 2, b, c, a)
+    out["sub_f_draw"], out["sub_b_draw"] = f_draw, b_draw
+    out["sub_traj"], out["sub_exp"], out["sub_vec"], out["sub_bvec"], out["sub_fvec"] = rt, re, rv, bvec, fvec
 
     # ---- TrajectoriesStatistics on the reference's own integrator pool
     sic = rng.random((13, n)) * 0.1

@@ -465,3 +465,32 @@ def test_trajectories_statistics_against_the_reference_itself():
     st.set_func_list([lambda x: x, lambda x: x ** 2])
     st.compute_stats(0., 1.25, 0.1, ic=g["stats_ic"], write_steps=4, num=3)
     assert rel(st.get_stats(), g["stats_mean_func"]) < 1e-12
+
+
+def test_subspace_clvs_against_the_reference_itself(monkeypatch):
+    """CovariantLyapunovsEstimator(method=1) == _compute_clv_sub_jit (lyapunov.py:1292-1329) for the same start bases:
+    FLV and BLV Benettin passes on the device, subspace intersection on the host."""
+    from qgs_b200.toolbox import lyapunov as lyap
+    f, Df, T = model("rp")
+    g = np.load(os.path.join(GOLDEN, "golden_extra_rp.npz"))
+    draws = [g["sub_f_draw"], g["sub_b_draw"]]          # the reference draws the FLV start first, then the BLV start
+
+    def stored_basis(n_traj, n_dim, n_vec, normal=False):
+        q, r = np.linalg.qr(draws.pop(0))
+        return q[None].copy(), r[None].copy()
+
+    monkeypatch.setattr(lyap, "_random_basis", stored_basis)
+    est = lyap.CovariantLyapunovsEstimator(method=1)
+    est.set_func(f, Df)
+    pre, tim, aft = g["clv_pretime"], g["clv_time"], g["clv_aftertime"]
+    est.compute_clvs(pre[0], tim[0], aft[0], aft[-1], 0.1, 0.1, ic=g["clv_ic"], write_steps=2, method=1,
+                     backward_vectors=True, forward_vectors=True)
+    t, traj, exps, vecs = est.get_clvs()
+    assert rel(traj, np.squeeze(g["sub_traj"])) < 1e-12
+    assert rel(est.get_blvs()[3], np.squeeze(g["sub_bvec"])) < 1e-8
+    assert rel(est.get_flvs()[3], np.squeeze(g["sub_fvec"])) < 1e-8
+    # a singular vector is defined up to its sign: compare column by column up to sign
+    ref = np.squeeze(g["sub_vec"])
+    sign = np.sign(np.sum(vecs * ref, axis=0, keepdims=True))
+    assert rel(vecs * sign, ref) < 1e-7
+    assert np.max(np.abs(exps - np.squeeze(g["sub_exp"]))) < 1e-6 * max(1., np.max(np.abs(g["sub_exp"])))
