@@ -150,6 +150,14 @@ QGSB_API int qgsb_clv_ginelli(const qgsb_tensor *t, long n_traj, const double *i
                               double *rec_traj /* (N, n, R) */, double *rec_exp /* (N, m, R) */,
                               double *rec_vec /* (N, n, m, R) */, double *device_ms);
 
+/* Covariant Lyapunov vectors by subspace intersection -- replaces the per-record SVD loop of _compute_clv_sub_jit
+ * (qgs/toolbox/lyapunov.py:1315-1320): CLV j = the direction common to span(BLV_0..j) and span(FLV_0..n-1-j), found
+ * as the null vector of a corner of FLV^T BLV instead of as a first singular vector (same direction; its sign, which
+ * is arbitrary in the reference too, is fixed by making the largest coefficient positive).  bvec, fvec, vec: host
+ * arrays (n_traj, n_dim, n_dim, n_records) in the layout of get_blvs() / get_flvs() / get_clvs(). */
+QGSB_API int qgsb_clv_subspace_intersect(long n_traj, int n_dim, long n_records, const double *bvec,
+                                         const double *fvec, double *vec);
+
 /* ---- device-resident ensemble (state stays in HBM between calls) ---------
  * State layout in HBM: tiled structure of arrays -- members in tiles of 128, variable i of member m at
  * (m / 128) * (n * 128) + i * 128 + m % 128; ld = n_traj rounded up to 128. */

@@ -61,6 +61,8 @@ _PROTOTYPES = {
                                         ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_long,
                                         ctypes.c_double, c_double_p, c_double_p, c_double_p, ctypes.c_long,
                                         c_double_p, c_double_p, c_double_p, c_double_p]),
+    "qgsb_clv_subspace_intersect": (ctypes.c_int, [ctypes.c_long, ctypes.c_int, ctypes.c_long, c_double_p, c_double_p,
+                                                   c_double_p]),
     "qgsb_ensemble_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_long, c_void_pp]),
     "qgsb_ensemble_destroy": (None, [ctypes.c_void_p]),
     "qgsb_ensemble_upload": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),

@@ -106,6 +106,142 @@ __global__ void __launch_bounds__(128) ginelli_kernel(const __grid_constant__ Gi
     }
 }
 
+
+// ---- subspace intersection (lyapunov.py:1315-1320) ---------------------------------------------------------------
+// CLV j of a record is the direction common to span(BLV_0..j) and span(FLV_0..n-1-j).  The reference takes the
+// first left singular vector of BLV[:, :j+1]^T FLV[:, :n-j] (whose largest singular value is 1: the two bases are
+// orthonormal and the dimensions add up to n + 1).  Equivalently u spans the null space of the j x (j+1) matrix
+// C_j = FLV[:, n-j:]^T BLV[:, :j+1], a corner of the single n x n matrix P = FLV^T BLV -- so one block per
+// (member, record) forms P once and finds every null vector by Gauss-Jordan elimination with pivoting inside
+// the row (thread = column), no SVD.  The sign of a singular vector is arbitrary; here the component of largest
+// modulus of u is positive.
+struct SubspaceParams {
+    long n_pairs;            // members of the batch x records
+    long R;                  // records (stride of the last axis of the arrays)
+    int n;
+    const double *bvec;      // (Nb, n, n, R)
+    const double *fvec;      // (Nb, n, n, R)
+    double *vec;             // (Nb, n, n, R)
+};
+
+__global__ void __launch_bounds__(64) subspace_kernel(const __grid_constant__ SubspaceParams P)
+{
+    extern __shared__ __align__(16) double smem_sub[];
+    const int n = P.n, tid = threadIdx.x, ld = n + 1;
+    const long pair = blockIdx.x, member = pair / P.R, rec = pair % P.R;
+    double *B = smem_sub;                    // (n, ld)   B[i][k] = BLV k, component i
+    double *F = B + (size_t)n * ld;
+    double *Pm = F + (size_t)n * ld;         // (n, ld)   Pm[a][b] = FLV_a . BLV_b
+    double *C = Pm + (size_t)n * ld;         // (n, ld)   work matrix
+    double *u = C + (size_t)n * ld;          // (n + 1)
+    __shared__ int perm[64], s_col;
+    __shared__ double s_best[2];
+    __shared__ int s_arg[2];
+    const size_t base = (size_t)member * n * n * P.R + rec;
+    for (int q = tid; q < n * n; q += blockDim.x) {
+        const int i = q / n, k = q - i * n;
+        B[i * ld + k] = P.bvec[base + (size_t)q * P.R];
+        F[i * ld + k] = P.fvec[base + (size_t)q * P.R];
+    }
+    __syncthreads();
+    for (int q = tid; q < n * n; q += blockDim.x) {
+        const int a = q / n, b = q - a * n;
+        double acc = 0.;
+        for (int i = 0; i < n; ++i) acc += F[i * ld + a] * B[i * ld + b];
+        Pm[a * ld + b] = acc;
+    }
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        const int cols = j + 1;              // unknowns; rows = j
+        // C = Pm[n-j : n, 0 : j+1]
+        for (int q = tid; q < j * cols; q += blockDim.x) {
+            const int r = q / cols, c = q - r * cols;
+            C[r * ld + c] = Pm[(n - j + r) * ld + c];
+        }
+        if (tid < cols) perm[tid] = 0;       // row + 1 once the column has been the pivot of that row
+        __syncthreads();
+        for (int k = 0; k < j; ++k) {
+            // pivot: the largest entry of row k among the columns not used yet
+            double best = -1.;
+            int arg = -1;
+            if (tid < cols && perm[tid] == 0) {
+                best = fabs(C[k * ld + tid]);
+                arg = tid;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (oa >= 0 && (arg < 0 || ob > best || (ob == best && oa < arg))) {
+                    best = ob;
+                    arg = oa;
+                }
+            }
+            if ((tid & 31) == 0) {
+                s_best[tid >> 5] = best;
+                s_arg[tid >> 5] = arg;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int p = s_arg[0];
+                if (s_arg[1] >= 0 && (p < 0 || s_best[1] > s_best[0])) p = s_arg[1];
+                s_col = p;
+            }
+            __syncthreads();
+            const int p = s_col;
+            const double piv = C[k * ld + p];
+            // Gauss-Jordan: clear column p in every other row; thread = column
+            if (tid < cols && tid != p && piv != 0.) {
+                const double ckc = C[k * ld + tid] / piv;
+                for (int r = 0; r < j; ++r)
+                    if (r != k) C[r * ld + tid] -= C[r * ld + p] * ckc;
+            }
+            __syncthreads();                  // everybody is done reading column p
+            if (tid < j && tid != k) C[tid * ld + p] = 0.;
+            if (tid == 0) perm[p] = k + 1;
+            __syncthreads();
+        }
+        // the one column never used as pivot is the free unknown: u_free = 1, u_p = -C[row(p)][free] / C[row(p)][p]
+        if (tid < cols) {
+            int freec = 0;
+            for (int c = 0; c < cols; ++c)
+                if (perm[c] == 0) freec = c;
+            double val = 1.;
+            if (perm[tid] != 0) {
+                const int r = perm[tid] - 1;
+                const double d = C[r * ld + tid];
+                val = d != 0. ? -C[r * ld + freec] / d : 0.;
+            }
+            u[tid] = val;
+        }
+        __syncthreads();
+        // normalise, largest component positive
+        if (tid < 32) {
+            double s2 = 0., big = 0.;
+            for (int c = tid; c < cols; c += 32) {
+                s2 += u[c] * u[c];
+                if (fabs(u[c]) > fabs(big)) big = u[c];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                const double ob = __shfl_xor_sync(0xffffffffu, big, o);
+                if (fabs(ob) > fabs(big)) big = ob;
+            }
+            const double scale = (big < 0. ? -1. : 1.) / sqrt(s2);
+            for (int c = tid; c < cols; c += 32) u[c] *= scale;
+        }
+        __syncthreads();
+        // clv_j = BLV[:, :j+1] @ u
+        if (tid < n) {
+            double acc = 0.;
+            for (int k = 0; k < cols; ++k) acc += B[tid * ld + k] * u[k];
+            P.vec[base + ((size_t)tid * n + j) * P.R] = acc;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace qgsb
 
 using namespace qgsb;
@@ -219,5 +355,40 @@ extern "C" int qgsb_clv_ginelli(const qgsb_tensor *t, long N, const double *ic, 
         total_ms += ms;
     }
     if (device_ms) *device_ms = total_ms;
+    QGSB_API_END
+}
+
+extern "C" int qgsb_clv_subspace_intersect(long N, int n, long R, const double *bvec, const double *fvec, double *vec)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(bvec && fvec && vec, "null argument");
+    QGSB_REQUIRE(N >= 1 && R >= 1 && n >= 1 && n <= 63, "sizes out of range (n_dim <= 63)");
+    ensure_init();
+    Context &cx = ctx();
+    cudaStream_t st = cx.stream;
+    const size_t per_member = (size_t)n * n * R;
+    const size_t budget = std::min<size_t>(cx.total_mem / 4, (size_t)24 << 30);
+    const long batch = std::max<long>(1, std::min<long>(N, (long)(budget / (3 * per_member * sizeof(double)))));
+    DevBuf<double> d_b((size_t)batch * per_member), d_f((size_t)batch * per_member), d_v((size_t)batch * per_member);
+    const size_t bytes = (4 * (size_t)n * (n + 1) + (n + 2)) * sizeof(double);
+    if (bytes > 48 * 1024)
+        QGSB_CUDA(cudaFuncSetAttribute(subspace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    for (long m0 = 0; m0 < N; m0 += batch) {
+        const long nb = std::min(batch, N - m0);
+        d_b.upload(bvec + (size_t)m0 * per_member, (size_t)nb * per_member, st);
+        d_f.upload(fvec + (size_t)m0 * per_member, (size_t)nb * per_member, st);
+        SubspaceParams P;
+        P.n_pairs = nb * R;
+        P.R = R;
+        P.n = n;
+        P.bvec = d_b.p;
+        P.fvec = d_f.p;
+        P.vec = d_v.p;
+        subspace_kernel<<<(unsigned)P.n_pairs, 64, bytes, st>>>(P);
+        count_launch();
+        QGSB_CUDA(cudaGetLastError());
+        d_v.download(vec + (size_t)m0 * per_member, (size_t)nb * per_member, st);
+        QGSB_CUDA(cudaStreamSynchronize(st));
+    }
     QGSB_API_END
 }

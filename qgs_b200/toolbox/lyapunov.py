@@ -272,7 +272,7 @@ class CovariantLyapunovsEstimator(_EstimatorBase):
 
     ``method`` 0: Ginelli et al. (forward Benettin pass storing every ``Q`` and ``R`` in HBM and the backward
     triangular recursion, both on the GPU: ``qgsb_clv_ginelli``); ``method`` 1: intersection of the BLV and FLV subspaces (both
-    Benettin passes on the GPU, SVDs on the host).
+    Benettin passes and the per-record intersections on the GPU: ``qgsb_clv_subspace_intersect``).
     """
 
     def __init__(self, num_threads=None, b=None, c=None, a=None, number_of_dimensions=None, noise_pert=0.,
@@ -348,13 +348,10 @@ class CovariantLyapunovsEstimator(_EstimatorBase):
         traj, exp, bvec = benettin(self.func, self.func_jac, self.ic, 0, n_dim, q0, r0, pretime, time, mdt,
                                    self.write_steps, False, 1., self.b, self.c, self.a)
         n_records = traj.shape[-1]
-        recorded_vec = np.zeros((n_traj, n_dim, n_dim, n_records))
-        for i_traj in range(n_traj):
-            for ti in range(n_records):
-                for j in range(n_dim):
-                    u, z, w = np.linalg.svd(bvec[i_traj, :, :j + 1, ti].T @ fvec[i_traj, :, :n_dim - j, ti])
-                    basis = bvec[i_traj, :, :j + 1, ti] @ u
-                    recorded_vec[i_traj, :, j, ti] = basis[:, 0]
+        # intersection of the BLV / FLV subspaces of every record (lyapunov.py:1315-1320) on the device
+        recorded_vec = np.empty((n_traj, n_dim, n_dim, n_records))
+        _lib.check(_lib.load().qgsb_clv_subspace_intersect(n_traj, n_dim, n_records, _lib.dptr(_lib.f64(bvec)),
+                                                           _lib.dptr(_lib.f64(fvec)), _lib.dptr(recorded_vec)))
         # local exponents: one micro-step of the tangent model on every (member, record) pair (:1322-1327)
         subtime = np.array([0., mdt])
         ys = np.ascontiguousarray(np.moveaxis(traj, 2, 1).reshape(n_traj * n_records, n_dim))
