@@ -41,7 +41,7 @@ struct GinelliParams {
     double *out_vec;         // (Nb, n, m, R)
 };
 
-__global__ void __launch_bounds__(128) ginelli_kernel(const __grid_constant__ GinelliParams P)
+__global__ void __launch_bounds__(1024) ginelli_kernel(const __grid_constant__ GinelliParams P)
 {
     extern __shared__ __align__(16) double smem_clv[];
     const int n = P.n, m = P.m, c = threadIdx.x;
@@ -258,7 +258,7 @@ extern "C" int qgsb_clv_ginelli(const qgsb_tensor *t, long N, const double *ic, 
     QGSB_REQUIRE(t && ic && q0 && dt_macro && sub_ptr && sub_dt && am0 && dte && rec_traj && rec_exp && rec_vec,
                  "null argument");
     QGSB_REQUIRE(N >= 1 && n_pre >= 0 && n_time >= 0 && n_after >= 0 && write_steps >= 0, "bad sizes");
-    QGSB_REQUIRE(n_vec >= 1 && n_vec <= t->view.n && n_vec <= 128, "n_vec must be in 1..min(n_dim, 128)");
+    QGSB_REQUIRE(n_vec >= 1 && n_vec <= t->view.n && n_vec <= 1024, "n_vec must be in 1..min(n_dim, 1024)");
     QGSB_REQUIRE(t->jnnz_in > 0, "tensor handle has no Jacobian tensor");
     QGSB_REQUIRE(noise_pert == 0. || noise != nullptr, "noise_pert needs a noise array");
     ensure_init();
@@ -340,9 +340,11 @@ extern "C" int qgsb_clv_ginelli(const qgsb_tensor *t, long N, const double *ic, 
         G.out_exp = d_oe.p;
         G.out_vec = d_ov.p;
         const size_t bytes = (mm + (size_t)m * (m + 1)) * sizeof(double);
+        QGSB_REQUIRE(bytes <= cx.smem_optin, "n_vec = %d: the backward recursion keeps two n_vec x n_vec matrices in "
+                     "shared memory (%zu bytes > %zu)", m, bytes, cx.smem_optin);
         if (bytes > 48 * 1024)
             QGSB_CUDA(cudaFuncSetAttribute(ginelli_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        ginelli_kernel<<<(unsigned)nb, std::max(32, (m + 31) / 32 * 32), bytes, st>>>(G);
+        ginelli_kernel<<<(unsigned)nb, std::max(32, (m + 31) / 32 * 32), bytes, st>>>(G);   // thread = column of A
         count_launch();
         QGSB_CUDA(cudaGetLastError());
         QGSB_CUDA(cudaEventRecord(cx.ev1, st));

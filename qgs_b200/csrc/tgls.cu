@@ -20,7 +20,7 @@
 namespace qgsb {
 
 struct TgShared {
-    double *xs, *y, *Y, *K, *Jv, *rdiag, *red, *fm, *kms, *KM;
+    double *xs, *y, *Y, *K, *Jv, *rdiag, *mexp, *red, *fm, *kms, *KM;
 };
 
 __device__ __forceinline__ TgShared carve(unsigned char *raw, const TensorView &T, const TgParams &P, long member)
@@ -34,6 +34,7 @@ __device__ __forceinline__ TgShared carve(unsigned char *raw, const TensorView &
     S.K = p;             p += (size_t)s * n;
     S.Jv = p;            p += T.jac.npos;
     S.rdiag = p;         p += m;
+    S.mexp = p;          p += m;      // local exponent of every vector at the last macro step
     S.red = p;           p += 64;
     double *mat = P.scratch ? P.scratch + (size_t)member * P.scratch_per_member : p;
     S.fm = mat;
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __
     __syncthreads();
     const size_t sbase = P.stored ? tile_base(member, n) : 0;
     long iw = 0;
-    double mexp = 0.;  // thread c < m keeps the local exponent of vector c
+    for (int c = tid; c < m; c += TG_THREADS) S.mexp[c] = 0.;
     for (long step = 0; step < steps; ++step) {
         if (P.stored) {                                                   // lyapunov.py:513 / :527
             const double *src = P.stored + (size_t)P.start_idx[step] * n * P.stored_ld + sbase;
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __
         }
         if (step >= P.n_pre) {
             const long ti = step - P.n_pre;
-            if (tid < m) mexp = log(fabs(S.rdiag[tid])) / P.dt_macro[step];   // :611 / :531
+            for (int c = tid; c < m; c += TG_THREADS) S.mexp[c] = log(fabs(S.rdiag[c])) / P.dt_macro[step];   // :611 / :531
             if (P.q_all) {
                 double *qa = P.q_all + ((size_t)member * (P.n_rec + 1) + ti) * nm;
                 for (int q = tid; q < nm; q += TG_THREADS) qa[q] = S.fm[q];
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __
                 for (int r = tid; r < n; r += TG_THREADS) ry[r] = S.Y[r];
                 if (P.rec_fm)
                     for (int q = tid; q < nm; q += TG_THREADS) rv[q] = S.fm[q];
-                if (tid < m) re[tid] = mexp;
+                for (int c = tid; c < m; c += TG_THREADS) re[c] = S.mexp[c];
                 ++iw;
             }
         }
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __
         for (int r = tid; r < n; r += TG_THREADS) ry[r] = S.Y[r];
         if (P.rec_fm)
             for (int q = tid; q < nm; q += TG_THREADS) rv[q] = S.fm[q];
-        if (tid < m) re[tid] = mexp;
+        for (int c = tid; c < m; c += TG_THREADS) re[c] = S.mexp[c];
         if (P.q_all) {
             double *qa = P.q_all + ((size_t)member * (P.n_rec + 1) + P.n_rec) * nm;
             for (int q = tid; q < nm; q += TG_THREADS) qa[q] = S.fm[q];
@@ -488,7 +489,7 @@ __global__ void moments_kernel(const double *__restrict__ y, long N, int n, doub
 static size_t tg_small_doubles(const qgsb_tensor *t, int m, int s)
 {
     const int n = t->view.n;
-    return (size_t)(n + 1) + 2 * (size_t)n + (size_t)s * n + t->view.jac.npos + m + 64;
+    return (size_t)(n + 1) + 2 * (size_t)n + (size_t)s * n + t->view.jac.npos + 2 * (size_t)m + 64;
 }
 
 static void fill_common(TgParams &P, const Tableau &tab, long N, int m, int adjoint, double inverse)
@@ -651,7 +652,6 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
     QGSB_REQUIRE(N >= 1, "need at least one trajectory");
     QGSB_REQUIRE(forward >= 0 && forward <= 2, "mode must be 0 (BLV), 1 (FLV) or 2 (BLV following the micro-steps)");
     QGSB_REQUIRE(n_vec >= 1 && n_vec <= t->view.n, "n_vec must be in 1..n_dim");
-    QGSB_REQUIRE(n_vec <= TG_THREADS, "n_vec larger than %d is not supported by the Benettin kernel", TG_THREADS);
     QGSB_REQUIRE(n_pre >= 0 && n_rec >= 0 && write_steps >= 0, "negative step count");
     QGSB_REQUIRE(t->jnnz_in > 0, "tensor handle has no Jacobian tensor");
     ensure_init();

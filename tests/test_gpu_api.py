@@ -494,3 +494,26 @@ def test_subspace_clvs_against_the_reference_itself(monkeypatch):
     sign = np.sign(np.sum(vecs * ref, axis=0, keepdims=True))
     assert rel(vecs * sign, ref) < 1e-7
     assert np.max(np.abs(exps - np.squeeze(g["sub_exp"]))) < 1e-6 * max(1., np.max(np.abs(g["sub_exp"])))
+
+
+def test_large_basis_lyapunov_more_vectors_than_a_block_has_threads():
+    """The 228-variable 6x6 model with n_vec = 150 > 128 (the generic Benettin kernel's block size): BLVs against
+    the oracle for the same start basis."""
+    import oracle
+    from qgs_b200.toolbox import lyapunov as lyap
+    f, Df, T = model("atm6x6")
+    b, c, a = oracle.rk4_tableau()
+    rng = np.random.default_rng(12)
+    ic = rng.random((2, 228)) * 0.01
+    np.random.seed(5)
+    q0, r0 = lyap._random_basis(2, 228, 150)
+    np.random.seed(5)
+    est = lyap.LyapunovsEstimator()
+    est.set_func(f, Df)
+    est.compute_lyapunovs(0., 0.3, 0.8, 0.1, 0.1, ic=ic, write_steps=2, n_vec=150)
+    t, traj, exps, vecs = est.get_lyapunovs()
+    pre = np.concatenate((np.arange(0., 0.3, 0.1), [0.3]))
+    tim = np.concatenate((np.arange(0.3, 0.8, 0.1), [0.8]))
+    rt, re, rv = oracle.compute_backward_lyap(T, pre, tim, 0.1, ic, 150, 2, False, 1., b, c, a, q0, r0)
+    assert exps.shape == (2, 150, 4)
+    assert rel(traj, rt) < 1e-10 and rel(exps, re) < 1e-7 and rel(vecs, rv) < 1e-7
