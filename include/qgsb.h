@@ -176,6 +176,13 @@ QGSB_API int qgsb_ensemble_integrate_record(qgsb_ensemble *e, long n_steps, cons
                                    double *d_rec, double *device_ms);
 /* Sum and sum of squares over members for every variable (ensemble statistics; NCCL all-reduce of
  * these 2n doubles is done by the caller across ranks). */
+/* Same integration, but the records stream to the caller's host array traj (N, n, n_records) -- the layout of
+ * qgsb_rk_integrate / get_trajectories() -- in chunks while the next chunk integrates; device memory is bounded
+ * independently of n_records and the ensemble stays resident (qgs_maooam.py:115-136 with write_steps > 0). */
+QGSB_API int qgsb_ensemble_integrate_trajectories(qgsb_ensemble *e, long n_steps, const double *dt, int s,
+                                                  const double *a, const double *b, const double *c,
+                                                  long write_steps, int time_direction, long n_records,
+                                                  double *traj, double *device_ms);
 QGSB_API int qgsb_ensemble_moments(qgsb_ensemble *e, double *sum /* (n) */, double *sumsq /* (n) */);
 /* Integrate the resident ensemble and return, for every record of integrate.py:190-221 (n_records of them), the
  * per-variable sum and sum of squares over the members -- the ensemble statistics of

@@ -72,6 +72,9 @@ _PROTOTYPES = {
     "qgsb_ensemble_integrate_record": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_long, c_double_p, ctypes.c_int,
                                                       c_double_p, c_double_p, c_double_p, ctypes.c_long,
                                                       ctypes.c_long, ctypes.c_void_p, c_double_p]),
+    "qgsb_ensemble_integrate_trajectories": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_long, c_double_p, ctypes.c_int,
+                                                            c_double_p, c_double_p, c_double_p, ctypes.c_long,
+                                                            ctypes.c_int, ctypes.c_long, c_double_p, c_double_p]),
     "qgsb_ensemble_moments": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p]),
     "qgsb_ensemble_integrate_moments": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_long, c_double_p, ctypes.c_int,
                                                        c_double_p, c_double_p, c_double_p, ctypes.c_long,

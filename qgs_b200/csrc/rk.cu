@@ -1236,6 +1236,90 @@ int qgsb_ensemble_integrate_moments(qgsb_ensemble *e, long n_steps, const double
     QGSB_API_END
 }
 
+// Trajectory streaming for the resident ensemble (the chunked-run idiom of
+// qgs_maooam.py:115-136 with write_steps > 0): the records of a bounded number of write steps are kept in HBM,
+// turned into the API layout and copied into the strided slice traj[:, :, r0:r1] of the caller's (N, n, R) array on
+// the copy stream while the next chunk integrates (two buffers).  Device memory no longer grows with R.
+int qgsb_ensemble_integrate_trajectories(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                                         const double *b, const double *c, long write_steps, int time_direction,
+                                         long R, double *traj, double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(e && traj, "null argument");
+    QGSB_REQUIRE(n_steps >= 0 && write_steps >= 0, "negative step count");
+    QGSB_REQUIRE(n_steps == 0 || dt != nullptr, "null dt array");
+    QGSB_REQUIRE(time_direction == 1 || time_direction == -1, "time_direction must be +1 or -1");
+    QGSB_REQUIRE(R == records_for(n_steps, write_steps), "n_records %ld inconsistent with %ld steps / write_steps %ld",
+                 R, n_steps, write_steps);
+    ensure_init();
+    Context &cx = ctx();
+    cudaStream_t st = cx.stream, so = cx.copy_out;
+    const Tableau tab = make_tableau(s, a, b);
+    const int n = e->tensor->view.n;
+    const long N = e->N, ld = e->ld;
+    const long rows = N * n;
+    PoolBuf<double> d_dt(std::max<long>(n_steps, 1));
+    if (n_steps) d_dt.upload(dt, n_steps, st);
+    const bool flip = time_direction == -1;
+    // regular records r = 0 .. R-2 (state before step r * write_steps) in chunks, then the final state as record R-1
+    const size_t rec_bytes = (size_t)n * ld * sizeof(double);
+    const long budget = std::max<long>(2, (long)(std::min<size_t>(cx.total_mem / 16, (size_t)4 << 30) / rec_bytes));
+    long per_chunk = std::max<long>(1, std::min<long>(std::max<long>(R - 1, 1), budget - 1));
+    if (const char *env = getenv("QGSB_STREAM_RECORDS")) per_chunk = std::max<long>(1, std::min<long>(per_chunk, atol(env)));
+    PoolBuf<double> d_rec((size_t)(per_chunk + 1) * n * ld);
+    PoolBuf<double> d_out0((size_t)rows * (per_chunk + 1)), d_out1((size_t)rows * (per_chunk + 1));
+    cudaEvent_t ready[2], freed[2];
+    for (int q = 0; q < 2; ++q) {
+        QGSB_CUDA(cudaEventCreateWithFlags(&ready[q], cudaEventDisableTiming));
+        QGSB_CUDA(cudaEventCreateWithFlags(&freed[q], cudaEventDisableTiming));
+    }
+    QGSB_CUDA(cudaEventRecord(cx.ev0, st));
+    int buf = 0;
+    auto ship = [&](double *d_out, long r0, long count) {
+        // host columns [h0, h0 + count) of every (member, variable) row; the record axis is reversed for backward runs
+        const long h0 = flip ? R - (r0 + count) : r0;
+        QGSB_CUDA(cudaEventRecord(ready[buf], st));
+        QGSB_CUDA(cudaStreamWaitEvent(so, ready[buf], 0));
+        QGSB_CUDA(cudaMemcpy2DAsync(traj + h0, (size_t)R * sizeof(double), d_out, (size_t)count * sizeof(double),
+                                    (size_t)count * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, so));
+        QGSB_CUDA(cudaEventRecord(freed[buf], so));
+        buf ^= 1;
+        QGSB_CUDA(cudaStreamWaitEvent(st, freed[buf], 0));    // the buffer about to be refilled has been shipped
+    };
+    if (write_steps > 0) {
+        for (long r0 = 0; r0 < R - 1; r0 += per_chunk) {
+            const long r1 = std::min(R - 1, r0 + per_chunk);
+            const long step0 = r0 * write_steps, step1 = std::min(n_steps, r1 * write_steps);
+            const long steps = step1 - step0, rc = records_for(steps, write_steps);
+            rk_advance(e->tensor, e->d_y.p, ld, N, steps, d_dt.p + step0, tab, write_steps, rc, d_rec.p);
+            double *d_out = buf ? d_out1.p : d_out0.p;
+            launch_rec_to_api(d_rec.p, d_out, N, n, r1 - r0, ld, flip ? 1 : 0);
+            ship(d_out, r0, r1 - r0);
+        }
+    } else {
+        rk_advance(e->tensor, e->d_y.p, ld, N, n_steps, d_dt.p, tab, 0, 1, nullptr);
+    }
+    {
+        double *d_out = buf ? d_out1.p : d_out0.p;
+        launch_rec_to_api(e->d_y.p, d_out, N, n, 1, ld, 0);
+        QGSB_CUDA(cudaEventRecord(cx.ev1, st));
+        ship(d_out, R - 1, 1);
+    }
+    QGSB_CUDA(cudaStreamSynchronize(so));
+    QGSB_CUDA(cudaStreamSynchronize(st));
+    for (int q = 0; q < 2; ++q) {
+        cudaEventDestroy(ready[q]);
+        cudaEventDestroy(freed[q]);
+    }
+    if (device_ms) {
+        float ms = 0.f;
+        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+        *device_ms = ms;
+    }
+    QGSB_API_END
+}
+
 void *qgsb_ensemble_device_ptr(qgsb_ensemble *e) { return e ? (void *)e->d_y.p : nullptr; }
 long qgsb_ensemble_ld(const qgsb_ensemble *e) { return e ? e->ld : 0; }
 

@@ -131,6 +131,44 @@ class DeviceEnsemble(object):
         self.time = time[-1] if forward else time[0]
         return ms.value
 
+    def integrate_trajectories(self, t0, t, dt, forward=True, write_steps=1, b=None, c=None, a=None, out=None):
+        """Advance every member from ``t0`` to ``t`` and return ``(time, traj)`` exactly as
+        ``RungeKuttaIntegrator.integrate`` + ``get_trajectories`` would (``traj`` ``(n_local, n_dim, n_records)``, not
+        squeezed), but from the state resident on the device -- no initial conditions are uploaded -- and with the
+        records streamed to the host in chunks while the integration goes on, so device memory does not grow with
+        the number of records.  ``out`` may be a preallocated (e.g. pinned) array."""
+        if a is None and b is None and c is None:
+            b, c, a = rk4_tableau()
+        time = np.concatenate((np.arange(t0, t, dt), np.full((1,), t)))
+        steps = directed_dt(time, 1 if forward else -1)
+        ws = int(write_steps)
+        rec_time = self._record_times(time, ws, forward)
+        R = len(rec_time)
+        b, c, a = _lib.f64(b), _lib.f64(c), _lib.f64(a)
+        if out is None:
+            out = np.empty((self.n_traj, self.n_dim, R))
+        if out.shape != (self.n_traj, self.n_dim, R) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape %s" % ((self.n_traj, self.n_dim, R),))
+        ms = ctypes.c_double()
+        _lib.check(_lib.load().qgsb_ensemble_integrate_trajectories(
+            self._handle, len(steps), _lib.dptr(steps), len(b), _lib.dptr(a), _lib.dptr(b), _lib.dptr(c), ws,
+            1 if forward else -1, R, _lib.dptr(out), ctypes.byref(ms)))
+        self.time = time[-1] if forward else time[0]
+        self.last_ms = ms.value
+        return rec_time, out
+
+    @staticmethod
+    def _record_times(time, ws, forward):
+        """Returned time vector of integrator.py:409-424 (for write_steps == 0 the reference returns time[-1] in both
+        directions)."""
+        if ws > 0 and forward:
+            rec_time = time[::ws]
+            return rec_time if rec_time[-1] == time[-1] else np.concatenate((rec_time, time[-1:]))
+        if ws > 0:
+            rec_time = time[::-ws][::-1]
+            return rec_time if rec_time[0] == time[0] else np.concatenate((time[:1], rec_time))
+        return time[-1:]
+
     def integrate_moments(self, t0, t, dt, forward=True, write_steps=1, b=None, c=None, a=None):
         """Advance every member from ``t0`` to ``t`` and return ``(time, mean, var)`` of the ensemble at every
         record the reference would write (integrate.py:190-221, integrator.py:397-424): ``mean`` and ``var`` have
@@ -144,18 +182,7 @@ class DeviceEnsemble(object):
         steps = directed_dt(time, 1 if forward else -1)
         n_steps = len(steps)
         ws = int(write_steps)
-        # returned time vector: integrator.py:409-424 (for write_steps == 0 the reference returns time[-1] in both
-        # directions)
-        if ws > 0 and forward:
-            rec_time = time[::ws]
-            if rec_time[-1] != time[-1]:
-                rec_time = np.concatenate((rec_time, time[-1:]))
-        elif ws > 0:
-            rec_time = time[::-ws][::-1]
-            if rec_time[0] != time[0]:
-                rec_time = np.concatenate((time[:1], rec_time))
-        else:
-            rec_time = time[-1:]
+        rec_time = self._record_times(time, ws, forward)
         R = len(rec_time)
         b, c, a = _lib.f64(b), _lib.f64(c), _lib.f64(a)
         s1, s2 = np.empty((R, self.n_dim)), np.empty((R, self.n_dim))

@@ -517,3 +517,32 @@ def test_large_basis_lyapunov_more_vectors_than_a_block_has_threads():
     rt, re, rv = oracle.compute_backward_lyap(T, pre, tim, 0.1, ic, 150, 2, False, 1., b, c, a, q0, r0)
     assert exps.shape == (2, 150, 4)
     assert rel(traj, rt) < 1e-10 and rel(exps, re) < 1e-7 and rel(vecs, rv) < 1e-7
+
+
+# ---- f-4: trajectory streaming from the resident ensemble ------------------------------------------------------------------
+@pytest.mark.parametrize("ws,forward,chunk", [(1, True, "3"), (4, True, "2"), (5, False, "2"), (0, True, "1"), (3, True, "")])
+def test_streamed_trajectories_equal_the_integrator(ws, forward, chunk):
+    """DeviceEnsemble.integrate_trajectories (records shipped chunk by chunk, state resident) is bitwise what
+    RungeKuttaIntegrator.integrate + get_trajectories return; a second call continues from the resident state."""
+    from qgs_b200.ensemble import DeviceEnsemble
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator
+    f, Df, T = model("maooam36")
+    ic = np.random.default_rng(14).random((300, 36)) * 0.01
+    integ = RungeKuttaIntegrator()
+    integ.set_func(f)
+    integ.integrate(0., 2.3, 0.1, ic=ic, forward=forward, write_steps=ws)
+    time, traj = integ.get_trajectories()
+    if chunk:
+        os.environ["QGSB_STREAM_RECORDS"] = chunk
+    try:
+        ens = DeviceEnsemble(f, ic)
+        t2, got = ens.integrate_trajectories(0., 2.3, 0.1, forward=forward, write_steps=ws)
+        assert np.array_equal(np.atleast_1d(time), t2)
+        assert np.array_equal(got, traj.reshape(got.shape))
+        if forward and ws:
+            # continue from the resident end state: same as restarting the integrator from its last record
+            t3, more = ens.integrate_trajectories(2.3, 3.1, 0.1, write_steps=ws)
+            integ.integrate(2.3, 3.1, 0.1, ic=traj[:, :, -1], write_steps=ws)
+            assert np.array_equal(more, integ.get_trajectories()[1])
+    finally:
+        os.environ.pop("QGSB_STREAM_RECORDS", None)
