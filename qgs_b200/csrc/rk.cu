@@ -984,6 +984,71 @@ static long records_for(long n_steps, long write_steps)
 
 extern "C" {
 
+// Trajectory streaming (the chunked-run idiom of qgs_maooam.py:115-136 with
+// write_steps > 0): the records of a bounded number of write steps are kept in HBM, turned into the API layout and
+// copied into the strided slice traj[:, :, r0:r1] of the caller's (N, n, R) array on the copy stream while the next
+// chunk integrates (two buffers).  Device memory does not grow with R.  d_y (n, ld) tiled is advanced in place.
+// ev0 / ev1 of the context bracket the integration.
+static void stream_trajectories(const qgsb_tensor *t, double *d_y, long ld, long N, long n_steps, const double *d_dt,
+                                const Tableau &tab, long write_steps, int time_direction, long R, double *traj)
+{
+    Context &cx = ctx();
+    cudaStream_t st = cx.stream, so = cx.copy_out;
+    const int n = t->view.n;
+    const long rows = N * n;
+    const bool flip = time_direction == -1;
+    // regular records r = 0 .. R-2 (state before step r * write_steps) in chunks, then the final state as record R-1
+    const size_t rec_bytes = (size_t)n * ld * sizeof(double);
+    const long budget = std::max<long>(2, (long)(std::min<size_t>(cx.total_mem / 16, (size_t)4 << 30) / rec_bytes));
+    long per_chunk = std::max<long>(1, std::min<long>(std::max<long>(R - 1, 1), budget - 1));
+    if (const char *env = getenv("QGSB_STREAM_RECORDS")) per_chunk = std::max<long>(1, std::min<long>(per_chunk, atol(env)));
+    PoolBuf<double> d_rec((size_t)(per_chunk + 1) * n * ld);
+    PoolBuf<double> d_out0((size_t)rows * per_chunk), d_out1((size_t)rows * per_chunk);
+    cudaEvent_t ready[2], freed[2];
+    for (int q = 0; q < 2; ++q) {
+        QGSB_CUDA(cudaEventCreateWithFlags(&ready[q], cudaEventDisableTiming));
+        QGSB_CUDA(cudaEventCreateWithFlags(&freed[q], cudaEventDisableTiming));
+    }
+    QGSB_CUDA(cudaEventRecord(cx.ev0, st));
+    int buf = 0;
+    auto ship = [&](double *d_out, long r0, long count) {
+        // host columns [h0, h0 + count) of every (member, variable) row; the record axis is reversed for backward runs
+        const long h0 = flip ? R - (r0 + count) : r0;
+        QGSB_CUDA(cudaEventRecord(ready[buf], st));
+        QGSB_CUDA(cudaStreamWaitEvent(so, ready[buf], 0));
+        QGSB_CUDA(cudaMemcpy2DAsync(traj + h0, (size_t)R * sizeof(double), d_out, (size_t)count * sizeof(double),
+                                    (size_t)count * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, so));
+        QGSB_CUDA(cudaEventRecord(freed[buf], so));
+        buf ^= 1;
+        QGSB_CUDA(cudaStreamWaitEvent(st, freed[buf], 0));    // the buffer about to be refilled has been shipped
+    };
+    if (write_steps > 0) {
+        for (long r0 = 0; r0 < R - 1; r0 += per_chunk) {
+            const long r1 = std::min(R - 1, r0 + per_chunk);
+            const long step0 = r0 * write_steps, step1 = std::min(n_steps, r1 * write_steps);
+            const long steps = step1 - step0, rc = records_for(steps, write_steps);
+            rk_advance(t, d_y, ld, N, steps, d_dt + step0, tab, write_steps, rc, d_rec.p);
+            double *d_out = buf ? d_out1.p : d_out0.p;
+            launch_rec_to_api(d_rec.p, d_out, N, n, r1 - r0, ld, flip ? 1 : 0);
+            ship(d_out, r0, r1 - r0);
+        }
+    } else {
+        rk_advance(t, d_y, ld, N, n_steps, d_dt, tab, 0, 1, nullptr);
+    }
+    {
+        double *d_out = buf ? d_out1.p : d_out0.p;
+        launch_rec_to_api(d_y, d_out, N, n, 1, ld, 0);
+        QGSB_CUDA(cudaEventRecord(cx.ev1, st));
+        ship(d_out, R - 1, 1);
+    }
+    QGSB_CUDA(cudaStreamSynchronize(so));
+    QGSB_CUDA(cudaStreamSynchronize(st));
+    for (int q = 0; q < 2; ++q) {
+        cudaEventDestroy(ready[q]);
+        cudaEventDestroy(freed[q]);
+    }
+}
+
 int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_steps, const double *dt, int s,
                       const double *a, const double *b, const double *c, long write_steps, int time_direction,
                       long R, double *traj, double *device_ms)
@@ -1004,7 +1069,7 @@ int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_ste
     const int n = t->view.n;
     const long ld = round_up(N, TILE);
     PoolBuf<double> d_ic((size_t)N * n), d_y((size_t)n * ld), d_dt(std::max<long>(n_steps, 1));
-    PoolBuf<double> d_rec, d_out((size_t)N * n * R);
+    PoolBuf<double> d_out(R == 1 ? (size_t)N * n : 1);
     if (n_steps) d_dt.upload(dt, n_steps, st);
     if (R == 1) {
         // write_steps == 0 (or a single time point): only the end state is returned (integrate.py:221).
@@ -1061,13 +1126,16 @@ int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_ste
         QGSB_CUDA(cudaEventRecord(cx.ev1, st));
         launch_soa_to_aos(d_y.p, d_out.p, N, n, ld);
     } else {
+        // trajectories: records stream to the caller's array chunk by chunk (bounded device memory)
         d_ic.upload(ic, (size_t)N * n, st);
         launch_aos_to_soa(d_ic.p, d_y.p, N, n, ld);
-        d_rec.alloc((size_t)R * n * ld);
-        QGSB_CUDA(cudaEventRecord(cx.ev0, st));
-        rk_advance(t, d_y.p, ld, N, n_steps, d_dt.p, tab, write_steps, R, d_rec.p);
-        QGSB_CUDA(cudaEventRecord(cx.ev1, st));
-        launch_rec_to_api(d_rec.p, d_out.p, N, n, R, ld, time_direction == -1);
+        stream_trajectories(t, d_y.p, ld, N, n_steps, d_dt.p, tab, write_steps, time_direction, R, traj);
+        if (device_ms) {
+            float ms = 0.f;
+            QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+            *device_ms = ms;
+        }
+        return 0;
     }
     d_out.download(traj, (size_t)N * n * R, st);
     QGSB_CUDA(cudaStreamSynchronize(st));
@@ -1236,10 +1304,7 @@ int qgsb_ensemble_integrate_moments(qgsb_ensemble *e, long n_steps, const double
     QGSB_API_END
 }
 
-// Trajectory streaming for the resident ensemble (the chunked-run idiom of
-// qgs_maooam.py:115-136 with write_steps > 0): the records of a bounded number of write steps are kept in HBM,
-// turned into the API layout and copied into the strided slice traj[:, :, r0:r1] of the caller's (N, n, R) array on
-// the copy stream while the next chunk integrates (two buffers).  Device memory no longer grows with R.
+// The resident ensemble's records streamed to the host (see stream_trajectories).
 int qgsb_ensemble_integrate_trajectories(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
                                          const double *b, const double *c, long write_steps, int time_direction,
                                          long R, double *traj, double *device_ms)
@@ -1254,64 +1319,10 @@ int qgsb_ensemble_integrate_trajectories(qgsb_ensemble *e, long n_steps, const d
                  R, n_steps, write_steps);
     ensure_init();
     Context &cx = ctx();
-    cudaStream_t st = cx.stream, so = cx.copy_out;
     const Tableau tab = make_tableau(s, a, b);
-    const int n = e->tensor->view.n;
-    const long N = e->N, ld = e->ld;
-    const long rows = N * n;
     PoolBuf<double> d_dt(std::max<long>(n_steps, 1));
-    if (n_steps) d_dt.upload(dt, n_steps, st);
-    const bool flip = time_direction == -1;
-    // regular records r = 0 .. R-2 (state before step r * write_steps) in chunks, then the final state as record R-1
-    const size_t rec_bytes = (size_t)n * ld * sizeof(double);
-    const long budget = std::max<long>(2, (long)(std::min<size_t>(cx.total_mem / 16, (size_t)4 << 30) / rec_bytes));
-    long per_chunk = std::max<long>(1, std::min<long>(std::max<long>(R - 1, 1), budget - 1));
-    if (const char *env = getenv("QGSB_STREAM_RECORDS")) per_chunk = std::max<long>(1, std::min<long>(per_chunk, atol(env)));
-    PoolBuf<double> d_rec((size_t)(per_chunk + 1) * n * ld);
-    PoolBuf<double> d_out0((size_t)rows * (per_chunk + 1)), d_out1((size_t)rows * (per_chunk + 1));
-    cudaEvent_t ready[2], freed[2];
-    for (int q = 0; q < 2; ++q) {
-        QGSB_CUDA(cudaEventCreateWithFlags(&ready[q], cudaEventDisableTiming));
-        QGSB_CUDA(cudaEventCreateWithFlags(&freed[q], cudaEventDisableTiming));
-    }
-    QGSB_CUDA(cudaEventRecord(cx.ev0, st));
-    int buf = 0;
-    auto ship = [&](double *d_out, long r0, long count) {
-        // host columns [h0, h0 + count) of every (member, variable) row; the record axis is reversed for backward runs
-        const long h0 = flip ? R - (r0 + count) : r0;
-        QGSB_CUDA(cudaEventRecord(ready[buf], st));
-        QGSB_CUDA(cudaStreamWaitEvent(so, ready[buf], 0));
-        QGSB_CUDA(cudaMemcpy2DAsync(traj + h0, (size_t)R * sizeof(double), d_out, (size_t)count * sizeof(double),
-                                    (size_t)count * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, so));
-        QGSB_CUDA(cudaEventRecord(freed[buf], so));
-        buf ^= 1;
-        QGSB_CUDA(cudaStreamWaitEvent(st, freed[buf], 0));    // the buffer about to be refilled has been shipped
-    };
-    if (write_steps > 0) {
-        for (long r0 = 0; r0 < R - 1; r0 += per_chunk) {
-            const long r1 = std::min(R - 1, r0 + per_chunk);
-            const long step0 = r0 * write_steps, step1 = std::min(n_steps, r1 * write_steps);
-            const long steps = step1 - step0, rc = records_for(steps, write_steps);
-            rk_advance(e->tensor, e->d_y.p, ld, N, steps, d_dt.p + step0, tab, write_steps, rc, d_rec.p);
-            double *d_out = buf ? d_out1.p : d_out0.p;
-            launch_rec_to_api(d_rec.p, d_out, N, n, r1 - r0, ld, flip ? 1 : 0);
-            ship(d_out, r0, r1 - r0);
-        }
-    } else {
-        rk_advance(e->tensor, e->d_y.p, ld, N, n_steps, d_dt.p, tab, 0, 1, nullptr);
-    }
-    {
-        double *d_out = buf ? d_out1.p : d_out0.p;
-        launch_rec_to_api(e->d_y.p, d_out, N, n, 1, ld, 0);
-        QGSB_CUDA(cudaEventRecord(cx.ev1, st));
-        ship(d_out, R - 1, 1);
-    }
-    QGSB_CUDA(cudaStreamSynchronize(so));
-    QGSB_CUDA(cudaStreamSynchronize(st));
-    for (int q = 0; q < 2; ++q) {
-        cudaEventDestroy(ready[q]);
-        cudaEventDestroy(freed[q]);
-    }
+    if (n_steps) d_dt.upload(dt, n_steps, cx.stream);
+    stream_trajectories(e->tensor, e->d_y.p, e->ld, e->N, n_steps, d_dt.p, tab, write_steps, time_direction, R, traj);
     if (device_ms) {
         float ms = 0.f;
         QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
