@@ -348,3 +348,17 @@ def test_reference_arm_runs_the_installed_reference_and_agrees_with_the_oracle()
         "print('reference arm ok', err)\n" % REPO)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=REPO)
     assert out.returncode == 0 and "reference arm ok" in out.stdout, out.stderr[-3000:]
+
+
+def test_resident_ensemble_record_times_follow_the_integrator_rules():
+    """DeviceEnsemble's record-time vector (streamed trajectories, record moments) == the time vector
+    RungeKuttaIntegrator.get_trajectories returns (integrator.py:409-424), forward, backward, ragged, write_steps 0."""
+    from qgs_b200.ensemble import DeviceEnsemble
+    from qgs_b200.integrators.integrate import returned_time
+    for t_end in (1.0, 1.35, 2.05):
+        time = np.concatenate((np.arange(0., t_end, 0.1), [t_end]))
+        for ws in (0, 1, 2, 3, 7, 50):
+            for forward in (True, False):
+                ref = np.atleast_1d(np.asarray(returned_time(time, 0., t_end, forward, ws)))
+                got = DeviceEnsemble._record_times(time, ws, forward)
+                assert np.array_equal(ref, got), (t_end, ws, forward)
