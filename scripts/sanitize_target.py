@@ -1,0 +1,80 @@
+"""One small invocation of every kernel family, for compute-sanitizer (memcheck / racecheck)."""
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from qgs_b200 import _lib  # noqa: E402
+from qgs_b200.ensemble import DeviceEnsemble  # noqa: E402
+from qgs_b200.functions.tendencies import tendencies_from_tensor  # noqa: E402
+from qgs_b200.integrators.integrator import RungeKuttaIntegrator, RungeKuttaTglsIntegrator  # noqa: E402
+from qgs_b200.toolbox.lyapunov import CovariantLyapunovsEstimator, LyapunovsEstimator  # noqa: E402
+
+_lib.init(0)
+which = sys.argv[1:] or ["rk", "large", "tangent", "clv", "stats"]
+
+
+def load(name):
+    z = np.load(os.path.join(REPO, "tests", "golden", "tensor_%s.npz" % name))
+    return tendencies_from_tensor(int(z["ndim"]), z["coo"], z["val"], z["jcoo"], z["jval"])
+
+
+rng = np.random.default_rng(0)
+if "rk" in which:
+    f, Df = load("maooam36")
+    integ = RungeKuttaIntegrator()
+    integ.set_func(f)
+    for rows_max, N in (("2048", 3), ("0", 200)):            # rows kernel; specialised kernel
+        os.environ["QGSB_RK_ROWS_MAX"] = rows_max
+        integ.integrate(0., 0.5, 0.1, ic=rng.random((N, 36)) * 0.01, write_steps=2)
+    f.tensor.use_specialised(False)
+    integ.integrate(0., 0.3, 0.1, ic=rng.random((130, 36)) * 0.01, write_steps=0)      # generic G1
+    os.environ.pop("QGSB_RK_ROWS_MAX")
+    print("rk ok", flush=True)
+if "large" in which:
+    f, Df = load("atm6x6")
+    integ = RungeKuttaIntegrator()
+    integ.set_func(f)
+    integ.integrate(0., 0.2, 0.1, ic=rng.random((2, 228)) * 0.01, write_steps=1)       # wide kernel
+    os.environ["QGSB_RK_ROWS_MAX"] = "0"
+    integ.integrate(0., 0.2, 0.1, ic=rng.random((100, 228)) * 0.01, write_steps=1)     # G3
+    os.environ["QGSB_RK_LARGE"] = "g2"
+    integ.integrate(0., 0.1, 0.1, ic=rng.random((5, 228)) * 0.01, write_steps=0)       # G2
+    os.environ.pop("QGSB_RK_ROWS_MAX")
+    os.environ.pop("QGSB_RK_LARGE")
+    print("large ok", flush=True)
+if "tangent" in which:
+    f, Df = load("maooam36")
+    tg = RungeKuttaTglsIntegrator()
+    tg.set_func(f, Df)
+    ic = rng.random((9, 36)) * 0.01
+    for kern in ("pack", "pack_dense", "reg", "generic"):
+        os.environ["QGSB_TGLS_KERNEL"] = kern
+        tg.integrate(0., 0.3, 0.1, ic=ic, write_steps=1)
+        tg.integrate(0., 0.2, 0.1, ic=ic, write_steps=0, adjoint=True, inverse=True)
+        est = LyapunovsEstimator()
+        est.set_func(f, Df)
+        est.compute_lyapunovs(0., 0.2, 0.5, 0.1, 0.05, ic=ic, write_steps=1, n_vec=36 if kern != "generic" else 7)
+        est.compute_lyapunovs(0., 0.2, 0.5, 0.1, 0.1, ic=ic, write_steps=2, n_vec=20, forward=True)
+    os.environ.pop("QGSB_TGLS_KERNEL")
+    print("tangent ok", flush=True)
+if "clv" in which:
+    f, Df = load("rp")
+    ic = rng.random((3, 20)) * 0.1
+    for method in (0, 1):
+        est = CovariantLyapunovsEstimator(method=method)
+        est.set_func(f, Df)
+        est.compute_clvs(0., 0.3, 0.8, 1.2, 0.1, 0.1, ic=ic, write_steps=2, method=method)
+    print("clv ok", flush=True)
+if "stats" in which:
+    f, Df = load("rp")
+    ens = DeviceEnsemble(f, rng.random((300, 20)) * 0.1)
+    os.environ["QGSB_STREAM_RECORDS"] = "2"
+    ens.integrate_trajectories(0., 0.7, 0.1, write_steps=1)
+    ens.integrate_moments(0.7, 1.2, 0.1, write_steps=2)
+    ens.moments()
+    f(0., rng.random((600, 20)))
+    Df(0., rng.random((4, 20)))
+    print("stats ok", flush=True)
