@@ -546,3 +546,57 @@ def test_streamed_trajectories_equal_the_integrator(ws, forward, chunk):
             assert np.array_equal(more, integ.get_trajectories()[1])
     finally:
         os.environ.pop("QGSB_STREAM_RECORDS", None)
+
+
+# ---- drop-in acceptance: the reference's own setup code + the overlay, on the device -----------------------------------------
+def test_overlay_runs_the_reference_workflow_on_the_gpu(tmp_path):
+    """The flow of qgs_maooam.py:78-117 -- QgParams, create_tendencies, RungeKuttaIntegrator.set_func / integrate /
+    get_trajectories, then the TGLS integrator -- written against the ORIGINAL dotted names, with `overlay/` in front
+    of the installed reference (baseline/_ref): parameters, inner products and the tensor are built by the
+    reference's code, the hot path runs on CUDA, and the result equals the run from the tensor fixture bitwise."""
+    import subprocess
+    import sys
+    ref_dir = os.path.join(REPO, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "qgs")):
+        pytest.skip("baseline/_ref is not installed")
+    out = tmp_path / "traj.npz"
+    code = (
+        "import warnings; warnings.filterwarnings('ignore')\n"
+        "import numpy as np\n"
+        "from qgs.params.params import QgParams\n"
+        "from qgs.functions.tendencies import create_tendencies\n"
+        "from qgs.integrators.integrator import RungeKuttaIntegrator, RungeKuttaTglsIntegrator\n"
+        "p = QgParams()\n"
+        "p.set_atmospheric_channel_fourier_modes(2, 2)\n"
+        "p.set_oceanic_basin_fourier_modes(2, 4)\n"
+        "p.set_params({'kd': 0.0290, 'kdp': 0.0290, 'n': 1.5, 'r': 1.e-7, 'h': 136.5, 'd': 1.1e-7})\n"
+        "p.atemperature_params.set_params({'eps': 0.7, 'T0': 289.3, 'hlambda': 15.06, })\n"
+        "p.gotemperature_params.set_params({'gamma': 5.6e8, 'T0': 301.46})\n"
+        "p.atemperature_params.set_insolation(103.3333, 0)\n"
+        "p.gotemperature_params.set_insolation(310., 0)\n"
+        "f, Df = create_tendencies(p)\n"
+        "assert type(f).__module__ == 'qgs_b200.functions.tendencies'\n"
+        "ic = np.random.default_rng(3).random((5, p.ndim)) * 0.01\n"
+        "integrator = RungeKuttaIntegrator()\n"
+        "integrator.set_func(f)\n"
+        "integrator.integrate(0., 10., 0.1, ic=ic, write_steps=5)\n"
+        "time, traj = integrator.get_trajectories()\n"
+        "tgls = RungeKuttaTglsIntegrator()\n"
+        "tgls.set_func(f, Df)\n"
+        "tgls.integrate(0., 1., 0.1, ic=ic[0], write_steps=0)\n"
+        "t2, x2, fm = tgls.get_trajectories()\n"
+        "np.savez(%r, time=time, traj=traj, ic=ic, fm=fm)\n"
+        "print('workflow ok', traj.shape, fm.shape)\n" % str(out))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(REPO, "overlay"), ref_dir]))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600, cwd=str(tmp_path))
+    assert res.returncode == 0 and "workflow ok" in res.stdout, res.stderr[-3000:]
+    z = np.load(out)
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator
+    f, Df, T = model("maooam36")
+    integ = RungeKuttaIntegrator()
+    integ.set_func(f)
+    integ.integrate(0., 10., 0.1, ic=z["ic"], write_steps=5)
+    time, traj = integ.get_trajectories()
+    assert np.array_equal(time, z["time"]) and z["traj"].shape == (5, 36, 21)
+    assert np.array_equal(traj, z["traj"])
+    assert z["fm"].shape == (36, 36) and np.all(np.isfinite(z["fm"]))
