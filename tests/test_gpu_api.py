@@ -600,3 +600,33 @@ def test_overlay_runs_the_reference_workflow_on_the_gpu(tmp_path):
     assert np.array_equal(time, z["time"]) and z["traj"].shape == (5, 36, 21)
     assert np.array_equal(traj, z["traj"])
     assert z["fm"].shape == (36, 36) and np.all(np.isfinite(z["fm"]))
+
+
+def test_leading_lyapunov_exponents_match_oracle_statistically():
+    """Long-run criterion of BASELINE.json: the leading Lyapunov exponents of an ensemble, estimated on the GPU and by
+    the CPU oracle from DIFFERENT random start bases, agree within the sampling error of the ensemble means
+    (RP-20 model, 48 members, 300 time units after a 100-unit transient; 4 standard errors, and 15 % for the sum)."""
+    import oracle
+    from qgs_b200.toolbox import lyapunov as lyap
+    f, Df, T = model("rp")
+    b, c, a = oracle.rk4_tableau()
+    rng = np.random.default_rng(33)
+    n_mem, n_vec = 48, 6
+    ic0 = rng.random((n_mem, 20)) * 0.1
+    spin = np.concatenate((np.arange(0., 500., 0.1), [500.]))
+    ic = oracle.integrate_runge_kutta_jit(T, spin, ic0, 1, 0, b, c, a)[:, :, 0]      # on the attractor
+    np.random.seed(1)
+    est = lyap.LyapunovsEstimator()
+    est.set_func(f, Df)
+    est.compute_lyapunovs(0., 100., 400., 0.1, 0.1, ic=ic, write_steps=10, n_vec=n_vec, vectors=False)
+    g = est.get_lyapunovs()[2].reshape(n_mem, n_vec, -1).mean(axis=2)               # (members, vectors)
+    pre = np.concatenate((np.arange(0., 100., 0.1), [100.]))
+    tim = np.concatenate((np.arange(100., 400., 0.1), [400.]))
+    q0 = np.stack([np.linalg.qr(rng.random((20, n_vec)))[0] for _ in range(n_mem)])
+    r0 = np.stack([np.eye(n_vec)] * n_mem)
+    o = oracle.compute_backward_lyap(T, pre, tim, 0.1, ic, n_vec, 10, False, 1., b, c, a, q0, r0)[1].mean(axis=2)
+    se = np.sqrt(g.var(axis=0) / n_mem + o.var(axis=0) / n_mem)
+    z = np.abs(g.mean(axis=0) - o.mean(axis=0)) / np.maximum(se, 1e-6)
+    assert np.all(z < 4.), (z, g.mean(axis=0), o.mean(axis=0))
+    assert g.mean(axis=0)[0] > 0.                       # the RP model is chaotic at these parameters
+    assert abs(g.mean(axis=0).sum() - o.mean(axis=0).sum()) < 0.15 * abs(o.mean(axis=0).sum()) + 3 * se.sum()
