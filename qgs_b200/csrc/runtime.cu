@@ -153,10 +153,40 @@ void register_spec(const SpecKernels *k) { registry()[k->hash] = k; }
 
 // the specialised tangent kernels bake in the sparsity pattern of the Jacobian tensor the module was generated
 // with; a handle created with another jcoo must not use them
+// FNV-1a over the (i, j)-sorted Jacobian entries kept by prepare_mat: all index tuples (int32), then all values
+static uint64_t jacobian_hash(const qgsb_tensor *t)
+{
+    uint64_t h = 1469598103934665603ULL;
+    auto mix = [&h](const void *p, size_t bytes) {
+        const unsigned char *c = (const unsigned char *)p;
+        for (size_t q = 0; q < bytes; ++q) {
+            h ^= (uint64_t)c[q];
+            h *= 1099511628211ULL;
+        }
+    };
+    const int rank = t->view.rank;
+    for (size_t p = 0; p < t->h_pos_i.size(); ++p)
+        for (int e = t->h_pos_ptr[p]; e < t->h_pos_ptr[p + 1]; ++e) {
+            const Entry &en = t->h_jent[e];
+            int32_t idx[5] = {t->h_pos_i[p], t->h_pos_j[p], 0, 0, 0};
+            if (rank == 5) {
+                idx[2] = (int32_t)(en.jk & 0xffffu);
+                idx[3] = (int32_t)(en.jk >> 16);
+                idx[4] = (int32_t)en.lm;
+            } else {
+                idx[2] = (int32_t)en.jk;
+            }
+            mix(idx, sizeof(int32_t) * rank);
+        }
+    for (const Entry &en : t->h_jent) mix(&en.v, sizeof(double));
+    return h;
+}
+
 static bool jacobian_matches(const qgsb_tensor *t)
 {
     const SpecKernels *k = t->spec;
     if (!k || !k->tangent || !k->jac_slot_table) return false;
+    if (k->jac_hash != 0) return jacobian_hash(t) == k->jac_hash;      // value-baked product: exact tensor only
     const int n = t->view.n;
     for (size_t p = 0; p < t->h_pos_i.size(); ++p) {
         const int i = t->h_pos_i[p], j = t->h_pos_j[p];

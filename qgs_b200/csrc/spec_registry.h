@@ -36,6 +36,8 @@ struct SpecKernels {
                            size_t smem_limit, cudaStream_t stream);
     int jac_slots;                 // doubles of shared memory holding the position values of one member
     const short *jac_slot_table;   // (n, n) row-major: slot of position (i, j), -1 where J_ij is structurally zero
+    uint64_t jac_hash;             // != 0: the tangent product has the Jacobian tensor's VALUES baked in (bilinear
+                                   // form); FNV-1a over its (i, j)-sorted entries -- see jacobian_hash()
 };
 
 void register_spec(const SpecKernels *k);

@@ -49,7 +49,7 @@ bool pack_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m)
     // a block must hold enough columns to fill its warps: with very few columns per member the per-member shared
     // state limits the packing and the generic kernel (one block per member) is the better fit
     const int jv = (spec_tangent_usable(t) && force != 2) ? t->spec->jac_slots : n * n;
-    const size_t per_member = (size_t)(jv + 8 * n + 2 * (size_t)n * m + 3 * m + 32) * sizeof(double);
+    const size_t per_member = (size_t)(jv + 10 * n + 2 * (size_t)n * m + 3 * m + 40) * sizeof(double);
     const int G = std::min<int>(pack::MAX_THREADS / m, (int)(ctx().smem_optin / per_member));
     return G >= 1 && G * m >= 96;
 }
@@ -110,8 +110,8 @@ const PackTables &pack_tables(const qgsb_tensor *t, bool spec)
             pc->tab.EF = EF;
         }
     }
-    // Jacobian positions, in the list order of the product policy
-    {
+    // Jacobian positions, in the list order of the product policy (not needed by a value-baked bilinear product)
+    if (!(spec && t->spec && t->spec->jac_hash != 0)) {
         const int npos = (int)t->h_pos_i.size();
         std::vector<int> order(npos);        // order[q] = position p served by list entry q
         std::vector<unsigned short> slots(npos);

@@ -53,7 +53,8 @@ struct Carve {
     __host__ __device__ Carve(int jv_, int m) : jv(even(jv_)), mp(even(m)), nm(even(N * m)) {}
     __host__ __device__ int o_jv() const { return 0; }
     __host__ __device__ int o_xs() const { return jv; }                 // N + 2 (xs[0] = 1)
-    __host__ __device__ int o_y() const { return o_xs() + even(N + 2); }
+    __host__ __device__ int o_xs2() const { return o_xs() + even(N + 2); }       // second stage-state buffer
+    __host__ __device__ int o_y() const { return o_xs2() + even(N + 2); }
     __host__ __device__ int o_Y() const { return o_y() + even(N); }
     __host__ __device__ int o_kst() const { return o_Y() + even(N); }
     __host__ __device__ int o_yacc() const { return o_kst() + even(N); }
@@ -74,7 +75,7 @@ struct Carve {
 
 template <int N>
 struct Mem {
-    double *jv, *xs, *y, *Y, *kst, *yacc, *rdiag, *tau, *scal, *fm, *facc;
+    double *jv, *xs, *xs2, *y, *Y, *kst, *yacc, *rdiag, *tau, *scal, *fm, *facc;
     int m;
 };
 
@@ -85,6 +86,7 @@ __device__ __forceinline__ Mem<N> carve(double *base, int jv, int m)
     Mem<N> S;
     S.jv = base + c.o_jv();
     S.xs = base + c.o_xs();
+    S.xs2 = base + c.o_xs2();
     S.y = base + c.o_y();
     S.Y = base + c.o_Y();
     S.kst = base + c.o_kst();
@@ -101,14 +103,17 @@ __device__ __forceinline__ Mem<N> carve(double *base, int jv, int m)
 // ---- product policies ------------------------------------------------------------------------------------------
 // A policy provides
 //   JV              doubles of shared memory per member for the Jacobian values
+//   kUsesJacobianValues   false: apply() works from the stage state xs directly (generated bilinear form)
 //   slot(i, j)      where the value of position (i, j) (1-based) goes inside that area
-//   apply(jv, col, km)   km = (J or J^T) @ col
+//   apply(jv, xs, col, km)   km = (J or J^T) @ col
 template <int N, bool ADJ>
 struct DenseProduct {
     static constexpr int JV = N * N;
+    static constexpr bool kUsesJacobianValues = true;
     static constexpr bool kZeroFill = true;   // structural zeros must read as 0
     __device__ static __forceinline__ int slot(int i, int j) { return (i - 1) * N + (j - 1); }
-    __device__ static __forceinline__ void apply(const double *jv, const double (&col)[N], double (&km)[N])
+    __device__ static __forceinline__ void apply(const double *jv, const double *, const double (&col)[N],
+                                                 double (&km)[N])
     {
 #pragma unroll
         for (int i = 0; i < N; ++i) km[i] = 0.;
@@ -255,21 +260,26 @@ __device__ __forceinline__ void tangent_step(const TensorView &T, const ShTab &t
         const double wa_in = st > 0 ? dt * P.a[st * s + st - 1] : 0.;       // (dt a[st]) @ k   integrate.py:216
         const double wb = dt * P.b[st];
         const double wa_out = st + 1 < s ? dt * P.a[(st + 1) * s + st] : 0.;
+        // The stage state alternates between two buffers: a thread that is already forming the state of the next
+        // stage cannot disturb a thread that still reads this one.  Products that work from the stage state itself
+        // (generated bilinear form) then need ONE barrier per stage; those that read Jacobian values built by the
+        // whole member need a second one.
+        double *xs = (st & 1) ? S.xs2 : S.xs;
         if (live)
-            for (int r = c; r < N; r += m) S.xs[r + 1] = st > 0 ? S.y[r] + wa_in * S.kst[r] : S.y[r];
+            for (int r = c; r < N; r += m) xs[r + 1] = st > 0 ? S.y[r] + wa_in * S.kst[r] : S.y[r];
         __syncthreads();
         if (live) {
             for (int r = c; r < N; r += m) {
-                const double k = f_row_tab<N>(T, tab, r, S.xs);
+                const double k = f_row_tab<N>(T, tab, r, xs);
                 S.kst[r] = k;
                 S.yacc[r] = st == 0 ? wb * k : S.yacc[r] + wb * k;
             }
-            jac_build<N, Prod>(T, tab, S.xs, S.jv, c, m);
+            if (Prod::kUsesJacobianValues) jac_build<N, Prod>(T, tab, xs, S.jv, c, m);
         }
-        __syncthreads();
+        if (Prod::kUsesJacobianValues) __syncthreads();
         if (live) {
             // km = inverse * (J or J^T) @ col        integrate.py:601-603, boundary == 0
-            Prod::apply(S.jv, col, km);
+            Prod::apply(S.jv, xs, col, km);
             double *fc = S.facc + c;
             const double *fmc = S.fm + c;
 #pragma unroll
@@ -291,6 +301,8 @@ __device__ __forceinline__ void tangent_step(const TensorView &T, const ShTab &t
             fmc[i * m] = col[i];
         }
     }
+    // an odd number of stages ends on the buffer the next step starts with
+    if (s & 1) __syncthreads();
 }
 
 // one nonlinear step of the macro ("stored") trajectory: S.Y <- RK(S.Y, dt)
@@ -459,7 +471,10 @@ __device__ __forceinline__ void init_member(const Mem<N> &S, int c, bool live)
         S.kst[r] = 0.;
         S.yacc[r] = 0.;
     }
-    if (c == 0) S.xs[0] = 1.;
+    if (c == 0) {
+        S.xs[0] = 1.;
+        S.xs2[0] = 1.;
+    }
 }
 
 // ---- plain tangent-linear integration (integrate.py:555-614) ----------------------------------------------------------

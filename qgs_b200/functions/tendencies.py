@@ -87,7 +87,7 @@ class DeviceTensor(object):
         Returns True when the handle now runs specialised kernels; silently stays on the generic
         CUDA kernels when the tensor is too large or nvcc is not installed."""
         from qgs_b200 import codegen
-        path = codegen.build_plugin(self.ndim, self.rank, self.coo, self.val, jcoo=self.jcoo)
+        path = codegen.build_plugin(self.ndim, self.rank, self.coo, self.val, jcoo=self.jcoo, jval=self.jval)
         if path is None:
             return False
         _lib.check(_lib.load().qgsb_load_plugin(path.encode()))
