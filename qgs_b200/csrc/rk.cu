@@ -324,7 +324,7 @@ struct G3Chunk {
 constexpr int G3_CHUNK = 256;               // entries per chunk
 constexpr int G3_STRIDE = G3_CHUNK + 4;     // the software pipeline reads one group of four past the end of a chunk
 constexpr int G3_RING = 2;
-constexpr int G3_MAX_GROUPS = 4;
+constexpr int G3_MAX_GROUPS = 8;
 
 struct G3Plan {
     int groups;
@@ -348,7 +348,7 @@ __device__ __forceinline__ void g3_fetch(G3Entry *ring, const G3Entry *__restric
 
 #define G3_X(off) (*reinterpret_cast<const double *>(xb + (off)))
 
-__global__ void __launch_bounds__(128 * G3_MAX_GROUPS)
+__global__ void __launch_bounds__(512)
 rk_g3_kernel(int n, int mb, int n_chunks, const __grid_constant__ G3Plan plan, const G3Entry *__restrict__ ent,
              const G3Chunk *__restrict__ chunks_g, const int *__restrict__ rowlen_g,
              const __grid_constant__ RkParams P, double *__restrict__ acc_g, double *__restrict__ xn_g)
@@ -453,6 +453,125 @@ rk_g3_kernel(int n, int mb, int n_chunks, const __grid_constant__ G3Plan plan, c
     }
 }
 #undef G3_X
+
+// G3, two members per thread: a broadcast read of a 16-byte entry costs a warp as many shared-memory wavefronts as
+// its two 8-byte reads of x (one wavefront per 32-bit word and warp, broadcast or not), so half of G3's traffic is
+// the entry stream.  Here thread mt of a row group owns members 2 mt and 2 mt + 1 -- their x_j sit side by side and
+// come in one LDS.128 -- and an entry is read once for 64 members instead of 32: 6 instead of 8 wavefronts per
+// term and 32 members.  Twice the rows groups (8) keep as many warps in flight with 64 members per block.
+#define G3_X2(off) (*reinterpret_cast<const double2 *>(xb + (off)))
+__global__ void __launch_bounds__(512)
+rk_g3p_kernel(int n, int mb, int n_chunks, const __grid_constant__ G3Plan plan, const G3Entry *__restrict__ ent,
+              const G3Chunk *__restrict__ chunks_g, const int *__restrict__ rowlen_g,
+              const __grid_constant__ RkParams P, double *__restrict__ acc_g, double *__restrict__ xn_g)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, s = P.s, tg = mb >> 1;
+    const int h = tid / tg, mt = tid - h * tg;        // row group, member pair inside the block
+    G3Entry *rings = reinterpret_cast<G3Entry *>(smem_raw);
+    G3Chunk *chunks_all = reinterpret_cast<G3Chunk *>(rings + (size_t)G3_STRIDE * G3_RING * plan.groups);
+    int *rowlen = reinterpret_cast<int *>(chunks_all + n_chunks);
+    unsigned char *xb = reinterpret_cast<unsigned char *>(rowlen + ((n + 3) & ~3)) + (size_t)mt * 16;  // pair of x_i at xb + i mb 8
+    const size_t rowb = (size_t)mb * 8;
+    long member = (long)blockIdx.x * mb + 2 * mt;     // even: the pair never straddles a tile, and is 16-byte aligned
+    const bool act = member < P.ld;
+    if (!act) member = P.ld - 2;
+    const size_t gbase = tile_base(member, n);
+    double *yg = P.y + gbase, *ag = acc_g + gbase, *xg = xn_g + gbase;
+    G3Entry *ring = rings + (size_t)G3_STRIDE * G3_RING * h;
+    const G3Chunk *chunks = chunks_all + plan.chunk0[h];
+    const int per_stage = plan.chunk0[h + 1] - plan.chunk0[h];
+    const int r_lo = plan.row0[h], r_hi = plan.row0[h + 1];
+    for (int q = tid; q < G3_STRIDE * G3_RING * plan.groups; q += blockDim.x)
+        rings[q] = G3Entry{0., 0u, 0u};                // read-ahead lands on valid offsets
+    for (int q = tid; q < n_chunks; q += blockDim.x) chunks_all[q] = chunks_g[q];
+    for (int q = tid; q < n; q += blockDim.x) rowlen[q] = rowlen_g[q];
+    if (h == 0) *reinterpret_cast<double2 *>(xb) = make_double2(1., 1.);
+    for (int i = r_lo; i < r_hi; ++i)
+        *reinterpret_cast<double2 *>(xb + (size_t)(i + 1) * rowb) = *reinterpret_cast<const double2 *>(yg + (size_t)i * TILE);
+    __syncthreads();
+
+    const long total = (long)per_stage * s * P.n_steps;
+    long chunk = 0;
+    if (total > 0) g3_fetch(ring, ent, chunks, 0, per_stage, mt, tg);
+
+    long iw = 0;
+    for (long ti = 0; ti < P.n_steps; ++ti) {
+        const double dt = P.dt[ti];
+        if (P.rec && P.write_steps > 0 && ti % P.write_steps == 0) {       // integrate.py:210-212
+            if (act) {
+                double *r = P.rec + (size_t)iw * n * P.ld + gbase;
+                for (int i = r_lo; i < r_hi; ++i)
+                    *reinterpret_cast<double2 *>(r + (size_t)i * TILE) = *reinterpret_cast<const double2 *>(yg + (size_t)i * TILE);
+            }
+            ++iw;
+        }
+        for (int st = 0; st < s; ++st) {
+            const double wb = dt * P.b[st];
+            const double wa = st + 1 < s ? dt * P.alpha[st + 1] : 0.;
+            const bool last = st + 1 == s;
+            for (int c = 0; c < per_stage; ++c, ++chunk) {
+                asm volatile("cp.async.wait_group 0;");
+                asm volatile("bar.sync %0, %1;" ::"r"(h + 1), "r"(tg));   // chunk landed for the group; chunk - 1 consumed
+                if (chunk + 1 < total) g3_fetch(ring, ent, chunks, chunk + 1, per_stage, mt, tg);
+                const uint4 *pe = reinterpret_cast<const uint4 *>(ring + (size_t)(chunk % G3_RING) * G3_STRIDE);
+                const G3Chunk ch = chunks[c];
+                uint4 c0 = pe[0], c1 = pe[1], c2 = pe[2], c3 = pe[3];
+                for (int r = 0; r < ch.nrows; ++r) {
+                    const int groups = rowlen[ch.row0 + r] >> 2;
+                    const size_t o = (size_t)(ch.row0 + r) * TILE;
+                    const double2 y_old = *reinterpret_cast<const double2 *>(yg + o);   // in flight while the row is summed
+                    const double2 a_old = st == 0 ? make_double2(0., 0.) : *reinterpret_cast<const double2 *>(ag + o);
+                    double k0 = 0., k1 = 0., k2 = 0., k3 = 0., l0 = 0., l1 = 0., l2 = 0., l3 = 0.;
+#pragma unroll 2
+                    for (int g = 0; g < groups; ++g) {
+                        const double2 a0 = G3_X2(c0.z), b0 = G3_X2(c0.w), a1 = G3_X2(c1.z), b1 = G3_X2(c1.w);
+                        const double2 a2 = G3_X2(c2.z), b2 = G3_X2(c2.w), a3 = G3_X2(c3.z), b3 = G3_X2(c3.w);
+                        pe += 4;
+                        const uint4 n0 = pe[0], n1 = pe[1], n2 = pe[2], n3 = pe[3];
+                        const double v0 = __hiloint2double(c0.y, c0.x), v1 = __hiloint2double(c1.y, c1.x);
+                        const double v2 = __hiloint2double(c2.y, c2.x), v3 = __hiloint2double(c3.y, c3.x);
+                        k0 = fma(a0.x * b0.x, v0, k0);                         // (a*b)*value, then +=  (sparse_mul.py:79)
+                        l0 = fma(a0.y * b0.y, v0, l0);
+                        k1 = fma(a1.x * b1.x, v1, k1);
+                        l1 = fma(a1.y * b1.y, v1, l1);
+                        k2 = fma(a2.x * b2.x, v2, k2);
+                        l2 = fma(a2.y * b2.y, v2, l2);
+                        k3 = fma(a3.x * b3.x, v3, k3);
+                        l3 = fma(a3.y * b3.y, v3, l3);
+                        c0 = n0;
+                        c1 = n1;
+                        c2 = n2;
+                        c3 = n3;
+                    }
+                    const double k = (k0 + k1) + (k2 + k3), l = (l0 + l1) + (l2 + l3);
+                    if (act) {
+                        const double2 ac = make_double2(a_old.x + wb * k, a_old.y + wb * l);
+                        if (!last) {
+                            *reinterpret_cast<double2 *>(ag + o) = ac;
+                            *reinterpret_cast<double2 *>(xg + o) = make_double2(y_old.x + wa * k, y_old.y + wa * l);
+                        } else {
+                            const double2 yn = make_double2(y_old.x + ac.x, y_old.y + ac.y);
+                            *reinterpret_cast<double2 *>(yg + o) = yn;
+                            *reinterpret_cast<double2 *>(xg + o) = yn;
+                        }
+                    }
+                }
+            }
+            __syncthreads();               // every group is done reading x
+            for (int i = r_lo; i < r_hi; ++i)
+                *reinterpret_cast<double2 *>(xb + (size_t)(i + 1) * rowb) = *reinterpret_cast<const double2 *>(xg + (size_t)i * TILE);
+            __syncthreads();               // the next stage state is complete
+        }
+    }
+    asm volatile("cp.async.wait_group 0;");
+    if (P.rec && act) {                                                     // integrate.py:221
+        double *r = P.rec + (size_t)(P.n_records - 1) * n * P.ld + gbase;
+        for (int i = r_lo; i < r_hi; ++i)
+            *reinterpret_cast<double2 *>(r + (size_t)i * TILE) = *reinterpret_cast<const double2 *>(yg + (size_t)i * TILE);
+    }
+}
+#undef G3_X2
 
 // ------------------------------------------------------------------------------------------------
 // Rows kernel: the latency regime (few members, many steps -- the reference's example scripts integrate ONE
@@ -724,6 +843,7 @@ static bool g3_enabled()
 struct G3Host {
     G3Plan plan;
     int mb = 0, n_chunks = 0;
+    bool pairs = false;   // two members per thread (rk_g3p_kernel)
     DevBuf<G3Entry> ent;
     DevBuf<int> meta;      // chunk list (4 ints each), then the padded row lengths
     size_t smem = 0;
@@ -751,7 +871,9 @@ static bool g3_prepare(const qgsb_tensor *t)
     if (total == 0) return false;
     auto *c = new qgsb_tensor::G3Cache();
     G3Plan &plan = c->plan;
-    const int G = (int)std::min<long>(G3_MAX_GROUPS, std::max<long>(1, total / 2048));
+    const char *mode = getenv("QGSB_G3_MODE");          // "single": one member per thread, four row groups (A/B)
+    const bool pairs = !(mode && !strcmp(mode, "single"));
+    const int G = (int)std::min<long>(pairs ? G3_MAX_GROUPS : 4, std::max<long>(1, total / (pairs ? 1024 : 2048)));
     plan.groups = G;
     std::vector<G3Chunk> chunks;
     int row = 0;
@@ -785,7 +907,14 @@ static bool g3_prepare(const qgsb_tensor *t)
         delete c;
         return false;
     }
-    const int mb = (int)std::min<size_t>(128, (limit - fixed) / (8 * (size_t)(n + 1))) & ~31;
+    // a row group is whole warps: 32 members per warp, or 64 with two members per thread
+    int mb = (int)std::min<size_t>(128, (limit - fixed) / (8 * (size_t)(n + 1))) & ~31;
+    if (pairs) mb &= ~63;
+    if (mb < 32 || (pairs && mb < 64)) {
+        delete c;
+        return false;
+    }
+    c->pairs = pairs;
     c->mb = mb;
     c->smem = fixed + (size_t)(n + 1) * 8 * mb;
     std::vector<G3Entry> h;
@@ -818,11 +947,18 @@ static bool launch_g3(const qgsb_tensor *t, RkParams &P)
     }
     const qgsb_tensor::G3Cache *c = t->g3_cache;
     PoolBuf<double> d_acc((size_t)n * P.ld), d_xn((size_t)n * P.ld);
-    set_smem(rk_g3_kernel, c->smem);
     const unsigned grid = (unsigned)((P.ld + c->mb - 1) / c->mb);
-    rk_g3_kernel<<<grid, c->mb * c->plan.groups, c->smem, ctx().stream>>>(
-        n, c->mb, c->n_chunks, c->plan, c->ent.p, reinterpret_cast<const G3Chunk *>(c->meta.p),
-        c->meta.p + (size_t)c->n_chunks * 4, P, d_acc.p, d_xn.p);
+    if (c->pairs) {
+        set_smem(rk_g3p_kernel, c->smem);
+        rk_g3p_kernel<<<grid, (c->mb / 2) * c->plan.groups, c->smem, ctx().stream>>>(
+            n, c->mb, c->n_chunks, c->plan, c->ent.p, reinterpret_cast<const G3Chunk *>(c->meta.p),
+            c->meta.p + (size_t)c->n_chunks * 4, P, d_acc.p, d_xn.p);
+    } else {
+        set_smem(rk_g3_kernel, c->smem);
+        rk_g3_kernel<<<grid, c->mb * c->plan.groups, c->smem, ctx().stream>>>(
+            n, c->mb, c->n_chunks, c->plan, c->ent.p, reinterpret_cast<const G3Chunk *>(c->meta.p),
+            c->meta.p + (size_t)c->n_chunks * 4, P, d_acc.p, d_xn.p);
+    }
     count_launch();
     QGSB_CUDA(cudaGetLastError());
     // the scratch arrays go back to the pool here; every user of the pool runs on the same stream
