@@ -538,8 +538,6 @@ void benettin_dispatch(const qgsb_tensor *t, const Tableau &tab, TgParams &P, De
     cudaStream_t st = ctx().stream;
     if (pack_tangent_supported(t, tab, m)) {
         launch_pack_tangent(t, P, true);
-    } else if (reg_tangent_supported(t, tab, m)) {
-        launch_reg_tangent(t, P, true);
     } else if (t->view.rank == 5) {
         const size_t bytes = place_matrices(t, P, scratch, 0);
         set_smem_attr(lyap_kernel<5>, bytes);
@@ -612,8 +610,6 @@ int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long N, const double *ic, int m
     QGSB_CUDA(cudaEventRecord(cx.ev0, st));
     if (pack_tangent_supported(t, tab, m)) {
         launch_pack_tangent(t, P, false);
-    } else if (reg_tangent_supported(t, tab, m)) {
-        launch_reg_tangent(t, P, false);
     } else if (t->view.rank == 5) {
         const size_t bytes = place_matrices(t, P, scratch, 0);
         set_smem_attr(tgls_kernel<5>, bytes);

@@ -15,12 +15,11 @@ namespace qgsb {
 
 static int forced_kernel()
 {
-    // QGSB_TGLS_KERNEL = pack | pack_dense | reg | generic  (testing / A-B measurements)
+    // QGSB_TGLS_KERNEL = pack | pack_dense | generic  (testing / A-B measurements)
     const char *e = getenv("QGSB_TGLS_KERNEL");
     if (!e || !e[0]) return 0;
     if (!strcmp(e, "pack")) return 1;
     if (!strcmp(e, "pack_dense")) return 2;
-    if (!strcmp(e, "reg")) return 3;
     if (!strcmp(e, "generic")) return 4;
     return 0;
 }
@@ -42,7 +41,7 @@ static bool spec_tangent_usable(const qgsb_tensor *t)
 bool pack_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m)
 {
     const int force = forced_kernel();
-    if (force == 3 || force == 4) return false;
+    if (force == 4) return false;
     if (!tab.chain || m < 1 || m > pack::MAX_THREADS) return false;
     const int n = t->view.n;
     if (!(spec_tangent_usable(t) && force != 2) && !dense_ndim(n)) return false;

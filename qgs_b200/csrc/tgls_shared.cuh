@@ -1,4 +1,4 @@
-// tgls_shared.cuh -- declarations shared by the tangent-linear kernels (tgls.cu, tgls_reg.cu).
+// tgls_shared.cuh -- declarations shared by the tangent-linear kernels (tgls.cu, tgls_pack.cuh, clv.cu).
 #pragma once
 #include "common.cuh"
 #include "kernels.cuh"
@@ -113,9 +113,5 @@ void launch_transpose_records(const double *d_in, double *d_out, long R, long in
 // packed kernels (tgls_pack.cu / tgls_pack.cuh)
 bool pack_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m);
 void launch_pack_tangent(const qgsb_tensor *t, const TgParams &P, bool lyap);
-
-// register-resident kernels (tgls_reg.cu)
-bool reg_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m);
-void launch_reg_tangent(const qgsb_tensor *t, const TgParams &P, bool lyap);
 
 }  // namespace qgsb

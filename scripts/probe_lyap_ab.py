@@ -7,7 +7,7 @@ from qgs_b200 import _lib  # noqa: E402
 from scripts.perf_probe2 import lyap, tgls  # noqa: E402
 
 _lib.init(0)
-for variant in (sys.argv[1:] or ("reg", "pack_dense", "pack")):
+for variant in (sys.argv[1:] or ("generic", "pack_dense", "pack")):
     os.environ["QGSB_TGLS_KERNEL"] = variant
     print("== variant %s" % variant, flush=True)
     tgls("maooam36", 8192, 50)
