@@ -69,6 +69,8 @@ QGSB_API int qgsb_tensor_info(const qgsb_tensor *t, int *ndim, int *rank, long *
  * row internally).  Mirrors qgs_b200.codegen.tensor_hash. */
 QGSB_API int qgsb_tensor_hash(int ndim, int rank, long nnz, const int32_t *coo, const double *val, uint64_t *hash);
 /* Forbid / allow the tensor-specialised kernels for this handle (testing and benchmarking). */
+/* 1 when the handle runs generated tangent-linear / Benettin kernels (module loaded and its Jacobian tensor matches) */
+QGSB_API int qgsb_tensor_has_tangent(const qgsb_tensor *t);
 QGSB_API int qgsb_tensor_use_specialised(qgsb_tensor *t, int enable);
 
 /* ---- raw contractions, qgs/functions/sparse_mul.py ---------------------------------------------- */

@@ -34,6 +34,7 @@ _PROTOTYPES = {
                                         ctypes.POINTER(ctypes.c_uint64)]),
     "qgsb_tensor_hash": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_long, c_int32_p, c_double_p,
                                         ctypes.POINTER(ctypes.c_uint64)]),
+    "qgsb_tensor_has_tangent": (ctypes.c_int, [ctypes.c_void_p]),
     "qgsb_tensor_use_specialised": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "qgsb_sparse_mul3": (ctypes.c_int, [ctypes.c_long, c_int32_p, c_double_p, ctypes.c_int, c_double_p, c_double_p,
                                         c_double_p]),

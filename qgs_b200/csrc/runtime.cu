@@ -143,16 +143,37 @@ void ensure_init()
 // ------------------------------------------------------------------------------------------------
 // specialised-kernel registry
 // ------------------------------------------------------------------------------------------------
-static std::map<uint64_t, const SpecKernels *> &registry()
+static std::map<uint64_t, SpecKernels> &registry()
 {
-    static std::map<uint64_t, const SpecKernels *> r;
+    static std::map<uint64_t, SpecKernels> r;
     return r;
 }
 
-void register_spec(const SpecKernels *k) { registry()[k->hash] = k; }
+// A module may carry the Runge-Kutta part, the tangent part or both; parts registered for the same tensor are merged.
+void register_spec(const SpecKernels *k)
+{
+    auto it = registry().find(k->hash);
+    if (it == registry().end()) {
+        registry()[k->hash] = *k;
+        return;
+    }
+    SpecKernels &m = it->second;
+    if (k->rk_chain) m.rk_chain = k->rk_chain;
+    if (k->tendencies) m.tendencies = k->tendencies;
+    if (k->tangent) {
+        m.tangent = k->tangent;
+        m.jac_slots = k->jac_slots;
+        m.jac_slot_table = k->jac_slot_table;
+        m.jac_hash = k->jac_hash;
+    }
+}
 
-// the specialised tangent kernels bake in the sparsity pattern of the Jacobian tensor the module was generated
-// with; a handle created with another jcoo must not use them
+const SpecKernels *find_spec(uint64_t hash)
+{
+    auto it = registry().find(hash);
+    return it == registry().end() ? nullptr : &it->second;
+}
+
 // FNV-1a over the (i, j)-sorted Jacobian entries kept by prepare_mat: all index tuples (int32), then all values
 static uint64_t jacobian_hash(const qgsb_tensor *t)
 {
@@ -193,12 +214,6 @@ static bool jacobian_matches(const qgsb_tensor *t)
         if (i < 1 || j < 1 || i > n || j > n || k->jac_slot_table[(i - 1) * n + (j - 1)] < 0) return false;
     }
     return true;
-}
-
-const SpecKernels *find_spec(uint64_t hash)
-{
-    auto it = registry().find(hash);
-    return it == registry().end() ? nullptr : it->second;
 }
 
 uint64_t tensor_hash(int n, int rank, long nnz, const int32_t *coo_sorted, const double *val_sorted)
@@ -549,7 +564,8 @@ int qgsb_load_plugin(const char *path)
     entry_fn entry = (entry_fn)dlsym(h, "qgsb_plugin_kernels");
     QGSB_REQUIRE(entry != nullptr, "%s does not export qgsb_plugin_kernels", path);
     const SpecKernels *k = entry();
-    QGSB_REQUIRE(k != nullptr && k->rk_chain != nullptr, "%s returned an empty kernel table", path);
+    QGSB_REQUIRE(k != nullptr && (k->rk_chain != nullptr || k->tangent != nullptr), "%s returned an empty kernel table",
+                 path);
     register_spec(k);
     QGSB_API_END
 }
@@ -634,9 +650,14 @@ int qgsb_tensor_info(const qgsb_tensor *t, int *ndim, int *rank, long *nnz, long
     if (rank) *rank = t->view.rank;
     if (nnz) *nnz = t->nnz_in;
     if (jnnz) *jnnz = t->jnnz_in;
-    if (kernel_kind) *kernel_kind = (t->spec && t->use_spec) ? 2 : (t->view.n > QGSB_G1_MAX_NDIM ? 1 : 0);
+    if (kernel_kind) *kernel_kind = (t->spec && t->use_spec && t->spec->rk_chain) ? 2 : (t->view.n > QGSB_G1_MAX_NDIM ? 1 : 0);
     if (hash) *hash = t->hash;
     QGSB_API_END
+}
+
+int qgsb_tensor_has_tangent(const qgsb_tensor *t)
+{
+    return t && t->spec && t->use_spec && t->spec->tangent && t->jac_matches_spec ? 1 : 0;
 }
 
 int qgsb_tensor_use_specialised(qgsb_tensor *t, int enable)

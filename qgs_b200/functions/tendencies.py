@@ -12,6 +12,7 @@ kernels without ever calling back into Python.
 system of degree <= 2 (rank 3) or <= 4 (rank 5), e.g. Lorenz-63/84).
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -83,16 +84,46 @@ class DeviceTensor(object):
         _lib.check(_lib.load().qgsb_tensor_use_specialised(self.handle, 1 if enable else 0))
 
     def specialise(self):
-        """Build (or fetch from the cache) a tensor-specialised kernel module with nvcc and attach it.
-        Returns True when the handle now runs specialised kernels; silently stays on the generic
-        CUDA kernels when the tensor is too large or nvcc is not installed."""
+        """Build (or fetch from the cache) the tensor-specialised Runge-Kutta / tendencies kernels with nvcc (a few
+        seconds) and attach them.  Returns True when the handle now runs specialised kernels; silently stays on the
+        generic CUDA kernels when the tensor is too large or nvcc is not installed."""
         from qgs_b200 import codegen
-        path = codegen.build_plugin(self.ndim, self.rank, self.coo, self.val, jcoo=self.jcoo, jval=self.jval)
+        path = codegen.build_plugin(self.ndim, self.rank, self.coo, self.val, part="rk")
         if path is None:
             return False
         _lib.check(_lib.load().qgsb_load_plugin(path.encode()))
         self.use_specialised(True)
         return self.kernel_kind == 2
+
+    @property
+    def has_tangent(self):
+        """True when generated tangent-linear / Benettin kernels are attached to this handle."""
+        return bool(_lib.load().qgsb_tensor_has_tangent(self.handle))
+
+    # member-steps x tangent vectors above which building the tangent kernels (tens of seconds of nvcc) pays off
+    TANGENT_JIT_WORK = 5e7
+
+    def ensure_tangent(self, work=None):
+        """Called by the tangent-linear integrator and the Lyapunov estimators before a launch of ``work`` =
+        members x steps x vectors (``None``: unconditionally): a handle
+        that runs run-time built specialised kernels gets the matching tangent kernels too (unrolled Householder QR,
+        four kernels: tens of seconds of nvcc once per tensor, cached on disk next to the first part).  Handles of the
+        prebuilt configurations already have them; without nvcc the generic tangent kernels serve."""
+        if work is not None and work < self.TANGENT_JIT_WORK:
+            return False
+        if self.has_tangent or self.kernel_kind != 2 or getattr(self, "_tangent_tried", False):
+            return self.has_tangent
+        self._tangent_tried = True
+        if os.environ.get("QGSB_JIT_TANGENT", "1") == "0":
+            return False
+        from qgs_b200 import codegen
+        path = codegen.build_plugin(self.ndim, self.rank, self.coo, self.val, jcoo=self.jcoo, jval=self.jval,
+                                    part="tangent")
+        if path is None:
+            return False
+        _lib.check(_lib.load().qgsb_load_plugin(path.encode()))
+        self.use_specialised(True)
+        return self.has_tangent
 
 
 class _TensorCallable(object):

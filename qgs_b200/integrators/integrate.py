@@ -96,6 +96,7 @@ def _integrate_runge_kutta_tgls_jit(f, fjac, time, ic, tg_ic, time_direction, wr
         raise ValueError("ic must have shape (n_traj, %d), got %s" % (tensor.ndim, ic.shape))
     if tg_ic.ndim != 3 or tg_ic.shape[0] != ic.shape[0] or tg_ic.shape[1] != ic.shape[1]:
         raise ValueError("tg_ic must have shape (n_traj, n_dim, n_tg_traj), got %s" % (tg_ic.shape,))
+    tensor.ensure_tangent(float(ic.shape[0]) * max(len(time) - 1, 0) * tg_ic.shape[2])
     b, c, a = _lib.f64(b), _lib.f64(c), _lib.f64(a)
     dt = directed_dt(time, time_direction)
     n_rec = n_records_of(time, write_steps)

@@ -55,6 +55,7 @@ def benettin(f, fjac, ic, mode, n_vec, q0, r0, pre_times, rec_times, mdt, write_
     ic = _lib.f64(ic)
     N, n = ic.shape
     m = int(n_vec)
+    tensor.ensure_tangent(float(N) * (len(pre_times) + len(rec_times) - 2) * m)
     backward_walk = mode == 1
     ptr_a, sub_a = _subtimes(pre_times, mdt, backward_walk)
     ptr_b, sub_b = _subtimes(rec_times, mdt, backward_walk)
@@ -94,6 +95,7 @@ def ginelli(f, fjac, ic, n_vec, q0, r0, am0, noise, noise_pert, pretime, time, a
     ic = _lib.f64(ic)
     N, n = ic.shape
     m = int(n_vec)
+    tensor.ensure_tangent(float(N) * (len(pretime) + len(time) + len(aftertime) - 3) * m)
     rec_times = np.concatenate((time[:-1], aftertime))
     ptr_a, sub_a = _subtimes(pretime, mdt, False)
     ptr_b, sub_b = _subtimes(rec_times, mdt, False)

@@ -250,9 +250,28 @@ def test_runtime_specialised_plugin_matches_generic():
     b, c, a = rk4_tableau()
     ic = np.random.default_rng(0).random((130, 36)) * 0.01
     tv = np.concatenate((np.arange(0., 5., 0.1), [5.]))
-    xg = _integrate_runge_kutta_jit(fg, tv, ic, 1, 10, b, c, a)
-    xs = _integrate_runge_kutta_jit(fs, tv, ic, 1, 10, b, c, a)
+    os.environ["QGSB_RK_ROWS_MAX"] = "0"            # the throughput kernels, not the block-per-member one
+    try:
+        xg = _integrate_runge_kutta_jit(fg, tv, ic, 1, 10, b, c, a)
+        xs = _integrate_runge_kutta_jit(fs, tv, ic, 1, 10, b, c, a)
+    finally:
+        del os.environ["QGSB_RK_ROWS_MAX"]
     assert rel(xs, xg) < 1e-11
+    # the tangent kernels of a run-time built module come as a second part, on demand
+    from qgs_b200.integrators.integrate import _integrate_runge_kutta_tgls_jit, _zeros_func
+    fg2, Dfg = tendencies_from_tensor(36, z["coo"], val, z["jcoo"], z["jval"], specialise=False)
+    fs2, Dfs = tendencies_from_tensor(36, z["coo"], val, z["jcoo"], z["jval"], specialise=True)
+    assert not fs2.tensor.has_tangent and not fs2.tensor.ensure_tangent(work=10.)     # small jobs do not trigger nvcc
+    assert fs2.tensor.ensure_tangent() and fs2.tensor.has_tangent
+    tg = np.repeat(np.eye(36)[None], 9, axis=0)
+    tt = np.concatenate((np.arange(0., 1., 0.1), [1.]))
+    os.environ["QGSB_TGLS_KERNEL"] = "generic"
+    try:
+        yg, mg = _integrate_runge_kutta_tgls_jit(fg2, Dfg, tt, ic[:9], tg, 1, 2, b, c, a, False, 1., _zeros_func)
+    finally:
+        del os.environ["QGSB_TGLS_KERNEL"]
+    ys, ms = _integrate_runge_kutta_tgls_jit(fs2, Dfs, tt, ic[:9], tg, 1, 2, b, c, a, False, 1., _zeros_func)
+    assert rel(ys, yg) < 1e-11 and rel(ms, mg) < 1e-10
 
 
 # ---- properties at the BASELINE size (2**20 members) --------------------------------------------------------------------
