@@ -523,10 +523,20 @@ rk_g3p_kernel(int n, int mb, int n_chunks, const __grid_constant__ G3Plan plan, 
                     const double2 y_old = *reinterpret_cast<const double2 *>(yg + o);   // in flight while the row is summed
                     const double2 a_old = st == 0 ? make_double2(0., 0.) : *reinterpret_cast<const double2 *>(ag + o);
                     double k0 = 0., k1 = 0., k2 = 0., k3 = 0., l0 = 0., l1 = 0., l2 = 0., l3 = 0.;
+                    double2 a3 = make_double2(0., 0.);
 #pragma unroll 2
                     for (int g = 0; g < groups; ++g) {
-                        const double2 a0 = G3_X2(c0.z), b0 = G3_X2(c0.w), a1 = G3_X2(c1.z), b1 = G3_X2(c1.w);
-                        const double2 a2 = G3_X2(c2.z), b2 = G3_X2(c2.w), a3 = G3_X2(c3.z), b3 = G3_X2(c3.w);
+                        // bit 0 of the first offset: same x_j as the entry before (entries are sorted by (i, j, k)), so
+                        // the value is carried in registers instead of read again -- a warp-uniform predicate
+                        double2 a0 = a3, a1, a2;
+                        if (!(c0.z & 1u)) a0 = G3_X2(c0.z);
+                        a1 = a0;
+                        if (!(c1.z & 1u)) a1 = G3_X2(c1.z);
+                        a2 = a1;
+                        if (!(c2.z & 1u)) a2 = G3_X2(c2.z);
+                        a3 = a2;
+                        if (!(c3.z & 1u)) a3 = G3_X2(c3.z);
+                        const double2 b0 = G3_X2(c0.w), b1 = G3_X2(c1.w), b2 = G3_X2(c2.w), b3 = G3_X2(c3.w);
                         pe += 4;
                         const uint4 n0 = pe[0], n1 = pe[1], n2 = pe[2], n3 = pe[3];
                         const double v0 = __hiloint2double(c0.y, c0.x), v1 = __hiloint2double(c1.y, c1.x);
@@ -920,9 +930,13 @@ static bool g3_prepare(const qgsb_tensor *t)
     std::vector<G3Entry> h;
     h.reserve(total);
     for (int i = 1; i <= n; ++i) {
-        for (int e = t->h_row_ptr[i]; e < t->h_row_ptr[i + 1]; ++e)
-            h.push_back(G3Entry{t->h_ent[e].v, (uint32_t)((t->h_ent[e].jk & 0xffffu) * (uint32_t)mb * 8u),
+        for (int e = t->h_row_ptr[i]; e < t->h_row_ptr[i + 1]; ++e) {
+            const uint32_t j = t->h_ent[e].jk & 0xffffu;
+            // two members per thread: flag the entries whose x_j is the one of the entry before in the same row
+            const bool reuse = pairs && e > t->h_row_ptr[i] && (t->h_ent[e - 1].jk & 0xffffu) == j;
+            h.push_back(G3Entry{t->h_ent[e].v, j * (uint32_t)mb * 8u | (reuse ? 1u : 0u),
                                 (uint32_t)((t->h_ent[e].jk >> 16) * (uint32_t)mb * 8u)});
+        }
         while (h.size() & 3) h.push_back(G3Entry{0., 0u, 0u});       // + 0 * x_0 * x_0
     }
     std::vector<int> meta(chunks.size() * 4 + rowlen.size());
