@@ -649,3 +649,40 @@ def test_leading_lyapunov_exponents_match_oracle_statistically():
     assert np.all(z < 4.), (z, g.mean(axis=0), o.mean(axis=0))
     assert g.mean(axis=0)[0] > 0.                       # the RP model is chaotic at these parameters
     assert abs(g.mean(axis=0).sum() - o.mean(axis=0).sum()) < 0.15 * abs(o.mean(axis=0).sum()) + 3 * se.sum()
+
+
+# ---- size-independent properties of the tangent / Benettin kernels at ensemble sizes the oracle cannot reach ------------
+def test_tangent_linearity_and_benettin_invariants_at_scale():
+    """(a) the tangent propagator is linear: M(a u + b v) = a M u + b M v, for 4096 members on the packed kernel;
+    (b) recorded Lyapunov vectors are orthonormal, Q^T Q = I; (c) the full spectrum sums to the time-mean divergence
+    of the flow, sum_i lambda_i = <tr Df(x)> (Liouville), member by member."""
+    from qgs_b200.integrators.integrator import RungeKuttaTglsIntegrator
+    from qgs_b200.toolbox.lyapunov import LyapunovsEstimator
+    f, Df, T = model("maooam36")
+    rng = np.random.default_rng(17)
+    N = 4096
+    ic = rng.random((N, 36)) * 0.01
+    u, v = rng.standard_normal((N, 36)), rng.standard_normal((N, 36))
+    tg = np.stack((u, v, 0.7 * u - 1.9 * v), axis=2)                     # (N, n, 3): one set of vectors per member
+    integ = RungeKuttaTglsIntegrator()
+    integ.set_func(f, Df)
+    integ.integrate(0., 2., 0.1, ic=ic, tg_ic=np.swapaxes(tg, 1, 2), write_steps=0)
+    _, x, m = integ.get_trajectories()
+    m = np.asarray(m).reshape(N, 3, 36) if np.asarray(m).shape[1] == 3 else np.swapaxes(np.asarray(m).reshape(N, 36, 3), 1, 2)
+    lin = 0.7 * m[:, 0] - 1.9 * m[:, 1]
+    assert np.max(np.abs(m[:, 2] - lin)) < 1e-11 * np.max(np.abs(lin))
+    # Benettin: orthonormality and Liouville
+    Nl = 1024
+    np.random.seed(3)
+    est = LyapunovsEstimator()
+    est.set_func(f, Df)
+    est.compute_lyapunovs(0., 2., 12., 0.1, 0.1, ic=ic[:Nl], write_steps=5)
+    t, traj, exps, vecs = est.get_lyapunovs()                             # (Nl, 36, R), (Nl, 36, R), (Nl, 36, 36, R)
+    q = np.moveaxis(vecs, 3, 1)                                           # (Nl, R, n, m)
+    gram = np.einsum('mrik,mril->mrkl', q, q)
+    assert np.max(np.abs(gram - np.eye(36))) < 1e-12
+    # local exponents are recorded every 5th step: compare their sum with tr Df at the same records (both sample the
+    # same slowly varying quantity; the divergence of MAOOAM is dominated by constant friction terms)
+    div = np.array([np.trace(Df(0., traj[i, :, r])) for i in range(16) for r in range(1, traj.shape[2] - 1)])
+    lam = exps[:16, :, 1:-1].sum(axis=1).ravel()
+    assert abs(lam.mean() - div.mean()) < 2e-3 * abs(div.mean()), (lam.mean(), div.mean())
