@@ -686,3 +686,49 @@ def test_tangent_linearity_and_benettin_invariants_at_scale():
     div = np.array([np.trace(Df(0., traj[i, :, r])) for i in range(16) for r in range(1, traj.shape[2] - 1)])
     lam = exps[:16, :, 1:-1].sum(axis=1).ravel()
     assert abs(lam.mean() - div.mean()) < 2e-3 * abs(div.mean()), (lam.mean(), div.mean())
+
+
+# ---- error convention of the C ABI: non-zero return + message, surfaced as exceptions; nothing falls back silently --------
+def test_c_abi_rejects_bad_calls_loudly():
+    import ctypes
+    from qgs_b200 import _lib
+    from qgs_b200.integrators.integrate import rk4_tableau
+    from qgs_b200.toolbox.lyapunov import CovariantLyapunovsEstimator, LyapunovsEstimator
+    from qgs_b200.integrators.integrator import RungeKuttaTglsIntegrator
+    lib = _lib.load()
+    f, Df, T = model("maooam36")
+    b, c, a = rk4_tableau()
+    ic = np.random.default_rng(0).random((4, 36)) * 0.01
+    dt = np.full(10, 0.1)
+    out = np.empty((4, 36, 3))
+
+    def call(n_records, write_steps=5, direction=1, members=4, s=4):
+        return lib.qgsb_rk_integrate(f.tensor.handle, members, _lib.dptr(ic), 10, _lib.dptr(dt), s, _lib.dptr(a),
+                                     _lib.dptr(b), _lib.dptr(c), write_steps, direction, n_records, _lib.dptr(out), None)
+
+    assert call(3) == 0
+    assert call(4) != 0 and b"inconsistent" in lib.qgsb_last_error()          # wrong record count
+    assert call(3, direction=0) != 0 and b"time_direction" in lib.qgsb_last_error()
+    assert call(3, members=0) != 0
+    assert call(3, s=40) != 0 and b"stages" in lib.qgsb_last_error()
+    assert lib.qgsb_rk_integrate(None, 4, _lib.dptr(ic), 10, _lib.dptr(dt), 4, _lib.dptr(a), _lib.dptr(b), _lib.dptr(c),
+                                 5, 1, 3, _lib.dptr(out), None) != 0                # null handle
+    bad = ctypes.c_void_p()
+    coo = np.array([[1, 0, 99]], dtype=np.int32)                                # index outside the state
+    rc = lib.qgsb_tensor_create(3, 3, 1, coo.ctypes.data_as(_lib.c_int32_p), _lib.dptr(np.ones(1)), 0,
+                                coo.ctypes.data_as(_lib.c_int32_p), _lib.dptr(np.ones(1)), ctypes.byref(bad))
+    assert rc != 0 and b"outside" in lib.qgsb_last_error()
+    # Python layer: exceptions, not fallbacks
+    est = LyapunovsEstimator()
+    est.set_func(f, Df)
+    with pytest.raises(RuntimeError, match="n_vec"):
+        est.compute_lyapunovs(0., 0.2, 0.5, 0.1, 0.1, ic=ic, n_vec=40)            # more vectors than dimensions
+    tg = RungeKuttaTglsIntegrator()
+    tg.set_func(f, Df)
+    with pytest.raises(NotImplementedError):
+        tg.integrate(0., 0.2, 0.1, ic=ic, boundary=lambda t, x: x)                # arbitrary boundary callables
+    f6, Df6, _ = model("atm6x6")
+    clv = CovariantLyapunovsEstimator(method=0)
+    clv.set_func(f6, Df6)
+    with pytest.raises(RuntimeError, match="shared memory"):                      # Ginelli keeps two n_vec^2 matrices on chip
+        clv.compute_clvs(0., 0.1, 0.3, 0.5, 0.1, 0.1, ic=np.random.default_rng(1).random((1, 228)) * 0.01)
