@@ -179,6 +179,22 @@ def tendencies_from_tensor(ndim, coo, val, jcoo=None, jval=None, specialise=True
     return Tendencies(tensor), JacobianTendencies(tensor)
 
 
+def tendencies_from_file(path, specialise=True):
+    """``(f, Df)`` from a tensor file written by ``save_tendencies`` / the ``QGSB_TENSOR_CACHE`` cache (row f-1: the
+    arrays of tendencies.py:92-96 without re-running the tensor construction)."""
+    from qgs_b200.functions import tensor_cache
+    ndim, coo, val, jcoo, jval = tensor_cache.load_tensor(path)
+    return tendencies_from_tensor(ndim, coo, val, jcoo if len(jval) else None, jval if len(jval) else None,
+                                  specialise=specialise)
+
+
+def save_tendencies(path, f):
+    """Write the tensor carried by ``f`` (or ``Df``) to ``path``."""
+    from qgs_b200.functions import tensor_cache
+    t = f.tensor
+    return tensor_cache.save_tensor(path, t.ndim, t.coo, t.val, t.jcoo, t.jval)
+
+
 def jacobian_tensor_from_coo(coo, val):
     """``T + sum_p swapaxes(T, 1, p+1)`` on coordinate lists (qgtensor.py:714-722), duplicates summed,
     entries returned in lexicographic order like pydata ``sparse`` does."""
@@ -265,12 +281,24 @@ def _build_reference_tensor(params, thermo=False):
 def create_tendencies(params, return_inner_products=False, return_qgtensor=False):
     """Same contract as the reference (tendencies.py:20-130): returns ``[f, Df, (inner products)?, (qgtensor)?]``
     with ``f(t, x)`` the tendencies and ``Df(t, x)`` the Jacobian matrix, both evaluated on the GPU."""
-    aip, oip, gip, agotensor = _build_reference_tensor(params)
+    from qgs_b200.functions import tensor_cache
+    cached = None if (return_inner_products or return_qgtensor) else tensor_cache.cache_file(params)
+    if cached is not None and os.path.exists(cached):
+        ndim, coo, val, jcoo, jval = tensor_cache.load_tensor(cached)
+        if ndim != params.ndim:
+            raise RuntimeError("%s holds a %d-variable tensor, the parameters describe %d variables"
+                               % (cached, ndim, params.ndim))
+        aip = oip = gip = agotensor = None
+    else:
+        aip, oip, gip, agotensor = _build_reference_tensor(params)
 
-    coo = agotensor.tensor.coords.T
-    val = agotensor.tensor.data
-    jcoo = agotensor.jacobian_tensor.coords.T
-    jval = agotensor.jacobian_tensor.data
+        coo = agotensor.tensor.coords.T
+        val = agotensor.tensor.data
+        jcoo = agotensor.jacobian_tensor.coords.T
+        jval = agotensor.jacobian_tensor.data
+        store = tensor_cache.cache_file(params)
+        if store is not None and not os.path.exists(store):
+            tensor_cache.save_tensor(store, params.ndim, coo, val, jcoo, jval)
 
     tensor = DeviceTensor(params.ndim, coo, val, jcoo, jval)
     f = Tendencies(tensor)

@@ -605,8 +605,24 @@ def test_overlay_runs_the_reference_workflow_on_the_gpu(tmp_path):
         "tgls.integrate(0., 1., 0.1, ic=ic[0], write_steps=0)\n"
         "t2, x2, fm = tgls.get_trajectories()\n"
         "np.savez(%r, time=time, traj=traj, ic=ic, fm=fm)\n"
+        # row f-1: the second create_tendencies with equal parameters reads the tensor file, not the tensor builder
+        "import os, sys, glob\n"
+        "files = glob.glob(os.path.join(os.environ['QGSB_TENSOR_CACHE'], 'tendencies_*.npz'))\n"
+        "assert len(files) == 1, files\n"
+        "import qgs_b200.functions.tendencies as tmod\n"
+        "def no_build(*args, **kwargs):\n"
+        "    raise AssertionError('tensor construction ran although the cache holds this configuration')\n"
+        "build, tmod._build_reference_tensor = tmod._build_reference_tensor, no_build\n"
+        "g, Dg = create_tendencies(p)\n"
+        "assert np.array_equal(g.tensor.coo, f.tensor.coo) and np.array_equal(g.tensor.val, f.tensor.val)\n"
+        "assert np.array_equal(g.tensor.jcoo, f.tensor.jcoo) and np.array_equal(g(0., ic), f(0., ic))\n"
+        "tmod._build_reference_tensor = build\n"
+        "p.set_params({'kd': 0.03})\n"                                      # any parameter change is a different entry
+        "create_tendencies(p)\n"
+        "assert len(glob.glob(os.path.join(os.environ['QGSB_TENSOR_CACHE'], 'tendencies_*.npz'))) == 2\n"
         "print('workflow ok', traj.shape, fm.shape)\n" % str(out))
-    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(REPO, "overlay"), ref_dir]))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(REPO, "overlay"), ref_dir]),
+               QGSB_TENSOR_CACHE=str(tmp_path / "tensors"))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600, cwd=str(tmp_path))
     assert res.returncode == 0 and "workflow ok" in res.stdout, res.stderr[-3000:]
     z = np.load(out)

@@ -362,3 +362,90 @@ def test_resident_ensemble_record_times_follow_the_integrator_rules():
                 ref = np.atleast_1d(np.asarray(returned_time(time, 0., t_end, forward, ws)))
                 got = DeviceEnsemble._record_times(time, ws, forward)
                 assert np.array_equal(ref, got), (t_end, ws, forward)
+
+
+# ---- tensor hand-off file and parameter fingerprint ----------------------------------------
+def test_tensor_file_round_trip_and_validation(tmp_path):
+    from qgs_b200.functions import tensor_cache
+    z = np.load(os.path.join(GOLDEN, "tensor_T4.npz"))
+    path = tensor_cache.save_tensor(str(tmp_path / "t4.npz"), int(z["ndim"]), z["coo"].astype(np.int64), z["val"],
+                                    z["jcoo"], z["jval"])
+    ndim, coo, val, jcoo, jval = tensor_cache.load_tensor(path)
+    assert ndim == int(z["ndim"]) and coo.dtype == np.int32 and coo.shape[1] == 5
+    assert np.array_equal(coo, z["coo"]) and np.array_equal(val, z["val"])
+    assert np.array_equal(jcoo, z["jcoo"]) and np.array_equal(jval, z["jval"])
+    assert os.listdir(tmp_path) == ["t4.npz"]                       # no temporary file left behind
+    # the golden fixtures are in the same format
+    assert tensor_cache.load_tensor(os.path.join(GOLDEN, "tensor_maooam36.npz"))[0] == 36
+    bad = str(tmp_path / "bad.npz")
+    np.savez(bad, ndim=3, coo=np.zeros((4, 3), np.int32), val=np.zeros(3), jcoo=np.zeros((0, 3), np.int32), jval=np.zeros(0))
+    with pytest.raises(ValueError, match="not a tendencies tensor"):
+        tensor_cache.load_tensor(bad)
+    np.savez(bad, ndim=3, coo=np.full((4, 3), 9, np.int32), val=np.zeros(4), jcoo=np.zeros((0, 3), np.int32), jval=np.zeros(0))
+    with pytest.raises(ValueError, match="outside"):
+        tensor_cache.load_tensor(bad)
+
+
+def test_parameter_fingerprint_tracks_values_not_identities(tmp_path, monkeypatch):
+    from qgs_b200.functions import tensor_cache
+
+    class Scaled(float):                                            # like qgs Parameter: a float with attributes
+        def __new__(cls, value, units=""):
+            obj = float.__new__(cls, value)
+            obj.units = units
+            return obj
+
+    class Block(object):
+        def __init__(self, kd, modes):
+            self.kd = Scaled(kd, "[1/s]")
+            self.modes = np.array(modes)
+            self.nested = {"eps": 0.7, "labels": ["a", "b"], "fn": np.sin}
+            self.me = self                                            # cycle
+
+    a, b = Block(0.029, [[1, 1], [1, 2]]), Block(0.029, [[1, 1], [1, 2]])
+    assert tensor_cache.fingerprint(a) == tensor_cache.fingerprint(b)      # equal values, different objects
+    assert tensor_cache.fingerprint(a) != tensor_cache.fingerprint(a, "thermo")
+    for change in (lambda o: setattr(o, "kd", Scaled(0.03, "[1/s]")), lambda o: setattr(o, "kd", Scaled(0.029, "[1/d]")),
+                   lambda o: o.modes.__setitem__((1, 1), 3), lambda o: o.nested.__setitem__("eps", 0.71),
+                   lambda o: o.nested["labels"].append("c"), lambda o: o.nested.__setitem__("fn", np.cos)):
+        c = Block(0.029, [[1, 1], [1, 2]])
+        change(c)
+        assert tensor_cache.fingerprint(c) != tensor_cache.fingerprint(a)
+    monkeypatch.delenv("QGSB_TENSOR_CACHE", raising=False)
+    assert tensor_cache.cache_file(a) is None
+    monkeypatch.setenv("QGSB_TENSOR_CACHE", str(tmp_path / "cache"))
+    path = tensor_cache.cache_file(a)
+    assert path == tensor_cache.cache_file(b) and os.path.isdir(os.path.dirname(path))
+
+
+def test_fingerprint_of_reference_parameter_objects():
+    """On the reference's own QgParams (from the installed baseline/_ref): equal set-ups built separately share a cache
+    entry, every changed scalar / mode set / basis kind gets its own."""
+    ref_dir = os.path.join(REPO, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "qgs")):
+        pytest.skip("baseline/_ref is not installed")
+    code = (
+        "import warnings; warnings.filterwarnings('ignore')\n"
+        "from qgs_b200 import compat; compat.install()\n"
+        "from qgs.params.params import QgParams\n"
+        "from qgs_b200.functions.tensor_cache import fingerprint\n"
+        "def make(kd=0.029, ny=2, mode='analytic', insolation=103.3333):\n"
+        "    p = QgParams()\n"
+        "    p.set_atmospheric_channel_fourier_modes(2, ny, mode=mode)\n"
+        "    p.set_oceanic_basin_fourier_modes(2, 4, mode=mode)\n"
+        "    p.set_params({'kd': kd, 'kdp': 0.0290, 'n': 1.5, 'r': 1.e-7, 'h': 136.5, 'd': 1.1e-7})\n"
+        "    p.atemperature_params.set_params({'eps': 0.7, 'T0': 289.3, 'hlambda': 15.06})\n"
+        "    p.gotemperature_params.set_params({'gamma': 5.6e8, 'T0': 301.46})\n"
+        "    p.atemperature_params.set_insolation(insolation, 0)\n"
+        "    p.gotemperature_params.set_insolation(310., 0)\n"
+        "    return p\n"
+        "base = fingerprint(make())\n"
+        "assert base == fingerprint(make())\n"
+        "others = [fingerprint(make(kd=0.03)), fingerprint(make(ny=3)), fingerprint(make(mode='symbolic')),\n"
+        "          fingerprint(make(insolation=104.))]\n"
+        "assert len(set(others + [base])) == 5\n"
+        "assert fingerprint(make(mode='symbolic')) == others[2]\n"
+        "print('fingerprints ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([REPO, ref_dir]))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0 and "fingerprints ok" in res.stdout, res.stderr[-3000:]
