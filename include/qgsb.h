@@ -14,7 +14,9 @@
  *     F-ordered int64 `coords.T` view, tendencies.py:92, to C-ordered int32).
  *   - return value 0 = success; non-zero = failure, message in qgsb_last_error() (thread local).
  *   - calls are synchronous (they return when results are in the caller's buffers), like the
- *     reference's integrate() which blocks on queue.join() (integrator.py:391).
+ *     reference's integrate() which blocks on queue.join() (integrator.py:391).  The library may be
+ *     called from several host threads: entry points serialise on one process-wide lock (one device
+ *     context per process, one process per GPU).
  *   - there is no CPU fallback: without a CUDA device every compute call fails with an error.
  */
 #ifndef QGSB_H

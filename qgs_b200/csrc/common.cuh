@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -38,7 +39,15 @@ struct Failure {};  // thrown internally, caught at the ABI boundary
         }                                     \
     } while (0)
 
-#define QGSB_API_BEGIN try {
+// The context (stream, scratch pool, kernel registry) is process-wide: entry points serialise on one lock, so the
+// library may be called from several host threads (ctypes releases the GIL) -- calls queue up like the reference's
+// integrate() calls queue on its worker pool.
+std::recursive_mutex &api_mutex();
+#define QGSB_API_LOCK std::lock_guard<std::recursive_mutex> api_guard__(qgsb::api_mutex());
+
+#define QGSB_API_BEGIN \
+    QGSB_API_LOCK      \
+    try {
 #define QGSB_API_END                                       \
     return 0;                                              \
     }                                                      \

@@ -1323,6 +1323,7 @@ int qgsb_ensemble_create(const qgsb_tensor *t, long N, qgsb_ensemble **out)
 void qgsb_ensemble_destroy(qgsb_ensemble *e)
 {
     if (!e) return;
+    QGSB_API_LOCK
     if (ctx().ready) {
         cudaSetDevice(ctx().device);
         cudaStreamSynchronize(ctx().stream);

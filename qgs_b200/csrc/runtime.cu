@@ -30,6 +30,12 @@ Context &ctx()
     return c;
 }
 
+std::recursive_mutex &api_mutex()
+{
+    static std::recursive_mutex m;
+    return m;
+}
+
 static void init_device(int device)
 {
     Context &c = ctx();
@@ -511,6 +517,7 @@ int qgsb_init(int device)
 
 void qgsb_shutdown(void)
 {
+    QGSB_API_LOCK
     Context &c = ctx();
     if (!c.ready) return;
     cudaSetDevice(c.device);
@@ -637,6 +644,7 @@ int qgsb_tensor_hash(int ndim, int rank, long nnz, const int32_t *coo, const dou
 void qgsb_tensor_destroy(qgsb_tensor *t)
 {
     if (!t) return;
+    QGSB_API_LOCK
     if (ctx().ready) cudaSetDevice(ctx().device);
     delete t;
 }

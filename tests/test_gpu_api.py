@@ -748,3 +748,54 @@ def test_c_abi_rejects_bad_calls_loudly():
     clv.set_func(f6, Df6)
     with pytest.raises(RuntimeError, match="shared memory"):                      # Ginelli keeps two n_vec^2 matrices on chip
         clv.compute_clvs(0., 0.1, 0.3, 0.5, 0.1, 0.1, ic=np.random.default_rng(1).random((1, 228)) * 0.01)
+
+
+def test_concurrent_host_threads_get_the_serial_results():
+    """ctypes drops the GIL during a call, so several Python threads can be inside libqgsb at once; the entry points
+    serialise on the library's lock and every thread gets bitwise the result of the same call made alone."""
+    import threading
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator, RungeKuttaTglsIntegrator
+    f, Df, T = model("maooam36")
+    g, Dg, _ = model("rp")
+    rng = np.random.default_rng(77)
+    jobs = []
+    for k in range(8):
+        if k % 2 == 0:
+            jobs.append(("rk", f, None, rng.random((300 + 700 * k, 36)) * 0.01))
+        elif k % 4 == 1:
+            jobs.append(("tg", g, Dg, rng.random((40 + k, 20)) * 0.1))
+        else:
+            jobs.append(("f", f, None, rng.random((5000, 36)) * 0.01))
+
+    def run(job):
+        kind, fn, dfn, ic = job
+        if kind == "rk":
+            integ = RungeKuttaIntegrator()
+            integ.set_func(fn)
+            integ.integrate(0., 3., 0.1, ic=ic, write_steps=3)
+            return integ.get_trajectories()[1]
+        if kind == "tg":
+            integ = RungeKuttaTglsIntegrator()
+            integ.set_func(fn, dfn)
+            integ.integrate(0., 1., 0.1, ic=ic, write_steps=0)
+            return integ.get_trajectories()[2]
+        return fn(0., ic)
+
+    serial = [run(job) for job in jobs]
+    for _ in range(3):
+        results, errors = [None] * len(jobs), []
+
+        def worker(i):
+            try:
+                results[i] = run(jobs[i])
+            except Exception as exc:                                  # noqa: BLE001 - reported below
+                errors.append(exc)
+
+        threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(jobs))]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        assert not errors, errors
+        for a, b in zip(serial, results):
+            assert np.array_equal(a, b)
