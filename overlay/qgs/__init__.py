@@ -7,7 +7,8 @@
 
 from ``qgs_b200`` (CUDA path) and (ii) extends its ``__path__`` with the real qgs package so that
 every other sub-package (params, basis, inner_products, tensors, diagnostics, ...) is the untouched
-reference.  User scripts such as ``qgs_maooam.py`` run unchanged.
+reference.  User scripts such as ``qgs_maooam.py`` run unchanged.  The one reference module that passes the tendencies
+into ``@njit`` code (``qgs.diagnostics.wind``, vertical velocity) is adapted on import, see ``qgs_b200/overlay_hooks.py``.
 
 The real package is looked up in ``$QGS_REFERENCE_PATH`` (the directory that contains ``qgs/``) or
 further down ``sys.path``.
@@ -36,6 +37,13 @@ def _real_package_dirs(subpackage=""):
 
 
 __path__ = [_HERE] + _real_package_dirs()
+
+# reference modules that pass the tendencies into numba code get a batched device evaluation instead (wind.py:705-714)
+try:
+    from qgs_b200 import overlay_hooks as _hooks
+    _hooks.install()
+except ImportError:
+    pass
 
 # tensor construction in the reference imports pydata `sparse` and `pebble`; use the stand-ins when absent
 try:

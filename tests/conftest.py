@@ -17,3 +17,19 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def write_plot_stubs(directory):
+    """Minimal stand-ins for the plotting packages qgs.diagnostics imports at module level (matplotlib, IPython,
+    ipywidgets are not in the image); nothing of them is used by the computations under test."""
+    import os
+    files = {"matplotlib/__init__.py": "", "matplotlib/pyplot.py": "def get_cmap(name=None):\n    return name\n",
+             "matplotlib/animation.py": "", "matplotlib/ticker.py": "def FuncFormatter(f):\n    return f\n",
+             "IPython/__init__.py": "", "IPython/display.py": "HTML = display = None\n",
+             "ipywidgets/__init__.py": "interactive = None\n"}
+    for rel, text in files.items():
+        path = os.path.join(str(directory), rel)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as fh:
+            fh.write(text)
+    return str(directory)

@@ -799,3 +799,50 @@ def test_concurrent_host_threads_get_the_serial_results():
         assert not errors, errors
         for a, b in zip(serial, results):
             assert np.array_equal(a, b)
+
+
+def test_vertical_velocity_diagnostic_under_the_overlay_matches_the_reference(tmp_path):
+    """A caller next to the path: MiddleLayerVerticalVelocity (qgs/diagnostics/wind.py:642-714) builds both tendencies
+    with create_tendencies / create_atmo_thermo_tendencies and evaluates them on every record of a trajectory.  Run
+    the same script twice -- overlay (CUDA tendencies, one batched evaluation) and plain reference (numba loop) -- and
+    compare the omega field."""
+    import subprocess
+    import sys
+    from conftest import write_plot_stubs
+    ref_dir = os.path.join(REPO, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "qgs")):
+        pytest.skip("baseline/_ref is not installed")
+    stubs = write_plot_stubs(tmp_path / "stubs")
+    code = (
+        "import warnings; warnings.filterwarnings('ignore')\n"
+        "import sys, numpy as np\n"
+        "from qgs.params.params import QgParams\n"
+        "from qgs.diagnostics.wind import MiddleLayerVerticalVelocity\n"
+        "p = QgParams()\n"
+        "p.set_atmospheric_channel_fourier_modes(2, 2)\n"
+        "p.set_oceanic_basin_fourier_modes(2, 4)\n"
+        "p.set_params({'kd': 0.0290, 'kdp': 0.0290, 'n': 1.5, 'r': 1.e-7, 'h': 136.5, 'd': 1.1e-7})\n"
+        "p.atemperature_params.set_params({'eps': 0.7, 'T0': 289.3, 'hlambda': 15.06, })\n"
+        "p.gotemperature_params.set_params({'gamma': 5.6e8, 'T0': 301.46})\n"
+        "p.atemperature_params.set_insolation(103.3333, 0)\n"
+        "p.gotemperature_params.set_insolation(310., 0)\n"
+        "diag = MiddleLayerVerticalVelocity(p)\n"
+        "print('tendencies from', type(diag._f).__module__)\n"
+        "data = np.random.default_rng(5).random((p.ndim, 300)) * 0.01\n"
+        "diag.set_data(np.arange(300) * 0.1, data)\n"
+        "np.savez(sys.argv[1], raw=diag._data, omega=diag.diagnostic)\n")
+    script = tmp_path / "omega.py"
+    script.write_text(code)
+    outputs = {}
+    for name, paths in (("overlay", [stubs, os.path.join(REPO, "overlay"), ref_dir]),
+                        ("reference", [stubs, os.path.join(REPO, "qgs_b200", "compat"), ref_dir])):
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join(paths))
+        res = subprocess.run([sys.executable, str(script), str(tmp_path / (name + ".npz"))], capture_output=True,
+                             text=True, env=env, timeout=900, cwd=str(tmp_path))
+        assert res.returncode == 0, res.stderr[-3000:]
+        assert ("tendencies from qgs_b200.functions.tendencies" in res.stdout) == (name == "overlay"), res.stdout
+        outputs[name] = np.load(tmp_path / (name + ".npz"))
+    a, b = outputs["overlay"], outputs["reference"]
+    assert a["raw"].shape == b["raw"].shape == (36, 300) and a["omega"].shape == b["omega"].shape
+    assert np.max(np.abs(a["raw"] - b["raw"])) <= 1e-12 * np.max(np.abs(b["raw"]))
+    assert np.max(np.abs(a["omega"] - b["omega"])) <= 1e-12 * np.max(np.abs(b["omega"]))

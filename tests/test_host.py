@@ -449,3 +449,43 @@ def test_fingerprint_of_reference_parameter_objects():
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([REPO, ref_dir]))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0 and "fingerprints ok" in res.stdout, res.stderr[-3000:]
+
+
+def test_overlay_adapts_the_vertical_velocity_diagnostic_on_import(tmp_path):
+    """qgs/diagnostics/wind.py:705-714 hands the tendencies to @njit code.  Under the overlay the module is the
+    reference's file, loaded by the reference's loader, with `_compute_omega_term` routed to the batched evaluation for
+    device tendencies and to the original loop for numba functions."""
+    from conftest import write_plot_stubs
+    ref_dir = os.path.join(REPO, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "qgs")):
+        pytest.skip("baseline/_ref is not installed")
+    code = (
+        "import warnings; warnings.filterwarnings('ignore')\n"
+        "import sys, numpy as np\n"
+        "from numba import njit\n"
+        "import qgs.diagnostics.wind as wind\n"
+        "from qgs_b200 import overlay_hooks\n"
+        "assert wind._qgsb_patched and not hasattr(wind._compute_omega_term, 'py_func')\n"
+        "assert wind.__file__.endswith('wind.py') and 'baseline' in wind.__file__\n"
+        "assert wind.__loader__.get_filename() == wind.__file__\n"
+        "@njit\n"
+        "def f(t, x): return 2. * x + t\n"
+        "@njit\n"
+        "def g(t, x): return x * x\n"
+        "time = np.arange(5) * 0.1\n"
+        "data = np.random.default_rng(0).random((7, 5))\n"
+        "assert np.allclose(wind._compute_omega_term(time, data, f, g), 2. * data + time[None, :] - data * data)\n"
+        "out = overlay_hooks.omega_term(time, data, lambda t, x: 2. * x, lambda t, x: x * x)\n"
+        "assert out.shape == (7, 5) and out.flags.c_contiguous and np.allclose(out, 2. * data - data * data)\n"
+        "try:\n"
+        "    overlay_hooks.omega_term(time, data[:, :4], f, g)\n"
+        "    raise SystemExit('record count mismatch accepted')\n"
+        "except ValueError:\n"
+        "    pass\n"
+        "overlay_hooks.install(); overlay_hooks.install()\n"
+        "assert sum(isinstance(m, overlay_hooks.PatchAfterImport) for m in sys.meta_path) == 1\n"
+        "print('hook ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([write_plot_stubs(tmp_path / "stubs"),
+                                                       os.path.join(REPO, "overlay"), ref_dir]))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0 and "hook ok" in res.stdout, res.stderr[-3000:]
