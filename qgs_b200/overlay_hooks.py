@@ -6,7 +6,7 @@ the vertical-velocity diagnostic, ``qgs/diagnostics/wind.py:678-679`` (construct
 (``_compute_omega_term``: a per-record loop ``func(time[i], data[:, i])`` over the whole trajectory).  When the overlay
 package is active, importing that module swaps the loop for ONE batched evaluation on the device -- the records of a
 trajectory are an ensemble of states as far as ``f`` is concerned.  Everything else in the module stays the
-reference's code; the reference's own numba tendencies still go through its original loop.
+reference's code.  Like ``set_func``, the adapted function takes tensor-backed tendencies only.
 """
 import importlib.abc
 import sys
@@ -27,14 +27,13 @@ def omega_term(time, data, func, thermo_func):
 
 def _patch_wind(module):
     from qgs_b200.functions.tendencies import Tendencies
-    original = module._compute_omega_term
 
     def _compute_omega_term(time, data, func, thermo_func):
-        if isinstance(func, Tendencies) and isinstance(thermo_func, Tendencies):
-            return omega_term(time, data, func, thermo_func)
-        return original(time, data, func, thermo_func)
+        if not (isinstance(func, Tendencies) and isinstance(thermo_func, Tendencies)):
+            raise TypeError("the overlay evaluates the vertical-velocity term on the device: both functions must come "
+                            "from create_tendencies / create_atmo_thermo_tendencies (there is no CPU fallback)")
+        return omega_term(time, data, func, thermo_func)
 
-    _compute_omega_term.__doc__ = original.__doc__
     module._compute_omega_term = _compute_omega_term
 
 

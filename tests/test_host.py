@@ -453,8 +453,8 @@ def test_fingerprint_of_reference_parameter_objects():
 
 def test_overlay_adapts_the_vertical_velocity_diagnostic_on_import(tmp_path):
     """qgs/diagnostics/wind.py:705-714 hands the tendencies to @njit code.  Under the overlay the module is the
-    reference's file, loaded by the reference's loader, with `_compute_omega_term` routed to the batched evaluation for
-    device tendencies and to the original loop for numba functions."""
+    reference's file, loaded by the reference's loader, with `_compute_omega_term` replaced by the batched evaluation of
+    device tendencies (anything else is rejected: no CPU path)."""
     from conftest import write_plot_stubs
     ref_dir = os.path.join(REPO, "baseline", "_ref")
     if not os.path.isdir(os.path.join(ref_dir, "qgs")):
@@ -474,7 +474,11 @@ def test_overlay_adapts_the_vertical_velocity_diagnostic_on_import(tmp_path):
         "def g(t, x): return x * x\n"
         "time = np.arange(5) * 0.1\n"
         "data = np.random.default_rng(0).random((7, 5))\n"
-        "assert np.allclose(wind._compute_omega_term(time, data, f, g), 2. * data + time[None, :] - data * data)\n"
+        "try:\n"
+        "    wind._compute_omega_term(time, data, f, g)\n"
+        "    raise SystemExit('numba functions accepted: that would be a CPU path')\n"
+        "except TypeError as exc:\n"
+        "    assert 'no CPU fallback' in str(exc)\n"
         "out = overlay_hooks.omega_term(time, data, lambda t, x: 2. * x, lambda t, x: x * x)\n"
         "assert out.shape == (7, 5) and out.flags.c_contiguous and np.allclose(out, 2. * data - data * data)\n"
         "try:\n"
