@@ -117,7 +117,7 @@ def main():
     _lib.init(0)
     peak = _lib.fp64_peak()
     rows = [rk("maooam36", 1 << 20, 1000), rk("rp", 1 << 20, 500), rk("dynT", 1 << 20, 200),
-            rk("T4", 1 << 17, 50), rk("atm6x6", 148 * 96 * 4, 20),
+            rk("T4", 148 * 2 * 128 * 4, 50), rk("atm6x6", 148 * 96 * 4, 20),
             tangent("maooam36", 8192, 50, 36, False), tangent("maooam36", 8192, 100, 36, True),
             tangent("maooam36", 8192, 100, 10, True), tangent("rp", 8192, 100, 20, True),
             tangent("dynT", 4096, 50, 38, True)]
