@@ -460,6 +460,165 @@ __device__ __forceinline__ void qr(const Mem<N> &S, int c, bool live, double (&c
     }
 }
 
+// ---- the same factorisation with the reflector loop ROLLED ------------------------------------------------------------
+// The fully unrolled qr<N> above is ~11.6k instructions (186 KB) that every warp streams from L2 once per step -- ncu
+// shows the Benettin kernel waiting for instruction fetch there (stall "no instruction" 1.1 per issue).  Here the
+// reflectors are taken in three groups; inside a group j is a run-time index, rows start at the group's first row and
+// the rows <= j are masked to zero, so one loop body per group (a few hundred instructions) serves all its reflectors.
+// More FMAs (masked rows), far fewer instruction bytes.  Same arithmetic on the unmasked rows, same results.
+template <int N, int JB, int JE>
+__device__ __forceinline__ void qr_factor_group(const Mem<N> &S, int c, bool live, double (&col)[N], double *Rout)
+{
+    constexpr int RB = JB & ~1;
+    const int m = S.m;
+    double *V = S.facc;
+    const int jend = JE < m ? JE : m;
+#pragma unroll 1
+    for (int j = JB; j < jend; ++j) {
+        double *x = V + j * N;
+        if (live && c == j) {
+#pragma unroll
+            for (int i = RB; i < N; i += 2) *reinterpret_cast<double2 *>(x + i) = make_double2(col[i], col[i + 1]);
+        }
+        __syncthreads();
+        if (live && c >= j) {
+            double d0 = 0., d1 = 0., d2 = 0., d3 = 0., n0 = 0., n1 = 0., n2 = 0., n3 = 0.;
+#pragma unroll
+            for (int i = RB; i < N; i += 2) {
+                double2 xi = *reinterpret_cast<const double2 *>(x + i);
+                if (i < JE) {                                  // rows that can be <= j in this group
+                    if (i <= j) xi.x = 0.;
+                    if (i + 1 <= j) xi.y = 0.;
+                }
+                if ((i >> 1) & 1) {
+                    d0 = fma(xi.x, col[i], d0);
+                    n0 = fma(xi.x, xi.x, n0);
+                    d1 = fma(xi.y, col[i + 1], d1);
+                    n1 = fma(xi.y, xi.y, n1);
+                } else {
+                    d2 = fma(xi.x, col[i], d2);
+                    n2 = fma(xi.x, xi.x, n2);
+                    d3 = fma(xi.y, col[i + 1], d3);
+                    n3 = fma(xi.y, xi.y, n3);
+                }
+            }
+            const double alpha = x[j];
+            const double nrm2 = (n0 + n1) + (n2 + n3), dot = (d0 + d1) + (d2 + d3);
+            double beta = alpha, tau = 0., scal = 0.;
+            if (nrm2 != 0.) {
+                beta = -copysign(sqrt(fma(alpha, alpha, nrm2)), alpha);
+                tau = (beta - alpha) * fast_rcp(beta);
+                scal = fast_rcp(alpha - beta);
+            }
+            double cj = 0.;
+#pragma unroll
+            for (int i = JB; i < JE; ++i)
+                if (i == j) cj = col[i];
+            if (c == j) {
+                cj = beta;
+                S.rdiag[j] = beta;
+                S.tau[j] = tau;
+                S.scal[j] = scal;
+            } else {
+                const double w = tau * fma(dot, scal, cj);
+                cj -= w;
+                const double ws = -(w * scal);
+#pragma unroll
+                for (int i = RB; i < N; i += 2) {
+                    double2 xi = *reinterpret_cast<const double2 *>(x + i);
+                    if (i < JE) {
+                        if (i <= j) xi.x = 0.;
+                        if (i + 1 <= j) xi.y = 0.;
+                    }
+                    col[i] = fma(ws, xi.x, col[i]);
+                    col[i + 1] = fma(ws, xi.y, col[i + 1]);
+                }
+            }
+#pragma unroll
+            for (int i = JB; i < JE; ++i)
+                if (i == j) col[i] = cj;
+            if (Rout != nullptr) Rout[j * m + c] = cj;
+        }
+    }
+}
+
+template <int N, int JB, int JE>
+__device__ __forceinline__ void qr_formq_group(const Mem<N> &S, int c, bool live, double (&col)[N])
+{
+    constexpr int RB = JB & ~1;
+    const int m = S.m;
+    const double *V = S.facc;
+    const int jend = JE < m ? JE : m;
+#pragma unroll 1
+    for (int j = jend - 1; j >= JB; --j) {
+        if (live && j <= c) {
+            const double *x = V + j * N;
+            double d0 = 0., d1 = 0., d2 = 0., d3 = 0.;
+#pragma unroll
+            for (int i = RB; i < N; i += 2) {
+                double2 xi = *reinterpret_cast<const double2 *>(x + i);
+                if (i < JE) {
+                    if (i <= j) xi.x = 0.;
+                    if (i + 1 <= j) xi.y = 0.;
+                }
+                if ((i >> 1) & 1) {
+                    d0 = fma(xi.x, col[i], d0);
+                    d1 = fma(xi.y, col[i + 1], d1);
+                } else {
+                    d2 = fma(xi.x, col[i], d2);
+                    d3 = fma(xi.y, col[i + 1], d3);
+                }
+            }
+            double cj = 0.;
+#pragma unroll
+            for (int i = JB; i < JE; ++i)
+                if (i == j) cj = col[i];
+            const double scal = S.scal[j];
+            const double w = S.tau[j] * fma((d0 + d1) + (d2 + d3), scal, cj);
+            cj -= w;
+            const double ws = -(w * scal);
+#pragma unroll
+            for (int i = RB; i < N; i += 2) {
+                double2 xi = *reinterpret_cast<const double2 *>(x + i);
+                if (i < JE) {
+                    if (i <= j) xi.x = 0.;
+                    if (i + 1 <= j) xi.y = 0.;
+                }
+                col[i] = fma(ws, xi.x, col[i]);
+                col[i + 1] = fma(ws, xi.y, col[i + 1]);
+            }
+#pragma unroll
+            for (int i = JB; i < JE; ++i)
+                if (i == j) col[i] = cj;
+        }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void qr_rolled(const Mem<N> &S, int c, bool live, double (&col)[N], double *Rout)
+{
+    static_assert(N % 2 == 0, "rows are processed in aligned pairs");
+    constexpr int B1 = (N / 3) & ~1, B2 = (2 * N / 3) & ~1;
+    const int m = S.m;
+    __syncthreads();                       // every thread is done with its private facc column
+    qr_factor_group<N, 0, B1>(S, c, live, col, Rout);
+    qr_factor_group<N, B1, B2>(S, c, live, col, Rout);
+    qr_factor_group<N, B2, N>(S, c, live, col, Rout);
+    if (Rout != nullptr && live)
+        for (int i = c + 1; i < m; ++i) Rout[i * m + c] = 0.;   // strictly lower part of column c
+    __syncthreads();                       // the last reflector, tau and scal are published
+#pragma unroll
+    for (int i = 0; i < N; ++i) col[i] = i == c ? 1. : 0.;
+    qr_formq_group<N, B2, N>(S, c, live, col);
+    qr_formq_group<N, B1, B2>(S, c, live, col);
+    qr_formq_group<N, 0, B1>(S, c, live, col);
+    if (live) {
+        double *fmc = S.fm + c;
+#pragma unroll
+        for (int i = 0; i < N; ++i) fmc[i * m] = col[i];
+    }
+}
+
 template <int N, class Prod>
 __device__ __forceinline__ void init_member(const Mem<N> &S, int c, bool live)
 {
@@ -531,7 +690,7 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
 }
 
 // ---- Benettin loop (lyapunov.py:471-632) ---------------------------------------------------------------------------------
-template <int N, class Prod>
+template <int N, class Prod, bool ROLLED>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride, int qr_remap)
 {
@@ -617,7 +776,10 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
                     for (int i = 0; i < N; ++i) col[i] = Sq.fm[i * m + cq];
                 }
             }
-            qr<N>(Sq, cq, liveq, col, Rout);
+            if (ROLLED)
+                qr_rolled<N>(Sq, cq, liveq, col, Rout);
+            else
+                qr<N>(Sq, cq, liveq, col, Rout);
             if (remap) {
                 __syncthreads();
                 if (live) {
@@ -718,7 +880,14 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
         kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, tab, geo.G, geo.stride, remap);
         return cudaGetLastError();
     };
-    if (lyap) return P.adjoint ? go_lyap(lyap_kernel<N, Adj>) : go_lyap(lyap_kernel<N, Fwd>);
+    if (lyap) {
+        // few vectors: the rolled factorisation (one resident loop body instead of n_vec unrolled reflectors) is faster
+        // [B200: MAOOAM-36, 10 vectors +12 %; 36 vectors -9 %]; QGSB_QR_ROLLED=0/1 forces one of them
+        const char *env = getenv("QGSB_QR_ROLLED");
+        const bool rolled = env ? (env[0] != '0') : (3 * P.m <= N);
+        if (rolled) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, true>) : go_lyap(lyap_kernel<N, Fwd, true>);
+        return P.adjoint ? go_lyap(lyap_kernel<N, Adj, false>) : go_lyap(lyap_kernel<N, Fwd, false>);
+    }
     return P.adjoint ? go(tgls_kernel<N, Adj>) : go(tgls_kernel<N, Fwd>);
 }
 
