@@ -1,3 +1,4 @@
+"""ncu target: a short packed Benettin (default) or tangent-linear (argument `tgls`) launch, MAOOAM-36."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qgs_b200 import _lib

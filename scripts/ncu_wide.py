@@ -1,3 +1,4 @@
+"""ncu target: a small ensemble (default 148 members of the 6x6 model) on the latency-regime kernels."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

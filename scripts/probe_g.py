@@ -1,3 +1,4 @@
+"""A/B of the members per block of the packed tangent kernels (QGSB_PACK_G is read at every launch)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qgs_b200 import _lib

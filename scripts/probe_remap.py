@@ -1,3 +1,4 @@
+"""A/B of the member-fastest column layout of the QR phase of the packed Benettin kernel (QGSB_QR_REMAP)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qgs_b200 import _lib
