@@ -317,10 +317,23 @@ def create_tendencies(params, return_inner_products=False, return_qgtensor=False
 def create_atmo_thermo_tendencies(params, return_atmo_thermo_tensor=False):
     """Same contract as tendencies.py:133-211: the partial thermodynamic tendencies used by the vertical wind
     diagnostic, evaluated with the same GPU contraction."""
-    aip, oip, gip, agotensor = _build_reference_tensor(params, thermo=True)
+    from qgs_b200.functions import tensor_cache
+    cached = None if return_atmo_thermo_tensor else tensor_cache.cache_file(params, "atmo_thermo")
+    if cached is not None and os.path.exists(cached):
+        ndim, coo, val, _, _ = tensor_cache.load_tensor(cached)
+        if ndim != params.ndim:
+            raise RuntimeError("%s holds a %d-variable tensor, the parameters describe %d variables"
+                               % (cached, ndim, params.ndim))
+        agotensor = None
+    else:
+        aip, oip, gip, agotensor = _build_reference_tensor(params, thermo=True)
 
-    coo = agotensor.tensor.coords.T
-    val = agotensor.tensor.data
+        coo = agotensor.tensor.coords.T
+        val = agotensor.tensor.data
+        store = tensor_cache.cache_file(params, "atmo_thermo")
+        if store is not None and not os.path.exists(store):
+            tensor_cache.save_tensor(store, params.ndim, coo, val, np.zeros((0, np.shape(coo)[1]), dtype=np.int32),
+                                     np.zeros(0))
 
     f = Tendencies(DeviceTensor(params.ndim, coo, val, specialise=False))
 

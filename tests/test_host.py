@@ -375,6 +375,10 @@ def test_tensor_file_round_trip_and_validation(tmp_path):
     assert np.array_equal(coo, z["coo"]) and np.array_equal(val, z["val"])
     assert np.array_equal(jcoo, z["jcoo"]) and np.array_equal(jval, z["jval"])
     assert os.listdir(tmp_path) == ["t4.npz"]                       # no temporary file left behind
+    # a tensor without Jacobian part (create_atmo_thermo_tendencies) round-trips too
+    thermo = tensor_cache.save_tensor(str(tmp_path / "thermo.npz"), ndim, coo, val, np.zeros((0, 5), np.int32), np.zeros(0))
+    assert tensor_cache.load_tensor(thermo)[3].shape == (0, 5) and len(tensor_cache.load_tensor(thermo)[4]) == 0
+    os.remove(thermo)
     # the golden fixtures are in the same format
     assert tensor_cache.load_tensor(os.path.join(GOLDEN, "tensor_maooam36.npz"))[0] == 36
     bad = str(tmp_path / "bad.npz")
