@@ -846,3 +846,16 @@ def test_vertical_velocity_diagnostic_under_the_overlay_matches_the_reference(tm
     assert a["raw"].shape == b["raw"].shape == (36, 300) and a["omega"].shape == b["omega"].shape
     assert np.max(np.abs(a["raw"] - b["raw"])) <= 1e-12 * np.max(np.abs(b["raw"]))
     assert np.max(np.abs(a["omega"] - b["omega"])) <= 1e-12 * np.max(np.abs(b["omega"]))
+
+
+def test_tensor_cache_serves_both_tensors_of_the_vertical_velocity_diagnostic():
+    """Row f-1 on the device: with QGSB_TENSOR_CACHE the second MiddleLayerVerticalVelocity reads the tendencies tensor
+    and the atmospheric thermodynamic tensor from files (the tensor construction is disabled for it) and produces
+    bitwise the same omega term (scripts/check_thermo_cache.py)."""
+    import subprocess
+    import sys
+    if not os.path.isdir(os.path.join(REPO, "baseline", "_ref", "qgs")):
+        pytest.skip("baseline/_ref is not installed")
+    res = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "check_thermo_cache.py")], capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0 and "thermo cache ok" in res.stdout, (res.stdout + res.stderr)[-3000:]
