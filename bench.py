@@ -19,6 +19,13 @@ STEPS_PER_LAUNCH classic-RK4 time steps of dt = 0.1 with write_steps = 0 -- one 
             baseline/_ref install on a bounded sample; the C oracle port (oracle/qgs_oracle.c, all host threads) is
             reported next to it as cpu_port, and replaces it (kind "port") when baseline/_ref or numba is missing.
 
+  lyapunov  BASELINE.json's fifth configuration as extra keys of the same line: the Benettin loop (tangent-linear RK4
+            of the 36 x 36 basis + Householder QR per step) of LyapunovsEstimator.compute_lyapunovs(0, 100, 200, 0.1,
+            0.1, write_steps=10) on 8192 members per GPU -- device-timed member-steps/s of qgsb_lyap_benettin with
+            its own FP64 roofline (525 532 flops per member-step), e2e through the Python class
+            (host arrays in, trajectory + exponents out), and the reference's LyapunovsEstimator on all host cores.
+  strong    the SAME total ensemble (2^20 members) split over the N GPUs: whole-job member-steps/s, device-timed.
+
 --impl reference times the reference's own CPU implementation of the path: RungeKuttaIntegrator from
 baseline/_ref through its public API (else the oracle port).  Under torchrun rank 0 alone runs it.
 """
@@ -43,6 +50,14 @@ DT = 0.1
 NDIM = 36
 FLOPS_PER_MEMBER_STEP = 4132          # 4 * sum_nnz(p + 1) + 14 * ndim, SURVEY.md section 8d
 TENSOR = os.path.join(REPO, "tests", "golden", "tensor_maooam36.npz")
+# the Lyapunov configuration (BASELINE.json configs[4])
+LYAP_MEMBERS_PER_GPU = 8192
+LYAP_ARGS = (0., 100., 200., 0.1, 0.1)      # t0, tw, t, dt, mdt of compute_lyapunovs
+LYAP_WRITE_STEPS = 10
+LYAP_NVEC = 36
+LYAP_STEPS = 2000                            # Benettin steps per member: 1000 of convergence + 1000 recorded
+# 4 (F_f + 2 jnnz + 2 n^2 m) + 14 n + 14 n m + 4 n m^2 - 4/3 m^3 with F_f = 907, jnnz = 699, n = m = 36
+LYAP_FLOPS_PER_MEMBER_STEP = 525532
 
 
 def workload_config(n_gpus):
@@ -184,6 +199,7 @@ class ReferenceNumba(object):
         p.atemperature_params.set_insolation(103.3333, 0)
         p.gotemperature_params.set_insolation(310., 0)
         f, Df = create_tendencies(p)
+        self.f, self.Df = f, Df
         self.cores = os.cpu_count() or 1
         self.integrator = RungeKuttaIntegrator(num_threads=self.cores)
         self.integrator.set_func(f)
@@ -214,6 +230,94 @@ class ReferenceNumba(object):
             pass
 
 
+class ReferenceLyapunov(object):
+    """The UNMODIFIED reference's LyapunovsEstimator (qgs/toolbox/lyapunov.py:41-468: numba + one worker process per
+    host core) from baseline/_ref on the Lyapunov configuration: compute_lyapunovs(0, 100, 200, 0.1, 0.1,
+    write_steps=10), 36 vectors."""
+
+    def __init__(self, ref):
+        from qgs.toolbox.lyapunov import LyapunovsEstimator
+        self.cores = ref.cores
+        self.est = LyapunovsEstimator(num_threads=self.cores)
+        self.est.set_func(ref.f, ref.Df)
+        # every worker JIT-compiles the Benettin loop on its first member
+        self.est.compute_lyapunovs(0., 0.2, 0.4, 0.1, 0.1, initial_conditions(0, self.cores), write_steps=1)
+        self.est.get_lyapunovs()
+
+    def rate(self, members=None):
+        members = members or 4 * self.cores
+        ic = initial_conditions(0, members)
+        t0 = time.perf_counter()
+        self.est.compute_lyapunovs(*LYAP_ARGS, ic, write_steps=LYAP_WRITE_STEPS)
+        self.est.get_lyapunovs()
+        wall = time.perf_counter() - t0
+        return {"value": members * LYAP_STEPS / wall, "unit": UNIT, "cores": self.cores, "kind": "reference",
+                "sample": "%d members x %d Benettin steps, 36 vectors, unmodified qgs LyapunovsEstimator (numba + %d "
+                          "worker processes) from baseline/_ref, %.1f s wall" % (members, LYAP_STEPS, self.cores, wall)}
+
+    def close(self):
+        try:
+            self.est.terminate()
+        except Exception:
+            pass
+
+
+def lyapunov_port_rate(target_seconds=8.0):
+    """The C oracle port of the Benettin loop on all host threads (used when the reference cannot run)."""
+    import oracle
+    T = oracle.Tensor.from_npz(TENSOR)
+    b, c, a = oracle.rk4_tableau()
+    cores = os.cpu_count() or 1
+    oracle.set_num_threads(cores)
+    members = cores
+    ic = initial_conditions(0, members)
+    rng = np.random.default_rng(7)
+    q0 = np.stack([np.linalg.qr(rng.random((NDIM, LYAP_NVEC)))[0] for _ in range(members)])
+    pre = np.concatenate((np.arange(LYAP_ARGS[0], LYAP_ARGS[1], LYAP_ARGS[3]), [LYAP_ARGS[1]]))
+    tim = np.concatenate((np.arange(LYAP_ARGS[1], LYAP_ARGS[2], LYAP_ARGS[3]), [LYAP_ARGS[2]]))
+    t0 = time.perf_counter()
+    oracle.compute_backward_lyap(T, pre, tim, LYAP_ARGS[4], ic, LYAP_NVEC, LYAP_WRITE_STEPS, False, 1., b, c, a, q0, None)
+    wall = time.perf_counter() - t0
+    return {"value": members * LYAP_STEPS / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d members x %d Benettin steps, 36 vectors, oracle/qgs_oracle.c with %d pthreads, %.1f s wall"
+                      % (members, LYAP_STEPS, cores, wall)}
+
+
+def cpu_legs(rk_seconds, with_port=True):
+    """All host-side baselines of one bench line, run BEFORE the GPU work and before any process group exists (the
+    other ranks must not spin in a collective while rank 0 times CPU code): the reference's RungeKuttaIntegrator and
+    LyapunovsEstimator from baseline/_ref when they can run here, else the C port; plus the C port of the RK4 path
+    as a second data point."""
+    base = port = lyap = None
+    ref = None
+    if os.environ.get("QGSB_BENCH_CPU", "") != "port":
+        try:
+            ref = ReferenceNumba()
+            base, _, _ = ref.rate(rk_seconds)
+        except Exception as exc:  # missing install / numba: say so and use the port
+            sys.stderr.write("reference numba path unavailable (%s); timing the C port instead\n" % (exc,))
+            base = None
+        if ref is not None and base is not None:
+            rl = None
+            try:
+                rl = ReferenceLyapunov(ref)
+                lyap = rl.rate()
+            except Exception as exc:
+                sys.stderr.write("reference LyapunovsEstimator unavailable (%s); timing the C port instead\n" % (exc,))
+            finally:
+                if rl is not None:
+                    rl.close()
+        if ref is not None:
+            ref.close()
+    if base is None:
+        base, _, _ = cpu_rate(rk_seconds)
+    elif with_port:
+        port, _, _ = cpu_rate(6.0)      # the C oracle port as a second data point (it is faster than numba)
+    if lyap is None:
+        lyap = lyapunov_port_rate()
+    return base, port, lyap
+
+
 def reference_or_port(target_seconds):
     """(baseline dict, members, wall): the reference's numba path when baseline/_ref can run here, else the C port."""
     if os.environ.get("QGSB_BENCH_CPU", "") != "port":
@@ -235,6 +339,7 @@ def run_reference(args, rank):
     rates, walls = [], []
     base = None
     ref = None
+    lyap = None
     if os.environ.get("QGSB_BENCH_CPU", "") != "port":
         try:
             ref = ReferenceNumba()
@@ -246,7 +351,18 @@ def run_reference(args, rank):
             rates.append(base["value"])
             walls.append(wall)
     if ref is not None:
+        rl = None
+        try:
+            rl = ReferenceLyapunov(ref)
+            lyap = rl.rate()
+        except Exception as exc:
+            sys.stderr.write("reference LyapunovsEstimator unavailable (%s); timing the C port instead\n" % (exc,))
+        finally:
+            if rl is not None:
+                rl.close()
         ref.close()
+    if lyap is None:
+        lyap = lyapunov_port_rate()
     value = float(np.mean(rates))
     base["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -254,6 +370,8 @@ def run_reference(args, rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.gpus), "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "lyapunov": {"metric": LYAP_METRIC, "value": lyap["value"], "unit": UNIT, "cpu_baseline": lyap,
+                         "e2e": {"value": lyap["value"], "unit": UNIT}},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -261,8 +379,77 @@ def run_reference(args, rank):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
+LYAP_METRIC = "Benettin member-steps/sec (tangent-linear RK4 of 36 vectors + QR per step), MAOOAM-36"
+
+
+def lyapunov_leg(lib, _lib, f, Df, rank, world, barrier, repeats):
+    """BASELINE.json configs[4]: LyapunovsEstimator.compute_lyapunovs(0, 100, 200, 0.1, 0.1, write_steps=10) on
+    LYAP_MEMBERS_PER_GPU members per rank, 36 vectors.  Returns (device seconds, e2e seconds, launches, finite) of
+    `repeats` calls on this rank."""
+    import ctypes
+    from qgs_b200.integrators.integrate import rk4_tableau, n_records_of
+    from qgs_b200.toolbox.lyapunov import LyapunovsEstimator, _subtimes
+    t0, tw, t, dt, mdt = LYAP_ARGS
+    ic = initial_conditions(1000 + rank, LYAP_MEMBERS_PER_GPU)
+    N = ic.shape[0]
+    b, c, a = rk4_tableau()
+    pre = np.concatenate((np.arange(t0, tw, dt), np.full((1,), tw)))
+    rec = np.concatenate((np.arange(tw, t, dt), np.full((1,), t)))
+    ptr_a, sub_a = _subtimes(pre, mdt)
+    ptr_b, sub_b = _subtimes(rec, mdt)
+    sub_ptr = np.ascontiguousarray(np.concatenate((ptr_a, ptr_b[1:] + ptr_a[-1])), dtype=np.int64)
+    sub_dt = np.ascontiguousarray(np.concatenate((sub_a, sub_b)))
+    dt_macro = np.ascontiguousarray(np.concatenate((np.diff(pre), np.diff(rec))))
+    n_pre, n_rec = len(pre) - 1, len(rec) - 1
+    assert n_pre + n_rec == LYAP_STEPS
+    R = n_records_of(rec, LYAP_WRITE_STEPS)
+    rec_traj, rec_exp = np.empty((N, NDIM, R)), np.empty((N, LYAP_NVEC, R))
+    ms = ctypes.c_double()
+    _lib.set_seed(21217, rank * N)
+
+    def device_call():
+        # q0 = NULL: start bases drawn and factorised on the device; rec_vec = NULL: exponents only
+        _lib.check(lib.qgsb_lyap_benettin(
+            f.tensor.handle, N, _lib.dptr(ic), 0, LYAP_NVEC, None, None, n_pre, n_rec, _lib.dptr(dt_macro),
+            sub_ptr.ctypes.data_as(_lib.c_long_p), _lib.dptr(sub_dt), 4, _lib.dptr(a), _lib.dptr(b), _lib.dptr(c),
+            LYAP_WRITE_STEPS, 0, 1., R, _lib.dptr(rec_traj), _lib.dptr(rec_exp), None, None, None, ctypes.byref(ms)))
+        return ms.value
+
+    device_call()                                   # warm-up (module load, pool growth)
+    barrier()
+    launches0 = _lib.launch_count()
+    dev_s = sum(device_call() for _ in range(repeats)) * 1e-3
+    launches = _lib.launch_count() - launches0
+    finite = bool(np.all(np.isfinite(rec_exp)))
+    # end to end through the reference-facing class: host ic in, (time, traj, exponents) out
+    est = LyapunovsEstimator()
+    est.set_func(f, Df)
+
+    def e2e_call():
+        est.compute_lyapunovs(t0, tw, t, dt, mdt, ic, write_steps=LYAP_WRITE_STEPS, vectors=False,
+                              member_offset=rank * N)
+        return est.get_lyapunovs()
+
+    e2e_call()
+    barrier()
+    t_wall = time.perf_counter()
+    for _ in range(repeats):
+        res = e2e_call()
+    barrier()
+    e2e_s = time.perf_counter() - t_wall
+    spectrum = np.asarray(res[2]).reshape(N, LYAP_NVEC, -1).mean(axis=(0, 2))
+    return dev_s, e2e_s, launches, finite, spectrum, (N * NDIM * 8, N * (NDIM + LYAP_NVEC) * R * 8)
+
+
 def run_ours(args, rank, world, local_rank):
     import ctypes
+
+    # host-side baselines first, on rank 0 alone and before the process group exists: the other ranks wait in the
+    # rendezvous of init_process_group (a sleeping TCP wait), not in a spinning NCCL barrier
+    base = port = lyap_cpu = None
+    if rank == 0:
+        base, port, lyap_cpu = cpu_legs(10.0)
+
     import torch
     from qgs_b200 import _lib
     from qgs_b200.functions.tendencies import tendencies_from_tensor
@@ -271,6 +458,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     torch.cuda.set_device(local_rank)
     if world > 1:
+        import datetime
         import torch.distributed as dist
         # NCCL prints its version banner on stdout when the first communicator comes up: keep stdout for the one
         # JSON line by pointing fd 1 at stderr until the group exists
@@ -278,7 +466,8 @@ def run_ours(args, rank, world, local_rank):
         saved = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                    timeout=datetime.timedelta(minutes=30))
             dist.barrier()
             torch.cuda.synchronize()
         finally:
@@ -289,7 +478,7 @@ def run_ours(args, rank, world, local_rank):
     lib = _lib.load()
 
     z = np.load(TENSOR)
-    f, _ = tendencies_from_tensor(int(z["ndim"]), z["coo"], z["val"], z["jcoo"], z["jval"])
+    f, Df = tendencies_from_tensor(int(z["ndim"]), z["coo"], z["val"], z["jcoo"], z["jval"])
     if f.tensor.kernel_kind != 2:
         raise RuntimeError("the MAOOAM-36 specialised kernels are not linked into libqgsb.so")
     b, c, a = rk4_tableau()
@@ -316,8 +505,8 @@ def run_ours(args, rank, world, local_rank):
     _lib.check(lib.qgsb_ensemble_upload(ens, _lib.dptr(ic_np)))
     ms = ctypes.c_double()
 
-    def launch():
-        _lib.check(lib.qgsb_ensemble_integrate(ens, n_steps, _lib.dptr(dt), 4, _lib.dptr(a), _lib.dptr(b),
+    def launch(handle=None):
+        _lib.check(lib.qgsb_ensemble_integrate(handle or ens, n_steps, _lib.dptr(dt), 4, _lib.dptr(a), _lib.dptr(b),
                                                _lib.dptr(c), ctypes.byref(ms)))
         return ms.value
 
@@ -355,14 +544,34 @@ def run_ours(args, rank, world, local_rank):
     s2 = np.empty(NDIM)
     _lib.check(lib.qgsb_ensemble_moments(ens, _lib.dptr(s1), _lib.dptr(s2)))
     moments = torch.from_numpy(np.concatenate((s1, s2))).cuda()
+    lib.qgsb_ensemble_destroy(ens)
+
+    # ---- strong scaling: the SAME 2^20-member ensemble split over the ranks (balanced contiguous blocks) ----
+    lo, hi = rank * members // world, (rank + 1) * members // world
+    strong_ms = total_ms
+    if world > 1:
+        ens_s = ctypes.c_void_p()
+        _lib.check(lib.qgsb_ensemble_create(f.tensor.handle, hi - lo, ctypes.byref(ens_s)))
+        _lib.check(lib.qgsb_ensemble_upload(ens_s, _lib.dptr(ic_np[lo:hi])))
+        for _ in range(args.warmup):
+            launch(ens_s)
+        barrier()
+        strong_ms = float(sum(launch(ens_s) for _ in range(args.steps)))
+        barrier()
+        lib.qgsb_ensemble_destroy(ens_s)
+
+    # ---- Lyapunov configuration ----
+    lyap_repeats = max(1, min(args.steps, 3))
+    ly_dev_s, ly_e2e_s, ly_launches, ly_finite, spectrum, ly_bytes = lyapunov_leg(lib, _lib, f, Df, rank, world,
+                                                                                  barrier, lyap_repeats)
+
     if dist is not None:
         dist.all_reduce(moments)
-        worst = torch.tensor([total_ms, e2e_s, wall_s], dtype=torch.float64).cuda()
+        worst = torch.tensor([total_ms, e2e_s, wall_s, strong_ms, ly_dev_s, ly_e2e_s], dtype=torch.float64).cuda()
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, wall_s = [float(v) for v in worst.cpu()]
+        total_ms, e2e_s, wall_s, strong_ms, ly_dev_s, ly_e2e_s = [float(v) for v in worst.cpu()]
     mean = (moments[:NDIM] / (members * world)).cpu().numpy()
     finite = bool(np.all(np.isfinite(mean)))
-    lib.qgsb_ensemble_destroy(ens)
 
     if rank == 0:
         member_steps = float(members) * n_steps * args.steps * world
@@ -376,29 +585,48 @@ def run_ours(args, rank, world, local_rank):
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except (ValueError, OSError):
                 traffic = None
-        base, _, _ = reference_or_port(10.0)
-        port = None
-        if base.get("kind") == "reference":
-            port, _, _ = cpu_rate(6.0)      # the C oracle port as a second data point (it is faster than numba)
+        ly_steps = float(LYAP_MEMBERS_PER_GPU) * LYAP_STEPS * lyap_repeats
+        ly_ach = LYAP_FLOPS_PER_MEMBER_STEP * ly_steps / ly_dev_s / 1e12       # per GPU: the slowest rank's time
+        peak_note = ("DFMA micro-benchmark measured on this device in this run (qgsb_fp64_peak); "
+                     "MEASURED_PEAKS.json has no FP64 entry")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(world),
                 "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                             "traffic": traffic,
-                             "peak_source": "DFMA micro-benchmark measured on this device in this run "
-                                            "(qgsb_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                             "traffic": traffic, "peak_source": peak_note,
                              "flops_per_member_step": FLOPS_PER_MEMBER_STEP, "kernel": "rk_chain_kernel (maooam36)"},
                 "cpu_baseline": base, "cpu_port": port,
                 "e2e": {"value": member_steps / e2e_s, "unit": UNIT,
                         "h2d_bytes_per_step": world * (members * NDIM * 8 + n_steps * 8),
                         "d2h_bytes_per_step": world * members * NDIM * 8,
                         "call": "qgsb_rk_integrate (C ABI behind RungeKuttaIntegrator.integrate), pinned host buffers"},
+                "strong": {"value": float(members) * n_steps * args.steps / (strong_ms * 1e-3), "unit": UNIT,
+                           "members_total": members, "ms_per_step": strong_ms / args.steps,
+                           "note": "the same 2^20-member ensemble split over the %d GPU(s); device-timed, max over "
+                                   "ranks" % world},
+                "lyapunov": {
+                    "metric": LYAP_METRIC, "value": ly_steps * world / ly_dev_s, "unit": UNIT,
+                    "ms_per_step": ly_dev_s / lyap_repeats * 1e3, "steps": lyap_repeats, "scaling": "weak",
+                    "config": {"workload": "LyapunovsEstimator.compute_lyapunovs(0, 100, 200, 0.1, 0.1, write_steps=10), "
+                                           "MAOOAM-36, %d members/GPU, 36 vectors, mdt = dt: %d Benettin steps per "
+                                           "member and call; start bases drawn on the device; exponents only"
+                                           % (LYAP_MEMBERS_PER_GPU, LYAP_STEPS),
+                               "members_per_gpu": LYAP_MEMBERS_PER_GPU, "n_vec": LYAP_NVEC},
+                    "roofline": {"bound": "fp64", "achieved": ly_ach, "peak": peak, "unit": "TFLOP/s",
+                                 "frac": ly_ach / peak, "traffic": None, "peak_source": peak_note,
+                                 "flops_per_member_step": LYAP_FLOPS_PER_MEMBER_STEP,
+                                 "kernel": "pack::lyap_kernel<36, bilinear product, pipelined QR>"},
+                    "e2e": {"value": ly_steps * world / ly_e2e_s, "unit": UNIT,
+                            "h2d_bytes_per_step": world * ly_bytes[0], "d2h_bytes_per_step": world * ly_bytes[1],
+                            "call": "LyapunovsEstimator.compute_lyapunovs(..., vectors=False) + get_lyapunovs(): host "
+                                    "numpy arrays in and out"},
+                    "cpu_baseline": lyap_cpu, "gpu_launches": int(ly_launches), "exponents_finite": ly_finite,
+                    "leading_exponents": [float(v) for v in spectrum[:4]]},
                 "gpu_launches": int(n_launches), "clocks": clocks,
                 "wall_s_timed_region": wall_s, "ensemble_mean_finite": finite}
         print(json.dumps(line), flush=True)
     if dist is not None:
-        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -15,8 +15,14 @@
  *   - return value 0 = success; non-zero = failure, message in qgsb_last_error() (thread local).
  *   - calls are synchronous (they return when results are in the caller's buffers), like the
  *     reference's integrate() which blocks on queue.join() (integrator.py:391).  The library may be
- *     called from several host threads: entry points serialise on one process-wide lock (one device
- *     context per process, one process per GPU).
+ *     called from several host threads: entry points serialise on one process-wide lock.
+ *   - devices: a process drives ONE device (one process per GPU under torchrun: LOCAL_RANK) or SEVERAL (any other
+ *     process on a multi-GPU box, see qgsb_init).  With several, the host-buffer entry points qgsb_rk_integrate,
+ *     qgsb_rk_tgls_integrate and qgsb_lyap_benettin split the members into contiguous blocks
+ *     [g N / G, (g + 1) N / G), one per device, and run them concurrently on the devices' own streams -- the
+ *     reference's fan-out of one integrate() over num_threads worker processes (integrator.py:121-142, 386-395).
+ *     Members are independent, nothing is exchanged, results are bitwise those of one device.  Handles and
+ *     resident ensembles live on the primary device (the first of the list).
  *   - there is no CPU fallback: without a CUDA device every compute call fails with an error.
  */
 #ifndef QGSB_H
@@ -40,10 +46,17 @@ typedef struct qgsb_ensemble qgsb_ensemble; /* device-resident ensemble state (s
 
 /* ---- runtime ---------------------------------------------------------------------------------- */
 
-/* Bind the calling process to one CUDA device (device < 0: LOCAL_RANK from the environment, else 0)
- * and create the library stream.  Replaces RungeKuttaIntegrator.start() spawning the worker pool
- * (qgs/integrators/integrator.py:121-142).  Idempotent. */
+/* Choose the device(s) and create the library streams.  Replaces RungeKuttaIntegrator.start() spawning the worker
+ * pool (qgs/integrators/integrator.py:121-142).  device >= 0: that device only.  device < 0: keep the current
+ * configuration when there is one; else QGSB_DEVICES ("all", a count, or a comma-separated list of ordinals) decides;
+ * without it a torchrun rank (LOCAL_RANK set) takes its own device and any other process every visible device.
+ * Idempotent. */
 QGSB_API int qgsb_init(int device);
+/* Drive exactly these devices (CUDA ordinals; the first is the primary one).  Handles created before stay valid as
+ * long as their device is still visible; resident ensembles must be re-created when the primary device changes. */
+QGSB_API int qgsb_set_devices(int n_devices, const int *devices);
+/* Number of devices the library drives (0 before initialisation). */
+QGSB_API int qgsb_device_count(void);
 /* Release scratch memory and the stream; replaces terminate() (integrator.py:113-119).  Idempotent. */
 QGSB_API void qgsb_shutdown(void);
 /* Launch on a caller-provided cudaStream_t (e.g. torch's current stream); NULL restores the own stream. */
@@ -123,8 +136,10 @@ QGSB_API int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long n_traj, const dou
  * forward == 1 (FLV, :480-552): the trajectory is first integrated forward over dt_macro reversed and
  *   stored in HBM, then walked backwards; dt_macro / sub_dt are given in execution (backward) order, negative.
  * forward == 2: like 0 but the nonlinear state follows the micro steps (Ginelli forward pass, :1212-1218).
- * q0 (N, n, n_vec), r0 (N, n_vec, n_vec) or NULL: the start basis (the reference draws
- * qr(random((n_dim, n_vec))), lyapunov.py:592-593, on the host side).
+ * q0 (N, n, n_vec), r0 (N, n_vec, n_vec) or NULL: the start basis.  The reference draws
+ * qr(random((n_dim, n_vec))), lyapunov.py:592-593; q0 == NULL does the same ON THE DEVICE (counter-based uniform
+ * draw keyed by qgsb_set_seed and the member's index, factorised by the kernel's own Householder QR), so no
+ * (N, n, n_vec) array crosses the bus and no host LAPACK runs.
  * rec_* follow _compute_*_lyap_traj_jit's return values: traj (N, n, R), exp (N, n_vec, R),
  * vec (N, n, n_vec, R); rec_vec may be NULL when only the exponents are wanted (no vector records are kept
  * or copied).  r_all (N, n_steps_total, n_vec, n_vec) or NULL stores every R factor and
@@ -136,6 +151,10 @@ QGSB_API int qgsb_lyap_benettin(const qgsb_tensor *t, long n_traj, const double 
                        int adjoint, double inverse_sign, long n_records,
                        double *rec_traj, double *rec_exp, double *rec_vec,
                        double *r_all, double *q_all, double *device_ms);
+
+/* Seed of the device-side start bases (q0 == NULL above); member_offset is added to the member index, so that a
+ * process holding members [lo, hi) of a larger ensemble draws what a single process would have drawn for them. */
+QGSB_API int qgsb_set_seed(uint64_t seed, long member_offset);
 
 /* Covariant Lyapunov vectors, method of Ginelli et al. -- replaces _compute_clv_gin_jit
  * (qgs/toolbox/lyapunov.py:1174-1288) with solve_triangular_matrix / normalize_matrix_columns

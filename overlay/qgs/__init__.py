@@ -38,6 +38,23 @@ def _real_package_dirs(subpackage=""):
 
 __path__ = [_HERE] + _real_package_dirs()
 
+
+def _real_version():
+    """``__version__`` of the real package (its __init__ is shadowed by this one): qgs/__init__.py:2."""
+    import re
+    for d in _real_package_dirs():
+        try:
+            with open(os.path.join(d, "__init__.py")) as fh:
+                m = re.search(r"__version__\s*=\s*['\"]([^'\"]+)['\"]", fh.read())
+        except OSError:
+            continue
+        if m:
+            return m.group(1)
+    return ""
+
+
+__version__ = _real_version()
+
 # reference modules that pass the tendencies into numba code get a batched device evaluation instead (wind.py:705-714)
 try:
     from qgs_b200 import overlay_hooks as _hooks

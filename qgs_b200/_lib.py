@@ -19,6 +19,9 @@ c_void_pp = ctypes.POINTER(ctypes.c_void_p)
 
 _PROTOTYPES = {
     "qgsb_init": (ctypes.c_int, [ctypes.c_int]),
+    "qgsb_set_devices": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "qgsb_device_count": (ctypes.c_int, []),
+    "qgsb_set_seed": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_long]),
     "qgsb_shutdown": (None, []),
     "qgsb_set_stream": (ctypes.c_int, [ctypes.c_void_p]),
     "qgsb_last_error": (ctypes.c_char_p, []),
@@ -130,6 +133,23 @@ def i32(a):
 
 def init(device=-1):
     check(load().qgsb_init(int(device)))
+
+
+def set_devices(devices):
+    """Drive exactly these CUDA devices (the first is the primary one); see ``qgsb_set_devices``."""
+    devices = [int(d) for d in devices]
+    arr = (ctypes.c_int * len(devices))(*devices)
+    check(load().qgsb_set_devices(len(devices), arr))
+
+
+def device_count():
+    """Number of devices the library drives (0 before the first ``init``)."""
+    return int(load().qgsb_device_count())
+
+
+def set_seed(seed, member_offset=0):
+    """Seed of the start bases the Benettin kernels draw on the device (``qgsb_set_seed``)."""
+    check(load().qgsb_set_seed(ctypes.c_uint64(int(seed) & ((1 << 64) - 1)), int(member_offset)))
 
 
 def device_info():

@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -39,9 +41,8 @@ struct Failure {};  // thrown internally, caught at the ABI boundary
         }                                     \
     } while (0)
 
-// The context (stream, scratch pool, kernel registry) is process-wide: entry points serialise on one lock, so the
-// library may be called from several host threads (ctypes releases the GIL) -- calls queue up like the reference's
-// integrate() calls queue on its worker pool.
+// Entry points serialise on one process-wide lock, so the library may be called from several host threads (ctypes
+// releases the GIL) -- calls queue up like the reference's integrate() calls queue on its worker pool.
 std::recursive_mutex &api_mutex();
 #define QGSB_API_LOCK std::lock_guard<std::recursive_mutex> api_guard__(qgsb::api_mutex());
 
@@ -58,10 +59,24 @@ std::recursive_mutex &api_mutex();
     }
 
 // ------------------------------------------------------------------------------------------------
-// process-wide context: one device, one stream (one process per GPU)
+// device contexts.  The library drives one OR SEVERAL devices from one process: slot 0 is the primary device (every
+// handle is created there), further slots are the other devices of the box.  A context owns its streams, timing
+// events and scratch pool.  ctx() is the context the CALLING THREAD is bound to (slot 0 unless the thread is one of
+// the per-device workers of run_sharded): the single-device code below the entry points never needs to know that
+// other devices exist.  This replaces the reference's pool of worker processes fed one trajectory at a time
+// (qgs/integrators/integrator.py:121-142, 386-395).
 // ------------------------------------------------------------------------------------------------
+constexpr int MAX_DEVICES = 16;
+
+struct PoolBlock {
+    void *p;
+    size_t bytes;
+    bool used;
+};
+
 struct Context {
     bool ready = false;
+    int slot = 0;
     int device = 0;
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
@@ -72,10 +87,28 @@ struct Context {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of the pipelined host-buffer paths
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long launches = 0;
+    std::vector<PoolBlock> pool;                          // grow-only scratch pool of this device
 };
 Context &ctx();
 void ensure_init();
 inline void count_launch(long n = 1) { ctx().launches += n; }
+
+// number of devices the library drives (>= 1 after ensure_init)
+int device_slots();
+// Contiguous balanced split of [0, n) over `parts`: part g is [g n / parts, (g + 1) n / parts)
+// (the rule of qgs_b200.ensemble.shard_bounds and of SURVEY.md section 8e).
+inline void shard_range(long n, int parts, int g, long *lo, long *hi)
+{
+    *lo = (long)((__int128)g * n / parts);
+    *hi = (long)((__int128)(g + 1) * n / parts);
+}
+// How many devices a call over n_members should use: all of them when every shard keeps at least min_per_device
+// members (so that the shards run the same kernel family as the whole ensemble would), else fewer, else 1.
+int shard_count(long n_members, long min_per_device);
+// Runs body(g, lo, hi) for the `parts` shards of [0, n) concurrently, shard g on device slot g: shard 0 on the calling
+// thread, the others on worker threads bound to their device for the duration of the call (ctx() is theirs).  A
+// failure in any shard is re-thrown on the calling thread with that shard's message.
+void run_sharded(long n, int parts, const std::function<void(int, long, long)> &body);
 
 // ------------------------------------------------------------------------------------------------
 // ensemble layout in HBM ("tiled structure of arrays"): members are grouped in tiles of TILE = 128;
@@ -123,12 +156,13 @@ struct DevBuf {
 // run many times with the same sizes (one integrate() per chunk of a long run), and cudaMalloc /
 // cudaFree of hundreds of MB per call would dominate their end-to-end time.
 void *pool_acquire(size_t bytes);
-void pool_release(void *p);
+void pool_release(Context *owner, void *p);
 void pool_trim();
 template <typename T>
 struct PoolBuf {
     T *p = nullptr;
     size_t n = 0;
+    Context *owner = nullptr;   // the device context whose pool the buffer came from (and goes back to)
     PoolBuf() {}
     explicit PoolBuf(size_t count) { alloc(count); }
     PoolBuf(const PoolBuf &) = delete;
@@ -137,10 +171,11 @@ struct PoolBuf {
     void alloc(size_t count) {
         release();
         n = count;
+        owner = &ctx();
         p = (T *)pool_acquire(std::max<size_t>(count, 1) * sizeof(T));
     }
     void release() {
-        if (p) pool_release(p);
+        if (p) pool_release(owner, p);
         p = nullptr;
         n = 0;
     }
@@ -215,11 +250,20 @@ struct qgsb_tensor {
     // tables of the packed tangent kernels, built on first use: [0] dense product, [1] generated product
     struct PackCache;
     mutable PackCache *pack_cache[2] = {nullptr, nullptr};
+    // ---- several devices: the handle lives on `device`; the other devices get a replica on first use ----
+    int device = 0;                                  // CUDA ordinal the device arrays above live on
+    int ndim_in = 0;                                 // the caller's arrays, kept to build replicas
+    std::vector<int32_t> in_coo, in_jcoo;
+    std::vector<double> in_val, in_jval;
+    mutable std::map<int, qgsb_tensor *> replicas;   // CUDA ordinal -> copy of this handle on that device
+    mutable std::mutex replica_mutex;
     ~qgsb_tensor();
 };
 
 namespace qgsb {
 void g3_release(qgsb_tensor::G3Cache *c);
+// the copy of handle t that lives on the calling thread's device (t itself on its own device)
+const qgsb_tensor *tensor_here(const qgsb_tensor *t);
 }
 
 struct qgsb_ensemble {

@@ -1199,20 +1199,11 @@ static void stream_trajectories(const qgsb_tensor *t, double *d_y, long ld, long
     }
 }
 
-int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_steps, const double *dt, int s,
-                      const double *a, const double *b, const double *c, long write_steps, int time_direction,
-                      long R, double *traj, double *device_ms)
+// one device's share of qgsb_rk_integrate: members [0, N) of ic / traj on the calling thread's device
+static void rk_integrate_device(const qgsb_tensor *t, long N, const double *ic, long n_steps, const double *dt, int s,
+                                const double *a, const double *b, long write_steps, int time_direction, long R,
+                                double *traj, double *device_ms)
 {
-    (void)c;
-    QGSB_API_BEGIN
-    QGSB_REQUIRE(t && ic && traj, "null argument");
-    QGSB_REQUIRE(N >= 1, "need at least one trajectory, got %ld", N);
-    QGSB_REQUIRE(n_steps >= 0 && write_steps >= 0, "negative step count");
-    QGSB_REQUIRE(n_steps == 0 || dt != nullptr, "null dt array");
-    QGSB_REQUIRE(time_direction == 1 || time_direction == -1, "time_direction must be +1 or -1");
-    QGSB_REQUIRE(R == records_for(n_steps, write_steps), "n_records %ld inconsistent with %ld steps / write_steps %ld",
-                 R, n_steps, write_steps);
-    ensure_init();
     Context &cx = ctx();
     cudaStream_t st = cx.stream;
     const Tableau tab = make_tableau(s, a, b);
@@ -1267,7 +1258,7 @@ int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_ste
                 QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
                 *device_ms = ms;
             }
-            return 0;
+            return;
         }
         d_ic.upload(ic, (size_t)N * n, st);
         launch_aos_to_soa(d_ic.p, d_y.p, N, n, ld);
@@ -1285,7 +1276,7 @@ int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_ste
             QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
             *device_ms = ms;
         }
-        return 0;
+        return;
     }
     d_out.download(traj, (size_t)N * n * R, st);
     QGSB_CUDA(cudaStreamSynchronize(st));
@@ -1294,6 +1285,34 @@ int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_ste
         QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
         *device_ms = ms;
     }
+}
+
+// Members are independent ODE solves: with several devices the ensemble is split into contiguous blocks, one per
+// device, each integrated by the single-device path above on its own streams (the reference deals trajectories to its
+// worker processes, integrator.py:386-395).  A shard never falls under the size at which the whole ensemble would
+// have chosen another kernel family, so the results are bitwise those of one device.
+int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_steps, const double *dt, int s,
+                      const double *a, const double *b, const double *c, long write_steps, int time_direction,
+                      long R, double *traj, double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t && ic && traj, "null argument");
+    QGSB_REQUIRE(N >= 1, "need at least one trajectory, got %ld", N);
+    QGSB_REQUIRE(n_steps >= 0 && write_steps >= 0, "negative step count");
+    QGSB_REQUIRE(n_steps == 0 || dt != nullptr, "null dt array");
+    QGSB_REQUIRE(time_direction == 1 || time_direction == -1, "time_direction must be +1 or -1");
+    QGSB_REQUIRE(R == records_for(n_steps, write_steps), "n_records %ld inconsistent with %ld steps / write_steps %ld",
+                 R, n_steps, write_steps);
+    ensure_init();
+    const int n = t->view.n;
+    const int parts = shard_count(N, std::max<long>(4096, 2 * rows_threshold()));
+    std::vector<double> ms(parts, 0.);
+    run_sharded(N, parts, [&](int g, long lo, long hi) {
+        rk_integrate_device(tensor_here(t), hi - lo, ic + (size_t)lo * n, n_steps, dt, s, a, b, write_steps,
+                            time_direction, R, traj + (size_t)lo * n * R, device_ms ? &ms[g] : nullptr);
+    });
+    if (device_ms) *device_ms = *std::max_element(ms.begin(), ms.end());
     QGSB_API_END
 }
 

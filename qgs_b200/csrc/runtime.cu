@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <map>
 #include <numeric>
+#include <thread>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -24,11 +25,15 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
-Context &ctx()
-{
-    static Context c;
-    return c;
-}
+// ------------------------------------------------------------------------------------------------
+// device contexts
+// ------------------------------------------------------------------------------------------------
+static Context g_ctx[MAX_DEVICES];
+static int g_slots = 0;                      // devices the library drives; 0 = not initialised
+static thread_local Context *tl_ctx = nullptr;
+
+Context &ctx() { return tl_ctx ? *tl_ctx : g_ctx[0]; }
+int device_slots() { return g_slots; }
 
 std::recursive_mutex &api_mutex()
 {
@@ -36,34 +41,12 @@ std::recursive_mutex &api_mutex()
     return m;
 }
 
-static void init_device(int device)
+static void context_open(Context &c, int slot, int device)
 {
-    Context &c = ctx();
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    QGSB_REQUIRE(e == cudaSuccess && count > 0,
-                 "no CUDA device available (%s); libqgsb has no CPU fallback",
-                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-    if (device < 0) {
-        const char *lr = getenv("LOCAL_RANK");
-        device = lr ? atoi(lr) % count : 0;
-    }
-    QGSB_REQUIRE(device < count, "device %d requested but only %d visible", device, count);
-    if (c.ready && c.device == device) return;
-    if (c.ready) {
-        cudaSetDevice(c.device);
-        cudaStreamSynchronize(c.stream);
-        pool_trim();                       // the scratch pool belongs to the device we are leaving
-        cudaStreamDestroy(c.own_stream);
-        cudaStreamDestroy(c.copy_in);
-        cudaStreamDestroy(c.copy_out);
-        cudaEventDestroy(c.ev0);
-        cudaEventDestroy(c.ev1);
-        c.ready = false;
-    }
     QGSB_CUDA(cudaSetDevice(device));
     cudaDeviceProp p;
     QGSB_CUDA(cudaGetDeviceProperties(&p, device));
+    c.slot = slot;
     c.device = device;
     c.sm_count = p.multiProcessorCount;
     c.cc_major = p.major;
@@ -79,23 +62,160 @@ static void init_device(int device)
     c.ready = true;
 }
 
-// ------------------------------------------------------------------------------------------------
-// scratch pool
-// ------------------------------------------------------------------------------------------------
-struct PoolBlock {
-    void *p;
-    size_t bytes;
-    bool used;
-};
-static std::vector<PoolBlock> &pool()
+static void context_close(Context &c)
 {
-    static std::vector<PoolBlock> blocks;
-    return blocks;
+    if (!c.ready) return;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    for (auto &blk : c.pool)
+        if (!blk.used) cudaFree(blk.p);
+    c.pool.erase(std::remove_if(c.pool.begin(), c.pool.end(), [](const PoolBlock &b) { return !b.used; }), c.pool.end());
+    cudaStreamDestroy(c.own_stream);
+    cudaStreamDestroy(c.copy_in);
+    cudaStreamDestroy(c.copy_out);
+    cudaEventDestroy(c.ev0);
+    cudaEventDestroy(c.ev1);
+    c.own_stream = c.stream = c.copy_in = c.copy_out = nullptr;
+    c.ev0 = c.ev1 = nullptr;
+    c.ready = false;
 }
 
+static void close_all()
+{
+    for (int g = 0; g < MAX_DEVICES; ++g) context_close(g_ctx[g]);
+    g_slots = 0;
+}
+
+// Which devices does the process drive?  An explicit ordinal: that one.  Otherwise QGSB_DEVICES ("all", a count, or a
+// comma-separated list of ordinals) decides; without it a process started by torchrun (LOCAL_RANK set: one process
+// per GPU) takes its own device, and any other process takes EVERY visible device -- one integrate() call then
+// spreads its members over the box like the reference's spreads them over its worker processes.
+static std::vector<int> choose_devices(int device, int count)
+{
+    std::vector<int> devs;
+    if (device >= 0) {
+        QGSB_REQUIRE(device < count, "device %d requested but only %d visible", device, count);
+        devs.push_back(device);
+        return devs;
+    }
+    const char *env = getenv("QGSB_DEVICES");
+    const char *lr = getenv("LOCAL_RANK");
+    if (env && env[0]) {
+        if (!strcmp(env, "all")) {
+            for (int d = 0; d < count; ++d) devs.push_back(d);
+        } else if (strchr(env, ',')) {
+            std::string list(env);
+            size_t pos = 0;
+            while (pos <= list.size()) {
+                size_t next = list.find(',', pos);
+                if (next == std::string::npos) next = list.size();
+                if (next > pos) devs.push_back(atoi(list.substr(pos, next - pos).c_str()));
+                pos = next + 1;
+            }
+        } else {
+            const int want = atoi(env);
+            // a single number is a COUNT of devices ("QGSB_DEVICES=1": stay on one device)
+            for (int d = 0; d < std::min(std::max(want, 1), count); ++d) devs.push_back(d);
+        }
+    } else if (lr) {
+        devs.push_back(atoi(lr) % count);
+    } else {
+        for (int d = 0; d < count; ++d) devs.push_back(d);
+    }
+    QGSB_REQUIRE(!devs.empty() && (int)devs.size() <= MAX_DEVICES, "QGSB_DEVICES selects %zu devices (1..%d allowed)",
+                 devs.size(), MAX_DEVICES);
+    for (size_t q = 0; q < devs.size(); ++q) {
+        QGSB_REQUIRE(devs[q] >= 0 && devs[q] < count, "device %d requested but only %d visible", devs[q], count);
+        for (size_t r = 0; r < q; ++r) QGSB_REQUIRE(devs[r] != devs[q], "device %d listed twice", devs[q]);
+    }
+    return devs;
+}
+
+static void init_devices(const std::vector<int> &devs)
+{
+    bool same = g_slots == (int)devs.size();
+    for (int g = 0; same && g < g_slots; ++g) same = g_ctx[g].device == devs[g];
+    if (same && g_ctx[0].ready) {
+        cudaSetDevice(g_ctx[0].device);
+        return;
+    }
+    close_all();
+    // the primary context now; the others when a sharded call first needs them (run_sharded)
+    context_open(g_ctx[0], 0, devs[0]);
+    for (size_t g = 1; g < devs.size(); ++g) {
+        g_ctx[g].slot = (int)g;
+        g_ctx[g].device = devs[g];
+    }
+    g_slots = (int)devs.size();
+}
+
+static void init_device(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    QGSB_REQUIRE(e == cudaSuccess && count > 0,
+                 "no CUDA device available (%s); libqgsb has no CPU fallback",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    init_devices(choose_devices(device, count));
+}
+
+void ensure_init()
+{
+    if (g_slots == 0 || !g_ctx[0].ready) init_device(-1);
+    else cudaSetDevice(ctx().device);
+}
+
+int shard_count(long n_members, long min_per_device)
+{
+    if (g_slots <= 1 || tl_ctx != nullptr) return 1;      // a worker never shards again
+    const long by_size = n_members / std::max<long>(min_per_device, 1);
+    return (int)std::max<long>(1, std::min<long>(g_slots, by_size));
+}
+
+void run_sharded(long n, int parts, const std::function<void(int, long, long)> &body)
+{
+    if (parts <= 1) {
+        body(0, 0, n);
+        return;
+    }
+    std::vector<std::string> errors(parts);
+    std::vector<int> failed(parts, 0);
+    auto shard = [&](int g) {
+        long lo, hi;
+        shard_range(n, parts, g, &lo, &hi);
+        try {
+            Context &c = g_ctx[g];
+            if (!c.ready) context_open(c, g, c.device);
+            else QGSB_CUDA(cudaSetDevice(c.device));
+            tl_ctx = &c;
+            if (hi > lo) body(g, lo, hi);
+        } catch (const Failure &) {
+            failed[g] = 1;
+            errors[g] = g_err;
+        } catch (const std::exception &e) {
+            failed[g] = 1;
+            errors[g] = std::string("exception: ") + e.what();
+        }
+        tl_ctx = nullptr;
+    };
+    std::vector<std::thread> workers;
+    for (int g = 1; g < parts; ++g) workers.emplace_back(shard, g);
+    shard(0);
+    for (auto &w : workers) w.join();
+    cudaSetDevice(g_ctx[0].device);
+    for (int g = 0; g < parts; ++g)
+        if (failed[g]) {
+            set_error("device %d (shard %d of %d): %s", g_ctx[g].device, g, parts, errors[g].c_str());
+            throw Failure();
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scratch pool (one per device context)
+// ------------------------------------------------------------------------------------------------
 void pool_trim()
 {
-    auto &b = pool();
+    auto &b = ctx().pool;
     for (size_t i = 0; i < b.size();) {
         if (!b[i].used) {
             cudaFree(b[i].p);
@@ -108,7 +228,7 @@ void pool_trim()
 
 void *pool_acquire(size_t bytes)
 {
-    auto &b = pool();
+    auto &b = ctx().pool;
     int best = -1;
     for (size_t i = 0; i < b.size(); ++i)
         if (!b[i].used && b[i].bytes >= bytes && (best < 0 || b[i].bytes < b[best].bytes)) best = (int)i;
@@ -131,19 +251,14 @@ void *pool_acquire(size_t bytes)
     return p;
 }
 
-void pool_release(void *p)
+void pool_release(Context *owner, void *p)
 {
-    for (auto &blk : pool())
+    // a buffer goes back to the pool of the device it came from; only the thread bound to that device touches it
+    for (auto &blk : owner->pool)
         if (blk.p == p) {
             blk.used = false;
             return;
         }
-}
-
-void ensure_init()
-{
-    if (!ctx().ready) init_device(-1);
-    else cudaSetDevice(ctx().device);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -506,31 +621,53 @@ extern "C" {
 
 const char *qgsb_last_error(void) { return g_err; }
 const char *qgsb_version(void) { return "qgsb 0.1 (sm_100a)"; }
-long qgsb_launch_count(void) { return ctx().launches; }
+long qgsb_launch_count(void)
+{
+    long total = 0;
+    for (int g = 0; g < MAX_DEVICES; ++g) total += g_ctx[g].launches;
+    return total;
+}
 
 int qgsb_init(int device)
 {
     QGSB_API_BEGIN
+    // device < 0 on an initialised library keeps the configuration (start() of every integrator passes -1)
+    if (device < 0 && g_slots > 0 && g_ctx[0].ready) {
+        QGSB_CUDA(cudaSetDevice(g_ctx[0].device));
+        return 0;
+    }
     init_device(device);
     QGSB_API_END
+}
+
+int qgsb_set_devices(int n_devices, const int *devices)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(n_devices >= 1 && n_devices <= MAX_DEVICES && devices != nullptr, "need 1..%d device ordinals",
+                 MAX_DEVICES);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    QGSB_REQUIRE(e == cudaSuccess && count > 0, "no CUDA device available (%s); libqgsb has no CPU fallback",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    std::vector<int> devs(devices, devices + n_devices);
+    for (int q = 0; q < n_devices; ++q) {
+        QGSB_REQUIRE(devs[q] >= 0 && devs[q] < count, "device %d requested but only %d visible", devs[q], count);
+        for (int r = 0; r < q; ++r) QGSB_REQUIRE(devs[r] != devs[q], "device %d listed twice", devs[q]);
+    }
+    init_devices(devs);
+    QGSB_API_END
+}
+
+int qgsb_device_count(void)
+{
+    QGSB_API_LOCK
+    return g_slots;
 }
 
 void qgsb_shutdown(void)
 {
     QGSB_API_LOCK
-    Context &c = ctx();
-    if (!c.ready) return;
-    cudaSetDevice(c.device);
-    cudaStreamSynchronize(c.stream);
-    pool_trim();
-    cudaStreamDestroy(c.own_stream);
-    cudaStreamDestroy(c.copy_in);
-    cudaStreamDestroy(c.copy_out);
-    c.copy_in = c.copy_out = nullptr;
-    cudaEventDestroy(c.ev0);
-    cudaEventDestroy(c.ev1);
-    c.own_stream = c.stream = nullptr;
-    c.ready = false;
+    close_all();
 }
 
 int qgsb_set_stream(void *cuda_stream)
@@ -571,22 +708,26 @@ int qgsb_load_plugin(const char *path)
     entry_fn entry = (entry_fn)dlsym(h, "qgsb_plugin_kernels");
     QGSB_REQUIRE(entry != nullptr, "%s does not export qgsb_plugin_kernels", path);
     const SpecKernels *k = entry();
-    QGSB_REQUIRE(k != nullptr && (k->rk_chain != nullptr || k->tangent != nullptr), "%s returned an empty kernel table",
+    QGSB_REQUIRE(k != nullptr, "%s returned no kernel table", path);
+    QGSB_REQUIRE(k->abi == QGSB_SPEC_ABI,
+                 "%s was built against kernel-table layout %u, this library uses %u: delete it (it is a cache) and let "
+                 "qgs_b200.codegen rebuild it", path, k->abi, (unsigned)QGSB_SPEC_ABI);
+    QGSB_REQUIRE((k->rk_chain != nullptr || k->tangent != nullptr), "%s returned an empty kernel table",
                  path);
     register_spec(k);
     QGSB_API_END
 }
 
-int qgsb_tensor_create(int ndim, int rank, long nnz, const int32_t *coo, const double *val, long jnnz,
-                       const int32_t *jcoo, const double *jval, qgsb_tensor **out)
+}  // extern "C"
+
+// builds a handle on the calling thread's device
+static qgsb_tensor *tensor_build(int ndim, int rank, long nnz, const int32_t *coo, const double *val, long jnnz,
+                                 const int32_t *jcoo, const double *jval)
 {
-    QGSB_API_BEGIN
-    QGSB_REQUIRE(out != nullptr, "null output handle");
-    QGSB_REQUIRE(ndim >= 1, "ndim must be positive");
-    ensure_init();
     HostTensor h = prepare_vec(ndim + 1, rank, nnz, coo, val);
     HostJac j = prepare_mat(ndim + 1, rank, jnnz, jcoo, jval, false);
     qgsb_tensor *t = new qgsb_tensor();
+    t->device = ctx().device;
     try {
         to_device(t->d_ent, h.ent);
         to_device(t->d_row_ptr, h.row_ptr);
@@ -628,6 +769,53 @@ int qgsb_tensor_create(int ndim, int rank, long nnz, const int32_t *coo, const d
     t->h_jent = j.ent;
     t->h_pos_ptr = j.pos_ptr;
     t->jac_matches_spec = jacobian_matches(t);
+    return t;
+}
+
+namespace qgsb {
+
+// The handle the calling thread's device works with: the caller's handle on its own device, else a replica built on
+// first use from the arrays the handle was created from (a few hundred KB; SURVEY.md section 8e: "tensor replicated
+// to every GPU").  Replicas follow the handle's specialisation switches and die with it.
+const qgsb_tensor *tensor_here(const qgsb_tensor *t)
+{
+    const int device = ctx().device;
+    if (t->device == device) return t;
+    std::lock_guard<std::mutex> guard(t->replica_mutex);
+    auto it = t->replicas.find(device);
+    if (it == t->replicas.end()) {
+        qgsb_tensor *r = tensor_build(t->ndim_in, t->view.rank, t->nnz_in, t->in_coo.data(), t->in_val.data(), t->jnnz_in,
+                                      t->in_jcoo.data(), t->in_jval.data());
+        it = t->replicas.emplace(device, r).first;
+    }
+    qgsb_tensor *r = it->second;
+    r->use_spec = t->use_spec;
+    if (r->spec != t->spec) {          // a module was loaded after the replica was made
+        r->spec = t->spec;
+        r->jac_matches_spec = t->jac_matches_spec;
+    }
+    return r;
+}
+
+}  // namespace qgsb
+
+extern "C" {
+
+int qgsb_tensor_create(int ndim, int rank, long nnz, const int32_t *coo, const double *val, long jnnz,
+                       const int32_t *jcoo, const double *jval, qgsb_tensor **out)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(out != nullptr, "null output handle");
+    QGSB_REQUIRE(ndim >= 1, "ndim must be positive");
+    ensure_init();
+    qgsb_tensor *t = tensor_build(ndim, rank, nnz, coo, val, jnnz, jcoo, jval);
+    t->ndim_in = ndim;
+    t->in_coo.assign(coo, coo + (size_t)nnz * rank);
+    t->in_val.assign(val, val + nnz);
+    if (jnnz > 0) {
+        t->in_jcoo.assign(jcoo, jcoo + (size_t)jnnz * rank);
+        t->in_jval.assign(jval, jval + jnnz);
+    }
     *out = t;
     QGSB_API_END
 }
@@ -645,8 +833,8 @@ void qgsb_tensor_destroy(qgsb_tensor *t)
 {
     if (!t) return;
     QGSB_API_LOCK
-    if (ctx().ready) cudaSetDevice(ctx().device);
-    delete t;
+    delete t;       // replicas included; every array is freed on its own device
+    if (g_slots > 0 && g_ctx[0].ready) cudaSetDevice(g_ctx[0].device);
 }
 
 int qgsb_tensor_info(const qgsb_tensor *t, int *ndim, int *rank, long *nnz, long *jnnz, int *kernel_kind,

@@ -295,13 +295,15 @@ __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __
     const size_t sbase = P.stored ? tile_base(member, n) : 0;
     long iw = 0;
     for (int c = tid; c < m; c += TG_THREADS) S.mexp[c] = 0.;
-    for (long step = 0; step < steps; ++step) {
-        if (P.stored) {                                                   // lyapunov.py:513 / :527
+    // step -1 (P.qr_at_start): only factorise the start matrix drawn on the device (lyapunov.py:592-593)
+    for (long step = P.qr_at_start ? -1 : 0; step < steps; ++step) {
+        const bool real = step >= 0;
+        if (real && P.stored) {                                           // lyapunov.py:513 / :527
             const double *src = P.stored + (size_t)P.start_idx[step] * n * P.stored_ld + sbase;
             for (int r = tid; r < n; r += TG_THREADS) S.Y[r] = src[(size_t)r * TILE];
             __syncthreads();
         }
-        if (step >= P.n_pre) {
+        if (real && step >= P.n_pre) {
             const long ti = step - P.n_pre;
             for (int c = tid; c < m; c += TG_THREADS) S.mexp[c] = log(fabs(S.rdiag[c])) / P.dt_macro[step];   // :611 / :531
             if (P.q_all) {
@@ -321,11 +323,14 @@ __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __
             }
         }
         // propagate the basis over the micro steps starting from the stored point (:598-600)
-        for (int r = tid; r < n; r += TG_THREADS) S.y[r] = S.Y[r];
-        __syncthreads();
-        for (long q = P.sub_ptr[step]; q < P.sub_ptr[step + 1]; ++q) tg_step<RANK>(T, P, S, P.sub_dt[q]);
+        if (real) {
+            for (int r = tid; r < n; r += TG_THREADS) S.y[r] = S.Y[r];
+            __syncthreads();
+            for (long q = P.sub_ptr[step]; q < P.sub_ptr[step + 1]; ++q) tg_step<RANK>(T, P, S, P.sub_dt[q]);
+        }
         // q_new = prop @ q ; q, r = qr(q_new)   (:602-604) -- fm already holds prop @ q by linearity
-        block_qr(n, m, S.fm, S.kms, S.rdiag, S.red, (P.r_all && step >= P.r_first) ? P.r_all + ((size_t)member * (steps - P.r_first) + (step - P.r_first)) * m * m : nullptr);
+        block_qr(n, m, S.fm, S.kms, S.rdiag, S.red, (real && P.r_all && step >= P.r_first) ? P.r_all + ((size_t)member * (steps - P.r_first) + (step - P.r_first)) * m * m : nullptr);
+        if (!real) continue;
         // next point of the stored trajectory (:601 / :622): one nonlinear step of length dt_macro
         if (P.forward == 2) {
             // Ginelli forward pass (lyapunov.py:1212-1218): the trajectory follows the micro-steps
@@ -568,29 +573,17 @@ using namespace qgsb;
 
 extern "C" {
 
-int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long N, const double *ic, int m, const double *tg_ic, long n_steps,
-                           const double *dt, int s, const double *a, const double *b, const double *c,
-                           long write_steps, int time_direction, int adjoint, double inverse_sign, long R,
-                           double *traj, double *fmat, double *device_ms)
+// one device's share of qgsb_rk_tgls_integrate
+static void tgls_integrate_device(const qgsb_tensor *t, long N, const double *ic, int m, const double *tg_ic,
+                                  long n_steps, const double *dt, int s, const double *a, const double *b,
+                                  long write_steps, int time_direction, int adjoint, double inverse_sign, long R,
+                                  double *traj, double *fmat, double *device_ms)
 {
-    (void)c;
-    QGSB_API_BEGIN
-    QGSB_REQUIRE(t && ic && tg_ic && traj && fmat, "null argument");
-    QGSB_REQUIRE(N >= 1 && m >= 1, "need at least one trajectory and one tangent vector");
-    QGSB_REQUIRE(n_steps >= 0 && write_steps >= 0, "negative step count");
-    QGSB_REQUIRE(t->jnnz_in > 0, "tensor handle has no Jacobian tensor");
-    QGSB_REQUIRE(time_direction == 1 || time_direction == -1, "time_direction must be +1 or -1");
-    ensure_init();
     Context &cx = ctx();
     cudaStream_t st = cx.stream;
     const Tableau tab = make_tableau(s, a, b);
     const int n = t->view.n;
     const size_t nm = (size_t)n * m;
-    {
-        long L = n_steps + 1, r = write_steps == 0 ? 1 : (L + write_steps - 1) / write_steps;
-        if (write_steps > 0 && (r - 1) * write_steps != L - 1) r += 1;
-        QGSB_REQUIRE(R == r, "n_records %ld inconsistent with %ld steps / write_steps %ld", R, n_steps, write_steps);
-    }
     PoolBuf<double> d_y((size_t)N * n), d_fm((size_t)N * nm), d_dt(std::max<long>(n_steps, 1));
     PoolBuf<double> d_ry((size_t)R * N * n), d_rf((size_t)R * N * nm), d_oy((size_t)R * N * n), d_of((size_t)R * N * nm);
     DevBuf<double> scratch;
@@ -633,45 +626,115 @@ int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long N, const double *ic, int m
         QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
         *device_ms = ms;
     }
-    QGSB_API_END
 }
 
-int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forward, int n_vec, const double *q0,
-                       const double *r0, long n_pre, long n_rec, const double *dt_macro, const long *sub_ptr,
-                       const double *sub_dt, int s, const double *a, const double *b, const double *c,
-                       long write_steps, int adjoint, double inverse_sign, long R, double *rec_traj,
-                       double *rec_exp, double *rec_vec, double *r_all, double *q_all, double *device_ms)
+// records kept on the device by one tangent / Benettin launch: bounded so that a long write_steps = 1 run is cut
+// into member batches instead of failing in cudaMalloc (the reference keeps such runs in host RAM)
+static long tangent_member_batch(long N, size_t bytes_per_member)
+{
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return N;
+    size_t budget = free_b / 2;
+    if (const char *env = getenv("QGSB_TANGENT_BUDGET_MB")) budget = (size_t)atol(env) << 20;   // tests
+    const long fit = (long)std::max<size_t>(1, budget / std::max<size_t>(bytes_per_member, 1));
+    return std::min(N, fit);
+}
+
+int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long N, const double *ic, int m, const double *tg_ic, long n_steps,
+                           const double *dt, int s, const double *a, const double *b, const double *c,
+                           long write_steps, int time_direction, int adjoint, double inverse_sign, long R,
+                           double *traj, double *fmat, double *device_ms)
 {
     (void)c;
     QGSB_API_BEGIN
-    QGSB_REQUIRE(t && ic && q0 && dt_macro && sub_ptr && sub_dt && rec_traj && rec_exp, "null argument");
-    QGSB_REQUIRE(N >= 1, "need at least one trajectory");
-    QGSB_REQUIRE(forward >= 0 && forward <= 2, "mode must be 0 (BLV), 1 (FLV) or 2 (BLV following the micro-steps)");
-    QGSB_REQUIRE(n_vec >= 1 && n_vec <= t->view.n, "n_vec must be in 1..n_dim");
-    QGSB_REQUIRE(n_pre >= 0 && n_rec >= 0 && write_steps >= 0, "negative step count");
+    QGSB_REQUIRE(t && ic && tg_ic && traj && fmat, "null argument");
+    QGSB_REQUIRE(N >= 1 && m >= 1, "need at least one trajectory and one tangent vector");
+    QGSB_REQUIRE(n_steps >= 0 && write_steps >= 0, "negative step count");
     QGSB_REQUIRE(t->jnnz_in > 0, "tensor handle has no Jacobian tensor");
+    QGSB_REQUIRE(time_direction == 1 || time_direction == -1, "time_direction must be +1 or -1");
     ensure_init();
+    const int n = t->view.n;
+    const size_t nm = (size_t)n * m;
+    {
+        long L = n_steps + 1, r = write_steps == 0 ? 1 : (L + write_steps - 1) / write_steps;
+        if (write_steps > 0 && (r - 1) * write_steps != L - 1) r += 1;
+        QGSB_REQUIRE(R == r, "n_records %ld inconsistent with %ld steps / write_steps %ld", R, n_steps, write_steps);
+    }
+    const int parts = shard_count(N, 1024);
+    std::vector<double> ms(parts, 0.);
+    run_sharded(N, parts, [&](int g, long lo, long hi) {
+        const qgsb_tensor *th = tensor_here(t);
+        // member batches sized to the device memory: records (R, batch, n + n m) twice (kernel order + API order)
+        const long batch = tangent_member_batch(hi - lo, (size_t)(2 * R + 1) * (n + nm) * sizeof(double));
+        for (long m0 = lo; m0 < hi; m0 += batch) {
+            const long nb = std::min(batch, hi - m0);
+            double part_ms = 0.;
+            tgls_integrate_device(th, nb, ic + (size_t)m0 * n, m, tg_ic + (size_t)m0 * nm, n_steps, dt, s, a, b,
+                                  write_steps, time_direction, adjoint, inverse_sign, R, traj + (size_t)m0 * n * R,
+                                  fmat + (size_t)m0 * nm * R, &part_ms);
+            ms[g] += part_ms;
+        }
+    });
+    if (device_ms) *device_ms = *std::max_element(ms.begin(), ms.end());
+    QGSB_API_END
+}
+
+// ---- start bases drawn on the device ------------------------------------------------------------------------------
+// The reference draws qr(random((n_dim, n_vec))) per member from numba's generator (lyapunov.py:592-593).  With
+// q0 == NULL the same is done here without host work: a counter-based generator (splitmix64 of seed, GLOBAL member
+// index and element index -- so a member's draw does not depend on how the ensemble is split over devices or batches)
+// fills the matrices with uniform [0, 1) numbers and the Benettin kernel factorises them with its own Householder QR
+// before the first step (TgParams::qr_at_start).
+static uint64_t g_seed = 0x243F6A8885A308D3ULL;
+static long g_member_offset = 0;
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+__global__ void random_basis_kernel(double *__restrict__ q, long n_members, long per_member, long member0, uint64_t seed)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_members * per_member) return;
+    const long member = idx / per_member, e = idx - member * per_member;
+    const uint64_t h = splitmix64(splitmix64(seed ^ splitmix64((uint64_t)(member0 + member))) + (uint64_t)e);
+    q[idx] = (double)(h >> 11) * (1. / 9007199254740992.);     // 53 random bits -> [0, 1)
+}
+
+// one device's share of qgsb_lyap_benettin; member0 = index of the first member in the whole ensemble
+static void benettin_device(const qgsb_tensor *t, long N, long member0, const double *ic, int forward, int n_vec,
+                            const double *q0, const double *r0, long n_pre, long n_rec, const double *dt_macro,
+                            const long *sub_ptr, const double *sub_dt, int s, const double *a, const double *b,
+                            long write_steps, int adjoint, double inverse_sign, long R, double *rec_traj,
+                            double *rec_exp, double *rec_vec, double *r_all, double *q_all, double *device_ms)
+{
     Context &cx = ctx();
     cudaStream_t st = cx.stream;
     const Tableau tab = make_tableau(s, a, b);
     const int n = t->view.n, m = n_vec;
     const size_t nm = (size_t)n * m;
     const long steps = n_pre + n_rec;
-    {
-        long L = n_rec + 1, r = write_steps == 0 ? 1 : (L + write_steps - 1) / write_steps;
-        if (write_steps > 0 && (r - 1) * write_steps != L - 1) r += 1;
-        QGSB_REQUIRE(R == r, "n_records %ld inconsistent with %ld recorded steps / write_steps %ld", R, n_rec,
-                     write_steps);
-    }
     const long n_sub = sub_ptr[steps];
-    DevBuf<double> d_y((size_t)N * n), d_q((size_t)N * nm), d_dtm(std::max<long>(steps, 1)), d_sub(std::max<long>(n_sub, 1));
-    DevBuf<long> d_ptr(steps + 1), d_idx(std::max<long>(steps, 1));
+    PoolBuf<double> d_y((size_t)N * n), d_q((size_t)N * nm), d_dtm(std::max<long>(steps, 1)), d_sub(std::max<long>(n_sub, 1));
+    PoolBuf<long> d_ptr(steps + 1), d_idx(std::max<long>(steps, 1));
     DevBuf<double> d_r0, d_rall, d_qall, d_stored, d_ys, scratch;
     // rec_vec == NULL: the vectors are not recorded (spectrum-only runs skip 8 n m bytes per member and record)
-    DevBuf<double> d_ry((size_t)R * N * n), d_rv(rec_vec ? (size_t)R * N * nm : 0), d_re((size_t)R * N * m);
-    DevBuf<double> d_oy((size_t)R * N * n), d_ov(rec_vec ? (size_t)R * N * nm : 0), d_oe((size_t)R * N * m);
+    PoolBuf<double> d_ry((size_t)R * N * n), d_rv(rec_vec ? (size_t)R * N * nm : 0), d_re((size_t)R * N * m);
+    PoolBuf<double> d_oy((size_t)R * N * n), d_ov(rec_vec ? (size_t)R * N * nm : 0), d_oe((size_t)R * N * m);
     d_y.upload(ic, (size_t)N * n, st);
-    d_q.upload(q0, (size_t)N * nm, st);
+    if (q0) {
+        d_q.upload(q0, (size_t)N * nm, st);
+    } else {
+        const long total = N * (long)nm;
+        random_basis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_q.p, N, (long)nm, g_member_offset + member0,
+                                                                             g_seed);
+        count_launch();
+        QGSB_CUDA(cudaGetLastError());
+    }
     if (steps) d_dtm.upload(dt_macro, steps, st);
     if (n_sub) d_sub.upload(sub_dt, n_sub, st);
     QGSB_CUDA(cudaMemcpyAsync(d_ptr.p, sub_ptr, sizeof(long) * (steps + 1), cudaMemcpyHostToDevice, st));
@@ -690,7 +753,8 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
     P.rec_y = d_ry.p;
     P.rec_fm = rec_vec ? d_rv.p : nullptr;
     P.rec_exp = d_re.p;
-    if (r0) {
+    P.qr_at_start = q0 ? 0 : 1;
+    if (r0 && q0) {
         d_r0.alloc((size_t)N * m * m);
         d_r0.upload(r0, (size_t)N * m * m, st);
         P.r0 = d_r0.p;
@@ -743,6 +807,65 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
         QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
         *device_ms = ms;
     }
+}
+
+int qgsb_set_seed(uint64_t seed, long member_offset)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(member_offset >= 0, "negative member offset");
+    g_seed = seed;
+    g_member_offset = member_offset;
+    QGSB_API_END
+}
+
+int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forward, int n_vec, const double *q0,
+                       const double *r0, long n_pre, long n_rec, const double *dt_macro, const long *sub_ptr,
+                       const double *sub_dt, int s, const double *a, const double *b, const double *c,
+                       long write_steps, int adjoint, double inverse_sign, long R, double *rec_traj,
+                       double *rec_exp, double *rec_vec, double *r_all, double *q_all, double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t && ic && dt_macro && sub_ptr && sub_dt && rec_traj && rec_exp, "null argument");
+    QGSB_REQUIRE(N >= 1, "need at least one trajectory");
+    QGSB_REQUIRE(forward >= 0 && forward <= 2, "mode must be 0 (BLV), 1 (FLV) or 2 (BLV following the micro-steps)");
+    QGSB_REQUIRE(n_vec >= 1 && n_vec <= t->view.n, "n_vec must be in 1..n_dim");
+    QGSB_REQUIRE(n_pre >= 0 && n_rec >= 0 && write_steps >= 0, "negative step count");
+    QGSB_REQUIRE(t->jnnz_in > 0, "tensor handle has no Jacobian tensor");
+    ensure_init();
+    const int n = t->view.n, m = n_vec;
+    const size_t nm = (size_t)n * m;
+    const long steps = n_pre + n_rec;
+    {
+        long L = n_rec + 1, r = write_steps == 0 ? 1 : (L + write_steps - 1) / write_steps;
+        if (write_steps > 0 && (r - 1) * write_steps != L - 1) r += 1;
+        QGSB_REQUIRE(R == r, "n_records %ld inconsistent with %ld recorded steps / write_steps %ld", R, n_rec,
+                     write_steps);
+    }
+    // bytes one member keeps on the device during the launch: records in kernel and API order, plus the optional
+    // stored trajectory (FLV), R factors and bases (Ginelli)
+    const size_t per_member = sizeof(double) * ((size_t)2 * R * (n + m + (rec_vec ? nm : 0)) + n + nm +
+                                                (forward == 1 ? (size_t)(steps + 1) * n : 0) +
+                                                (r_all ? (size_t)std::max<long>(steps, 1) * m * m : 0) +
+                                                (q_all ? (size_t)(n_rec + 1) * nm : 0));
+    const int parts = shard_count(N, 1024);
+    std::vector<double> ms(parts, 0.);
+    run_sharded(N, parts, [&](int g, long lo, long hi) {
+        const qgsb_tensor *th = tensor_here(t);
+        const long batch = tangent_member_batch(hi - lo, per_member);
+        for (long m0 = lo; m0 < hi; m0 += batch) {
+            const long nb = std::min(batch, hi - m0);
+            double part_ms = 0.;
+            benettin_device(th, nb, m0, ic + (size_t)m0 * n, forward, n_vec, q0 ? q0 + (size_t)m0 * nm : nullptr,
+                            r0 ? r0 + (size_t)m0 * m * m : nullptr, n_pre, n_rec, dt_macro, sub_ptr, sub_dt, s, a, b,
+                            write_steps, adjoint, inverse_sign, R, rec_traj + (size_t)m0 * n * R,
+                            rec_exp + (size_t)m0 * m * R, rec_vec ? rec_vec + (size_t)m0 * nm * R : nullptr,
+                            r_all ? r_all + (size_t)m0 * steps * m * m : nullptr,
+                            q_all ? q_all + (size_t)m0 * (n_rec + 1) * nm : nullptr, &part_ms);
+            ms[g] += part_ms;
+        }
+    });
+    if (device_ms) *device_ms = *std::max_element(ms.begin(), ms.end());
     QGSB_API_END
 }
 

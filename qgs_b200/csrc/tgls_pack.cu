@@ -63,6 +63,13 @@ struct qgsb_tensor::PackCache {
 
 qgsb_tensor::~qgsb_tensor()
 {
+    // replicas first: each frees its arrays on its own device
+    for (auto &kv : replicas) {
+        cudaSetDevice(kv.first);
+        delete kv.second;
+    }
+    replicas.clear();
+    cudaSetDevice(device);
     delete pack_cache[0];
     delete pack_cache[1];
     qgsb::g3_release(g3_cache);

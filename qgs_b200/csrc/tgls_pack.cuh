@@ -61,7 +61,8 @@ struct Carve {
     __host__ __device__ int o_rdiag() const { return o_yacc() + even(N); }
     __host__ __device__ int o_tau() const { return o_rdiag() + mp; }
     __host__ __device__ int o_scal() const { return o_tau() + mp; }
-    __host__ __device__ int o_fm() const { return o_scal() + mp; }
+    __host__ __device__ int o_flag() const { return o_scal() + mp; }           // 2 doubles: progress counter of qr_async
+    __host__ __device__ int o_fm() const { return o_flag() + 2; }
     __host__ __device__ int o_facc() const { return o_fm() + nm; }
     __host__ __device__ int total() const
     {
@@ -76,6 +77,7 @@ struct Carve {
 template <int N>
 struct Mem {
     double *jv, *xs, *xs2, *y, *Y, *kst, *yacc, *rdiag, *tau, *scal, *fm, *facc;
+    int *flag;
     int m;
 };
 
@@ -94,6 +96,7 @@ __device__ __forceinline__ Mem<N> carve(double *base, int jv, int m)
     S.rdiag = base + c.o_rdiag();
     S.tau = base + c.o_tau();
     S.scal = base + c.o_scal();
+    S.flag = reinterpret_cast<int *>(base + c.o_flag());
     S.fm = base + c.o_fm();
     S.facc = base + c.o_facc();
     S.m = m;
@@ -619,6 +622,131 @@ __device__ __forceinline__ void qr_rolled(const Mem<N> &S, int c, bool live, dou
     }
 }
 
+// ---- the same factorisation PIPELINED: flags instead of block barriers ------------------------------------------------
+// qr / qr_rolled march all warps of the block through the reflectors in lockstep: publish, __syncthreads, consume --
+// 36 times per step, and between two barriers every warp walks the same latency chain (broadcast loads -> dot
+// products -> square root -> reciprocals -> update -> publish), so the FP64 pipe idles most of the time (ncu, round 1:
+// barrier + wait are the top stalls of this phase, 31 % of the samples for 20 % of the instructions).  Here a column's
+// owner publishes its reflector and bumps the member's progress counter in shared memory; a consumer waits only for
+// the counter of ITS member to pass j.  With the columns dealt member-index-fastest a warp holds a few consecutive
+// columns of all members: the chain of owners runs through one warp at a time while the other warps apply the
+// reflectors already published to their own columns at their own pace, and a warp whose columns are all finished
+// leaves the loop.  Same arithmetic as qr_rolled (reflector groups, masked rows).
+template <int N, int JB, int JE>
+__device__ __forceinline__ void qr_factor_group_async(const Mem<N> &S, int c, bool live, double (&col)[N], double *Rout)
+{
+    constexpr int RB = JB & ~1;
+    constexpr int NP = (N - RB) / 2;
+    const int m = S.m;
+    double *V = S.facc;
+    volatile int *pub = S.flag;
+    const int jend = JE < m ? JE : m;
+#pragma unroll 1
+    for (int j = JB; j < jend; ++j) {
+        const bool part = live && c >= j;
+        if (!__any_sync(0xffffffffu, part)) break;         // every column of this warp is finished (c only matters >= j)
+        double *x = V + j * N;
+        if (part && c == j) {
+#pragma unroll
+            for (int i = RB; i < N; i += 2) *reinterpret_cast<double2 *>(x + i) = make_double2(col[i], col[i + 1]);
+            __threadfence_block();
+            *pub = j + 1;
+        }
+        __syncwarp();
+        if (part) {
+            if (c != j) {
+                while (*pub <= j) {
+                }
+                __threadfence_block();
+            }
+            double2 xr[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int i = RB + 2 * q;
+                xr[q] = *reinterpret_cast<const double2 *>(x + i);
+                if (i < JE) {                                  // rows that can be <= j in this group
+                    if (i <= j) xr[q].x = 0.;
+                    if (i + 1 <= j) xr[q].y = 0.;
+                }
+            }
+            double d0 = 0., d1 = 0., d2 = 0., d3 = 0., n0 = 0., n1 = 0., n2 = 0., n3 = 0.;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int i = RB + 2 * q;
+                if (q & 1) {
+                    d0 = fma(xr[q].x, col[i], d0);
+                    n0 = fma(xr[q].x, xr[q].x, n0);
+                    d1 = fma(xr[q].y, col[i + 1], d1);
+                    n1 = fma(xr[q].y, xr[q].y, n1);
+                } else {
+                    d2 = fma(xr[q].x, col[i], d2);
+                    n2 = fma(xr[q].x, xr[q].x, n2);
+                    d3 = fma(xr[q].y, col[i + 1], d3);
+                    n3 = fma(xr[q].y, xr[q].y, n3);
+                }
+            }
+            const double alpha = x[j];
+            const double nrm2 = (n0 + n1) + (n2 + n3), dot = (d0 + d1) + (d2 + d3);
+            double beta = alpha, tau = 0., scal = 0.;
+            if (nrm2 != 0.) {
+                beta = -copysign(sqrt(fma(alpha, alpha, nrm2)), alpha);
+                tau = (beta - alpha) * fast_rcp(beta);
+                scal = fast_rcp(alpha - beta);
+            }
+            double cj = 0.;
+#pragma unroll
+            for (int i = JB; i < JE; ++i)
+                if (i == j) cj = col[i];
+            if (c == j) {
+                cj = beta;
+                S.rdiag[j] = beta;
+                S.tau[j] = tau;
+                S.scal[j] = scal;
+            } else {
+                const double w = tau * fma(dot, scal, cj);
+                cj -= w;
+                const double ws = -(w * scal);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const int i = RB + 2 * q;
+                    col[i] = fma(ws, xr[q].x, col[i]);
+                    col[i + 1] = fma(ws, xr[q].y, col[i + 1]);
+                }
+            }
+#pragma unroll
+            for (int i = JB; i < JE; ++i)
+                if (i == j) col[i] = cj;
+            if (Rout != nullptr) Rout[j * m + c] = cj;
+        }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void qr_async(const Mem<N> &S, int c, bool live, double (&col)[N], double *Rout)
+{
+    static_assert(N % 2 == 0, "rows are processed in aligned pairs");
+    constexpr int B1 = (N / 3) & ~1, B2 = (2 * N / 3) & ~1;
+    const int m = S.m;
+    if (live && c == 0) *S.flag = 0;
+    __syncthreads();                       // every thread is done with its private facc column; counters are reset
+    qr_factor_group_async<N, 0, B1>(S, c, live, col, Rout);
+    qr_factor_group_async<N, B1, B2>(S, c, live, col, Rout);
+    qr_factor_group_async<N, B2, N>(S, c, live, col, Rout);
+    if (Rout != nullptr && live)
+        for (int i = c + 1; i < m; ++i) Rout[i * m + c] = 0.;   // strictly lower part of column c
+    __syncthreads();                       // every reflector, tau and scal are published
+#pragma unroll
+    for (int i = 0; i < N; ++i) col[i] = i == c ? 1. : 0.;
+    qr_formq_group<N, B2, N>(S, c, live, col);
+    qr_formq_group<N, B1, B2>(S, c, live, col);
+    qr_formq_group<N, 0, B1>(S, c, live, col);
+    if (live) {
+        double *fmc = S.fm + c;
+#pragma unroll
+        for (int i = 0; i < N; ++i) fmc[i * m] = col[i];
+    }
+}
+
 template <int N, class Prod>
 __device__ __forceinline__ void init_member(const Mem<N> &S, int c, bool live)
 {
@@ -690,7 +818,9 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
 }
 
 // ---- Benettin loop (lyapunov.py:471-632) ---------------------------------------------------------------------------------
-template <int N, class Prod, bool ROLLED>
+// QRM: the re-orthonormalisation -- 0 unrolled with a block barrier per reflector (qr), 1 rolled (qr_rolled),
+// 2 pipelined: rolled, flags instead of barriers (qr_async)
+template <int N, class Prod, int QRM>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride, int qr_remap)
 {
@@ -727,16 +857,19 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
     const size_t sbase = (P.stored && live) ? tile_base(member, N) : 0;
     long iw = 0;
     double mexp = 0.;
+    // step -1 (P.qr_at_start): the start matrix was drawn on the device and is only factorised here -- the
+    // reference's q, r = qr(random((n_dim, n_vec))) of lyapunov.py:592-593 -- without duplicating the QR code
 #pragma unroll 1
-    for (long step = 0; step < steps; ++step) {
-        if (P.stored) {                                                   // lyapunov.py:513 / :527
+    for (long step = P.qr_at_start ? -1 : 0; step < steps; ++step) {
+        const bool real = step >= 0;
+        if (real && P.stored) {                                           // lyapunov.py:513 / :527
             if (live) {
                 const double *src = P.stored + (size_t)P.start_idx[step] * N * P.stored_ld + sbase;
                 for (int r = c; r < N; r += m) S.Y[r] = src[(size_t)r * TILE];
             }
             __syncthreads();
         }
-        if (step >= P.n_pre) {
+        if (real && step >= P.n_pre) {
             const long ti = step - P.n_pre;
             if (live) mexp = log(fabs(S.rdiag[c])) / P.dt_macro[step];   // :611 / :531
             if (P.q_all && live) {
@@ -761,13 +894,17 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
             }
         }
         // propagate the basis over the micro steps starting from the stored point (:598-600)
-        if (live)
-            for (int r = c; r < N; r += m) S.y[r] = S.Y[r];
-        const long q0 = P.sub_ptr[step], q1 = P.sub_ptr[step + 1];
-        for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, tab, P, S, P.sub_dt[q], col, c, live);
+        long q0 = 0, q1 = 0;
+        if (real) {
+            if (live)
+                for (int r = c; r < N; r += m) S.y[r] = S.Y[r];
+            q0 = P.sub_ptr[step];
+            q1 = P.sub_ptr[step + 1];
+            for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, tab, P, S, P.sub_dt[q], col, c, live);
+        }
         // q, r = qr(prop @ q)   (:602-604)
         {
-            double *Rout = (P.r_all && liveq && step >= P.r_first)
+            double *Rout = (real && P.r_all && liveq && step >= P.r_first)
                                ? P.r_all + ((size_t)memberq * (steps - P.r_first) + (step - P.r_first)) * m * m : nullptr;
             if (remap) {                     // hand the columns over through the fm area (tangent_step left them there)
                 __syncthreads();
@@ -776,7 +913,9 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
                     for (int i = 0; i < N; ++i) col[i] = Sq.fm[i * m + cq];
                 }
             }
-            if (ROLLED)
+            if (QRM == 2)
+                qr_async<N>(Sq, cq, liveq, col, Rout);
+            else if (QRM == 1)
                 qr_rolled<N>(Sq, cq, liveq, col, Rout);
             else
                 qr<N>(Sq, cq, liveq, col, Rout);
@@ -788,6 +927,7 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
                 }
             }
         }
+        if (!real) continue;
         if (P.forward == 2 || (!P.stored && q1 - q0 == 1 && P.sub_dt[q0] == P.dt_macro[step])) {
             // Ginelli forward pass follows the micro steps; and with a single micro step of the macro length the
             // "stored" trajectory point (:601 / :622) is bit-for-bit the state the tangent step just produced
@@ -881,12 +1021,13 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
         return cudaGetLastError();
     };
     if (lyap) {
-        // few vectors: the rolled factorisation (one resident loop body instead of n_vec unrolled reflectors) is faster
-        // [B200: MAOOAM-36, 10 vectors +12 %; 36 vectors -9 %]; QGSB_QR_ROLLED=0/1 forces one of them
-        const char *env = getenv("QGSB_QR_ROLLED");
-        const bool rolled = env ? (env[0] != '0') : (3 * P.m <= N);
-        if (rolled) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, true>) : go_lyap(lyap_kernel<N, Fwd, true>);
-        return P.adjoint ? go_lyap(lyap_kernel<N, Adj, false>) : go_lyap(lyap_kernel<N, Fwd, false>);
+        // QGSB_QR_MODE = 0 (unrolled, a block barrier per reflector) | 1 (rolled) | 2 (pipelined, the default);
+        // see the comments at qr / qr_rolled / qr_async and profiles/ for the A/B measurements
+        const char *env = getenv("QGSB_QR_MODE");
+        const int mode = env ? atoi(env) : 2;
+        if (mode == 2) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 2>) : go_lyap(lyap_kernel<N, Fwd, 2>);
+        if (mode == 1) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 1>) : go_lyap(lyap_kernel<N, Fwd, 1>);
+        return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 0>) : go_lyap(lyap_kernel<N, Fwd, 0>);
     }
     return P.adjoint ? go(tgls_kernel<N, Adj>) : go(tgls_kernel<N, Fwd>);
 }

@@ -39,6 +39,7 @@ struct TgParams {
     double *r_all;            // (N, steps - r_first, m, m) or null: R of every step >= r_first
     long r_first;
     double *q_all;            // (N, n_rec + 1, n, m) or null
+    int qr_at_start;          // != 0: fm holds a raw start matrix; factorise it before the first step (lyapunov.py:592-593)
     // --- placement of the big matrices ---
     double *scratch;          // global scratch when shared memory is too small, else null
     size_t scratch_per_member;

@@ -24,13 +24,13 @@ from qgs_b200.integrators.integrate import directed_dt, rk4_tableau, tensor_of
 
 
 def shard_bounds(n_traj, world_size, rank):
-    """Contiguous partition of the members: rank ``g`` gets ``[g * ceil(N/G), min(N, (g+1) * ceil(N/G)))``."""
+    """Balanced contiguous partition of the members: rank ``g`` gets ``[g * N // G, (g + 1) * N // G)`` -- block sizes
+    differ by at most one and no rank is left empty when ``N >= G`` (the library's own split across the devices of
+    one process, ``qgsb::shard_range``, is the same rule)."""
     if world_size < 1 or not 0 <= rank < world_size:
         raise ValueError("bad rank %d / world size %d" % (rank, world_size))
-    per = -(-int(n_traj) // world_size)
-    lo = min(rank * per, n_traj)
-    hi = min(lo + per, n_traj)
-    return lo, hi
+    n_traj = int(n_traj)
+    return rank * n_traj // world_size, (rank + 1) * n_traj // world_size
 
 
 def _dist():
@@ -94,10 +94,13 @@ class DeviceEnsemble(object):
         self.lo, self.hi = 0, ic.shape[0]
         dist = _dist()
         if sharded and dist is not None:
+            # the same test on every rank, before anything collective: no rank may go on alone into an all-reduce
+            if ic.shape[0] < dist.get_world_size():
+                raise ValueError("%d members cannot be sharded over %d ranks" % (ic.shape[0], dist.get_world_size()))
             self.lo, self.hi = shard_bounds(ic.shape[0], dist.get_world_size(), dist.get_rank())
         local = _lib.f64(ic[self.lo:self.hi])
         if local.shape[0] == 0:
-            raise ValueError("this rank received no members (fewer members than ranks)")
+            raise ValueError("an ensemble needs at least one member")
         self.n_traj = local.shape[0]
         self.n_dim = self.tensor.ndim
         self.time = 0.
@@ -252,13 +255,13 @@ def sharded_lyapunov_spectrum(f, Df, ic, t0, tw, t, dt, mdt, n_vec=None, write_s
     ic = np.atleast_2d(np.asarray(ic, dtype=np.float64))
     dist = _dist()
     world, rank = (dist.get_world_size(), dist.get_rank()) if dist is not None else (1, 0)
+    if ic.shape[0] < world:      # the same test on every rank: nobody enters the all-reduce alone
+        raise ValueError("%d members cannot be sharded over %d ranks" % (ic.shape[0], world))
     lo, hi = shard_bounds(ic.shape[0], world, rank)
-    if hi <= lo:
-        raise ValueError("this rank received no members (fewer members than ranks)")
     est = LyapunovsEstimator()
     est.set_func(f, Df)
     est.compute_lyapunovs(t0, tw, t, dt, mdt, ic=ic[lo:hi], write_steps=write_steps, n_vec=n_vec, forward=forward,
-                          vectors=False)
+                          vectors=False, member_offset=lo)
     res = est.get_lyapunovs()
     exps = np.asarray(res[2])
     m = est.n_vec

@@ -34,6 +34,9 @@ def load_tensor(path):
     """Read a tensor file; returns ``(ndim, coo, val, jcoo, jval)``.  Validates shapes so that a truncated or foreign
     file raises here instead of producing a wrong model."""
     with np.load(path) as z:
+        version = int(z["format_version"]) if "format_version" in z else FORMAT_VERSION   # the golden fixtures predate it
+        if version != FORMAT_VERSION:
+            raise ValueError("%s: tensor file format %d, this build reads format %d" % (path, version, FORMAT_VERSION))
         ndim = int(z["ndim"])
         coo, val, jcoo, jval = z["coo"], z["val"], z["jcoo"], z["jval"]
     if coo.ndim != 2 or coo.shape[1] not in (3, 5) or len(val) != coo.shape[0]:
@@ -105,16 +108,38 @@ def _walk(obj, h, stack):
             _walk(getattr(obj, name), h, stack)
 
 
+_BUILDER_KEY = None
+
+
+def _builder_key():
+    """Version of the reference package plus a digest of the source of the modules that BUILD the tensor
+    (qgs/tensors, qgs/inner_products): equal parameters must not be served a tensor an older construction produced.
+    Under the overlay ``import qgs`` is the overlay package; it re-exports the real ``__version__`` and its
+    ``__path__`` leads to the real sub-packages."""
+    global _BUILDER_KEY
+    if _BUILDER_KEY is None:
+        key = hashlib.sha256()
+        try:
+            import qgs
+            key.update(str(getattr(qgs, "__version__", "")).encode())
+            import glob
+            for base in list(getattr(qgs, "__path__", [])):
+                for sub in ("tensors", "inner_products"):
+                    for src in sorted(glob.glob(os.path.join(base, sub, "*.py"))):
+                        with open(src, "rb") as fh:
+                            key.update(os.path.basename(src).encode() + b"\0" + fh.read())
+        except (ImportError, OSError):
+            pass
+        _BUILDER_KEY = key.hexdigest()
+    return _BUILDER_KEY
+
+
 def fingerprint(params, *extra):
     """Hex digest that changes whenever any value reachable from ``params`` (scalars, arrays, mode blocks, symbolic basis
     functions, nested parameter containers) changes."""
     h = hashlib.sha256()
     h.update(b"qgsb-tensor-v%d;" % FORMAT_VERSION)
-    try:
-        import qgs
-        h.update(str(getattr(qgs, "__version__", "")).encode())
-    except ImportError:
-        pass
+    h.update(_builder_key().encode())
     _walk(params, h, frozenset())
     for item in extra:
         _walk(item, h, frozenset())

@@ -7,12 +7,15 @@ micro-steps ``mdt`` over each step ``dt``, ``np.linalg.qr``, ``log|diag R| / dt`
 CUDA launch for the whole ensemble (``qgsb_lyap_benettin``): the basis is propagated directly
 (``prop @ q`` by linearity), re-orthonormalised by a Householder QR with LAPACK's sign convention,
 and the nonlinear trajectory is recomputed on the fly instead of being stored (BLV) or kept in HBM
-(FLV).  The backward passes of the CLV methods (triangular back-substitution, subspace SVDs) act on
-the GPU-produced ``Q``/``R`` factors on the host.
+(FLV).  The backward passes of the CLV methods run on the device too: the Ginelli recursion in
+``qgsb_clv_ginelli``, the subspace intersections in ``qgsb_clv_subspace_intersect``.
 
-The random start basis of the reference comes from numba's unseeded generator
-(lyapunov.py:592-593); here it is drawn with ``numpy.random`` on the host, so ``np.random.seed``
-makes runs reproducible.
+The random start basis of the reference comes from numba's unseeded generator (lyapunov.py:592-593).
+``LyapunovsEstimator`` draws and factorises it ON THE DEVICE (``qgsb_lyap_benettin`` with ``q0 = NULL``: a
+counter-based uniform generator keyed by a seed and the member's index, then the kernel's own Householder
+QR), so neither host random numbers nor a stacked LAPACK QR of ``(n_traj, n_dim, n_vec)`` stand in front
+of the launch; the seed itself comes from ``numpy.random``, so ``np.random.seed`` makes runs reproducible.
+``benettin(..., q0=<array>)`` still takes a host basis (the golden tests feed the reference's own draws).
 """
 import ctypes
 import multiprocessing
@@ -45,10 +48,13 @@ def _subtimes(times, mdt, backward=False):
 
 
 def benettin(f, fjac, ic, mode, n_vec, q0, r0, pre_times, rec_times, mdt, write_steps, adjoint, inverse, b, c, a,
-             want_r=False, want_vectors=True):
+             want_r=False, want_vectors=True, seed=None, member_offset=0):
     """Run ``qgsb_lyap_benettin``.  ``pre_times`` / ``rec_times`` are the directed time vectors of the
     convergence phase and of the recorded phase.  mode 0: BLV, 1: FLV, 2: BLV whose trajectory follows the
-    micro-steps (Ginelli forward pass).  Returns ``traj (N,n,R), exp (N,m,R), vec (N,n,m,R)[, r_all]``."""
+    micro-steps (Ginelli forward pass).  ``q0 = None``: the start bases ``qr(random((n_dim, n_vec)))`` of
+    lyapunov.py:592-593 are drawn on the device (``seed``: a fresh one from ``numpy.random`` when ``None``;
+    ``member_offset``: global index of ``ic[0]`` when ``ic`` is a block of a larger ensemble).
+    Returns ``traj (N,n,R), exp (N,m,R), vec (N,n,m,R)[, r_all]``."""
     tensor = tensor_of(f)
     if tensor_of(fjac, "fjac") is not tensor:
         raise ValueError("f and fjac must come from the same create_tendencies() call")
@@ -65,8 +71,13 @@ def benettin(f, fjac, ic, mode, n_vec, q0, r0, pre_times, rec_times, mdt, write_
     n_pre, n_rec = len(pre_times) - 1, len(rec_times) - 1
     R = n_records_of(rec_times, write_steps)
     b, c, a = _lib.f64(b), _lib.f64(c), _lib.f64(a)
-    q0 = _lib.f64(q0)
-    r0 = None if r0 is None else _lib.f64(r0)
+    if q0 is None:
+        # start bases drawn and factorised on the device; the members of a sharded ensemble keep their global index
+        _lib.set_seed(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64) if seed is None else seed, member_offset)
+        r0 = None
+    else:
+        q0 = _lib.f64(q0)
+        r0 = None if r0 is None else _lib.f64(r0)
     rec_traj = np.empty((N, n, R))
     rec_exp = np.empty((N, m, R))
     rec_vec = np.empty((N, n, m, R)) if want_vectors else None
@@ -216,11 +227,14 @@ class LyapunovsEstimator(_EstimatorBase):
         self._inverse = 1.
 
     def compute_lyapunovs(self, t0, tw, t, dt, mdt, ic=None, write_steps=1, n_vec=None, forward=False, adjoint=False,
-                          inverse=False, vectors=True):
+                          inverse=False, vectors=True, member_offset=0, start_basis=None):
         """Estimate the BLVs between ``tw`` and ``t`` (``forward=False``) or the FLVs between ``t0`` and ``tw``
         (``forward=True``) -- lyapunov.py:232-358.  Results via :meth:`get_lyapunovs`.  ``vectors=False`` (an
         extension) keeps only the trajectory and the local exponents: no ``(n_traj, n_dim, n_vec, n_records)`` array
-        is recorded or copied, and ``get_lyapunovs`` returns ``None`` for the vectors."""
+        is recorded or copied, and ``get_lyapunovs`` returns ``None`` for the vectors.  ``member_offset`` (an
+        extension): global index of ``ic[0]`` when this process holds one block of a sharded ensemble.
+        ``start_basis`` (an extension): ``(q0 (n_traj, n_dim, n_vec), r0 (n_traj, n_vec, n_vec))`` host arrays to
+        start from instead of the device-side random draw (parity tests feed the reference's own draws)."""
         if self.func is None or self.func_jac is None:
             print('No function to integrate defined!')
             return 0
@@ -243,17 +257,19 @@ class LyapunovsEstimator(_EstimatorBase):
         if inverse:
             self._inverse *= -1.
 
-        q0, r0 = _random_basis(self.n_traj, self.n_dim, self.n_vec)
+        # start bases: qr(random((n_dim, n_vec))) per member (lyapunov.py:592-593), drawn on the device
+        q0, r0 = (None, None) if start_basis is None else start_basis
         if not forward:
             self.n_records = n_records_of(self._time, write_steps)
-            res = benettin(self.func, self.func_jac, self.ic, 0, self.n_vec, q0, r0, self._pretime, self._time, mdt,
-                           write_steps, adjoint, self._inverse, self.b, self.c, self.a, want_vectors=vectors)
+            res = benettin(self.func, self.func_jac, self.ic, 0, self.n_vec, q0, r0, self._pretime, self._time,
+                           mdt, write_steps, adjoint, self._inverse, self.b, self.c, self.a, want_vectors=vectors,
+                           member_offset=member_offset)
         else:
             self.n_records = n_records_of(self._pretime, write_steps)
             # walk back over posttime (= self._time) first, then over time (= self._pretime): lyapunov.py:509-546
             res = benettin(self.func, self.func_jac, self.ic, 1, self.n_vec, q0, r0, self._time[::-1].copy(),
                            self._pretime[::-1].copy(), mdt, write_steps, adjoint, self._inverse, self.b, self.c,
-                           self.a, want_vectors=vectors)
+                           self.a, want_vectors=vectors, member_offset=member_offset)
         self._recorded_traj, self._recorded_exp, self._recorded_vec = res
 
     def get_lyapunovs(self):

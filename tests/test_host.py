@@ -239,7 +239,10 @@ def test_shard_bounds_partition():
             parts = [shard_bounds(N, G, g) for g in range(G)]
             assert parts[0][0] == 0 and parts[-1][1] == N
             assert all(parts[i][1] == parts[i + 1][0] for i in range(G - 1))
-            assert max(hi - lo for lo, hi in parts) == -(-N // G)
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1 and max(sizes) == -(-N // G)
+            assert N < G or min(sizes) >= 1          # no rank is left empty (N = 9, G = 8 used to give 2,2,2,2,1,0,0,0)
+    assert [shard_bounds(9, 8, g)[1] - shard_bounds(9, 8, g)[0] for g in range(8)].count(0) == 0
 
 
 _GLOO_WORKER = r"""
@@ -497,3 +500,50 @@ def test_overlay_adapts_the_vertical_velocity_diagnostic_on_import(tmp_path):
                                                        os.path.join(REPO, "overlay"), ref_dir]))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0 and "hook ok" in res.stdout, res.stderr[-3000:]
+
+
+# ---- generated modules: versioned, and safe to build from several processes at once -------------------------
+def test_plugin_built_against_another_kernel_table_layout_is_refused(tmp_path):
+    """A module left in the JIT cache by an older build must not be read with the new SpecKernels layout:
+    qgsb_load_plugin checks the layout version the module was compiled with (no device needed)."""
+    import subprocess
+    from qgs_b200 import _lib
+    src = tmp_path / "stale.cu"
+    src.write_text('#include "spec_registry.h"\n'
+                   'static const qgsb::SpecKernels k = {QGSB_SPEC_ABI + 1u, 1ULL, 3, 3, 1, "stale", nullptr, nullptr, '
+                   'nullptr, 0, nullptr, 0ULL};\n'
+                   'extern "C" __attribute__((visibility("default"))) const qgsb::SpecKernels *qgsb_plugin_kernels(void) '
+                   '{ return &k; }\n')
+    so = tmp_path / "stale.so"
+    subprocess.check_call(["nvcc", "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-I", os.path.join(REPO, "qgs_b200", "csrc"),
+                           "-o", str(so), str(src)])
+    lib = _lib.load()
+    assert lib.qgsb_load_plugin(str(so).encode()) != 0
+    msg = lib.qgsb_last_error().decode()
+    assert "layout" in msg and "rebuild" in msg
+
+
+def test_concurrent_plugin_builds_of_one_tensor_do_not_collide(tmp_path):
+    """Under torchrun every rank misses the JIT cache at once: builders write private scratch files, queue on
+    a lock and the module is compiled once; every process ends up with the same complete shared object."""
+    import subprocess
+    import sys
+    worker = ("import sys, numpy as np; sys.path.insert(0, %r)\n"
+              "from qgs_b200 import codegen\n"
+              "coo = np.array([[1, 0, 1], [1, 0, 2], [2, 0, 1], [2, 0, 2], [2, 1, 3], [3, 0, 3], [3, 1, 2]])\n"
+              "val = np.array([-10., 10., 28., -1., -1., -2.5, 1.])\n"
+              "print(codegen.build_plugin(3, 3, coo, val, part='rk'))\n" % REPO)
+    env = dict(os.environ, QGSB_JIT_DIR=str(tmp_path))
+    procs = [subprocess.Popen([sys.executable, "-c", worker], env=env, stdout=subprocess.PIPE, text=True)
+             for _ in range(3)]
+    paths = {p.communicate()[0].strip() for p in procs}
+    assert all(p.returncode == 0 for p in procs)
+    assert len(paths) == 1 and paths != {"None"}
+    path = paths.pop()
+    from qgs_b200 import codegen
+    assert os.path.exists(path) and codegen.source_key() in os.path.basename(path)
+    left = sorted(os.listdir(str(tmp_path)))
+    assert [x for x in left if x.endswith(".so")] == [os.path.basename(path)]
+    assert not [x for x in left if x.endswith(".tmp") or x.endswith(".cu")]        # scratch files are gone
+    from qgs_b200 import _lib
+    assert _lib.load().qgsb_load_plugin(path.encode()) == 0
