@@ -456,7 +456,7 @@ __device__ __forceinline__ void qr(const Mem<N> &S, int c, bool live, double (&c
             }
         }
     }
-    if (live) {
+    if (live && S.fm != nullptr) {
         double *fmc = S.fm + c;
 #pragma unroll
         for (int i = 0; i < N; ++i) fmc[i * m] = col[i];
@@ -615,7 +615,7 @@ __device__ __forceinline__ void qr_rolled(const Mem<N> &S, int c, bool live, dou
     qr_formq_group<N, B2, N>(S, c, live, col);
     qr_formq_group<N, B1, B2>(S, c, live, col);
     qr_formq_group<N, 0, B1>(S, c, live, col);
-    if (live) {
+    if (live && S.fm != nullptr) {
         double *fmc = S.fm + c;
 #pragma unroll
         for (int i = 0; i < N; ++i) fmc[i * m] = col[i];
@@ -740,7 +740,7 @@ __device__ __forceinline__ void qr_async(const Mem<N> &S, int c, bool live, doub
     qr_formq_group<N, B2, N>(S, c, live, col);
     qr_formq_group<N, B1, B2>(S, c, live, col);
     qr_formq_group<N, 0, B1>(S, c, live, col);
-    if (live) {
+    if (live && S.fm != nullptr) {
         double *fmc = S.fm + c;
 #pragma unroll
         for (int i = 0; i < N; ++i) fmc[i * m] = col[i];
@@ -963,6 +963,98 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
     }
 }
 
+// ---- the re-orthonormalisation as its own launch ---------------------------------------------------------------------
+// One Benettin step = tangent propagation (tgls_kernel, one launch) + this kernel.  Why two launches beat the fused
+// lyap_kernel for large ensembles: inside the fused kernel the tangent phase costs 84k cycles per block and step where
+// tgls_kernel alone needs 38k -- the fused step body (product + 186 KB of unrolled reflectors) is streamed from L2 by
+// every warp once per step (stall "no instruction" 1.1 per issue), and 255 registers allow ONE block per SM, so the
+// latency chain of the factorisation (36 reflectors x ~45 dependent FP64 instructions) idles the whole SM.  Here the
+// code of a launch is resident, the kernel needs half the registers, and two blocks per SM overlap their chains.
+// The state crosses L2 / HBM between the launches: 2 x 8 n m bytes per member and launch, read and written as whole
+// contiguous blocks of G matrices.
+// Shared memory per member: the n x m matrix area (input staging, then the published reflectors, then output staging)
+// and the three scalar arrays.
+template <int N>
+struct QrCarve {
+    int nm, mp;
+    __host__ __device__ QrCarve(int m) : nm(even(N * m)), mp(even(m)) {}
+    __host__ __device__ int o_v() const { return 0; }
+    __host__ __device__ int o_rdiag() const { return nm; }
+    __host__ __device__ int o_tau() const { return o_rdiag() + mp; }
+    __host__ __device__ int o_scal() const { return o_tau() + mp; }
+    __host__ __device__ int o_flag() const { return o_scal() + mp; }
+    __host__ __device__ int total() const
+    {
+        int t = o_flag() + 2;
+        while (t % 16 != 2) t += 2;      // members of one warp read the same offset of their own area: spread the banks
+        return t;
+    }
+};
+
+template <int N, int QRM, int BLOCKS>
+__global__ void __launch_bounds__(MAX_THREADS, BLOCKS)
+qr_kernel(const __grid_constant__ TgParams P, int G, int stride)
+{
+    extern __shared__ __align__(16) double smem_pack[];
+    const int m = P.m, t = threadIdx.x, nm = N * m;
+    const long member0 = (long)blockIdx.x * G;
+    const int members = (int)min((long)G, P.n_members - member0);
+    // the block's matrices are contiguous in HBM: coalesced copy into the members' areas (row-major n x m each)
+    {
+        const double *src = P.fm + (size_t)member0 * nm;
+        const int total = members * nm;
+        for (int q = t; q < total; q += blockDim.x) {
+            const int g = q / nm;
+            smem_pack[(size_t)g * stride + (q - g * nm)] = src[q];
+        }
+    }
+    // columns dealt member-index-fastest: a warp holds the same few columns of all members (see lyap_kernel)
+    const int c = t / G, g = t - c * G;
+    const bool live = c < m && g < members;
+    const long member = member0 + g;
+    const QrCarve<N> cv(m);
+    double *base = smem_pack + (size_t)(live ? g : 0) * stride;
+    Mem<N> S;
+    S.jv = S.xs = S.xs2 = S.y = S.Y = S.kst = S.yacc = nullptr;
+    S.facc = base + cv.o_v();
+    S.fm = nullptr;                       // the factorisations keep Q in registers; it is staged out below
+    S.rdiag = base + cv.o_rdiag();
+    S.tau = base + cv.o_tau();
+    S.scal = base + cv.o_scal();
+    S.flag = reinterpret_cast<int *>(base + cv.o_flag());
+    S.m = m;
+    __syncthreads();
+    double col[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) col[i] = live ? S.facc[i * m + c] : 0.;
+    if (live && P.mexp_g != nullptr && P.dt_step != 0.)                   // lyapunov.py:611 / :531
+        P.mexp_g[member * m + c] = log(fabs(P.rdiag_g[member * m + c])) / P.dt_step;
+    double *Rout = (P.r_all != nullptr && P.r_step >= 0 && live)
+                       ? P.r_all + ((size_t)member * P.r_count + P.r_step) * m * m : nullptr;
+    // (the factorisations start with a barrier: every column is in registers before the area is overwritten)
+    if (QRM == 2)
+        qr_async<N>(S, c, live, col, Rout);
+    else if (QRM == 1)
+        qr_rolled<N>(S, c, live, col, Rout);
+    else
+        qr<N>(S, c, live, col, Rout);
+    __syncthreads();                       // every thread is done reading the reflectors
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) S.facc[i * m + c] = col[i];
+        P.rdiag_g[member * m + c] = S.rdiag[c];
+    }
+    __syncthreads();
+    {
+        double *dst = P.fm + (size_t)member0 * nm;
+        const int total = members * nm;
+        for (int q = t; q < total; q += blockDim.x) {
+            const int gg = q / nm;
+            dst[q] = smem_pack[(size_t)gg * stride + (q - gg * nm)];
+        }
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------
 // table_bytes: size of the ELL tables, which are always staged in shared memory behind the members' areas
 template <int N>
@@ -991,13 +1083,46 @@ inline size_t table_bytes(const PackTables &tab, int n)
     return b;
 }
 
-// launches the packed kernel for one policy pair; returns cudaErrorInvalidValue when it does not fit
+// launches the packed kernel for one policy pair; returns cudaErrorInvalidValue when it does not fit.
+// mode 0: tangent-linear integration, 1: fused Benettin loop, 2: one re-orthonormalisation (qr_kernel)
 template <int N, class Fwd, class Adj>
-inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTables &tables, bool lyap,
+inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTables &tables, int mode,
                           size_t smem_limit, cudaStream_t stream)
 {
     static_assert(Fwd::JV == Adj::JV, "both directions of a product share one Jacobian layout");
     if (P.m < 1 || P.m > MAX_THREADS) return cudaErrorInvalidValue;
+    // QGSB_QR_MODE = 0 (unrolled, a block barrier per reflector) | 1 (rolled) | 2 (pipelined: flags instead of
+    // barriers); see the comments at qr / qr_rolled / qr_async and profiles/ for the A/B measurements
+    const char *qenv = getenv("QGSB_QR_MODE");
+    if (mode == 2) {
+        const QrCarve<N> cv(P.m);
+        const size_t per_member = (size_t)cv.total() * sizeof(double);
+        int G = MAX_THREADS / P.m;
+        if (const char *env = getenv("QGSB_QR_G")) G = std::max(1, std::min(G, atoi(env)));      // A/B measurements
+        G = std::min<int>(G, (int)(smem_limit / per_member));
+        if (G < 1) return cudaErrorInvalidValue;
+        const int threads = ((G * P.m + 31) / 32) * 32;
+        const size_t smem = (size_t)G * per_member;
+        const unsigned blocks = (unsigned)((P.n_members + G - 1) / G);
+        const int qmode = qenv ? atoi(qenv) : (3 * P.m <= N ? 1 : 0);
+        auto go_qr = [&](auto kernel) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            kernel<<<blocks, threads, smem, stream>>>(P, G, cv.total());
+            return cudaGetLastError();
+        };
+        // two blocks per SM (128 registers: the unrolled factorisation spills) or one (no spills, one chain per SM)
+        const char *benv = getenv("QGSB_QR_BLOCKS");
+        const int per_sm = benv ? atoi(benv) : 2;
+        if (per_sm >= 2) {
+            if (qmode == 2) return go_qr(qr_kernel<N, 2, 2>);
+            if (qmode == 1) return go_qr(qr_kernel<N, 1, 2>);
+            return go_qr(qr_kernel<N, 0, 2>);
+        }
+        if (qmode == 2) return go_qr(qr_kernel<N, 2, 1>);
+        if (qmode == 1) return go_qr(qr_kernel<N, 1, 1>);
+        return go_qr(qr_kernel<N, 0, 1>);
+    }
     const Geometry geo = geometry<N>(Fwd::JV, P.m, smem_limit, table_bytes(tables, N));
     if (geo.G < 1) return cudaErrorInvalidValue;
     const PackTables &tab = tables;
@@ -1020,13 +1145,12 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
         kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, tab, geo.G, geo.stride, remap);
         return cudaGetLastError();
     };
-    if (lyap) {
-        // QGSB_QR_MODE = 0 (unrolled, a block barrier per reflector) | 1 (rolled) | 2 (pipelined, the default);
-        // see the comments at qr / qr_rolled / qr_async and profiles/ for the A/B measurements
-        const char *env = getenv("QGSB_QR_MODE");
-        const int mode = env ? atoi(env) : 2;
-        if (mode == 2) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 2>) : go_lyap(lyap_kernel<N, Fwd, 2>);
-        if (mode == 1) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 1>) : go_lyap(lyap_kernel<N, Fwd, 1>);
+    if (mode == 1) {
+        // few vectors: the rolled factorisation (one resident loop body instead of n_vec unrolled reflectors) is faster
+        // [B200: MAOOAM-36, 10 vectors +12 %; 36 vectors -9 %]
+        const int qmode = qenv ? atoi(qenv) : (3 * P.m <= N ? 1 : 0);
+        if (qmode == 2) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 2>) : go_lyap(lyap_kernel<N, Fwd, 2>);
+        if (qmode == 1) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 1>) : go_lyap(lyap_kernel<N, Fwd, 1>);
         return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 0>) : go_lyap(lyap_kernel<N, Fwd, 0>);
     }
     return P.adjoint ? go(tgls_kernel<N, Adj>) : go(tgls_kernel<N, Fwd>);

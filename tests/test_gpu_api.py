@@ -529,7 +529,7 @@ def test_large_basis_lyapunov_more_vectors_than_a_block_has_threads():
     np.random.seed(5)
     est = lyap.LyapunovsEstimator()
     est.set_func(f, Df)
-    est.compute_lyapunovs(0., 0.3, 0.8, 0.1, 0.1, ic=ic, write_steps=2, n_vec=150)
+    est.compute_lyapunovs(0., 0.3, 0.8, 0.1, 0.1, ic=ic, write_steps=2, n_vec=150, start_basis=(q0, r0))
     t, traj, exps, vecs = est.get_lyapunovs()
     pre = np.concatenate((np.arange(0., 0.3, 0.1), [0.3]))
     tim = np.concatenate((np.arange(0.3, 0.8, 0.1), [0.8]))
