@@ -582,13 +582,10 @@ static bool benettin_split(const qgsb_tensor *t, const Tableau &tab, TgParams &P
     if (!pack_tangent_supported(t, tab, P.m)) return false;
     const long N = P.n_members, steps = P.n_pre + P.n_rec;
     if (policy < 0 && N < 2L * ctx().sm_count * std::max(1, 256 / P.m)) return false;
-    if (P.forward == 0)      // the state must simply continue: one micro step of the macro length (lyapunov.py:598-601)
-        for (long s = 0; s < steps; ++s)
-            if (H.sub_ptr[s + 1] - H.sub_ptr[s] != 1 || H.sub_dt[H.sub_ptr[s]] != H.dt_macro[s]) return false;
     cudaStream_t st = ctx().stream;
     const int n = t->view.n, m = P.m;
     const size_t nm = (size_t)n * m;
-    PoolBuf<double> d_rdiag((size_t)N * m), d_mexp((size_t)N * m);
+    PoolBuf<double> d_rdiag((size_t)N * m), d_mexp((size_t)N * m), d_yw((size_t)N * n);
     rdiag_init_kernel<<<(unsigned)((N * m + 255) / 256), 256, 0, st>>>(P.r0, N, m, d_rdiag.p, d_mexp.p);
     count_launch();
     TgParams Q = P;                     // the factorisation launches
@@ -623,7 +620,23 @@ static bool benettin_split(const qgsb_tensor *t, const Tableau &tab, TgParams &P
         const long q0 = H.sub_ptr[step], q1 = H.sub_ptr[step + 1];
         K.n_steps = q1 - q0;
         K.dt = P.sub_dt + q0;
+        // BLV mode (lyapunov.py:598-601, :622): the tangent model starts from the stored trajectory point and takes the
+        // micro steps; the next stored point is ONE nonlinear step of the macro length.  With a single micro step of
+        // that length the two coincide bit for bit and the state simply continues; else the tangent launch works on a
+        // copy and a separate launch advances the stored point.  Ginelli mode (:1212-1218) follows the micro steps.
+        const bool continues = P.forward == 2 || (q1 - q0 == 1 && H.sub_dt[q0] == H.dt_macro[step]);
+        if (continues) {
+            K.y = P.y;
+        } else {
+            QGSB_CUDA(cudaMemcpyAsync(d_yw.p, P.y, sizeof(double) * N * n, cudaMemcpyDeviceToDevice, st));
+            K.y = d_yw.p;
+        }
         if (K.n_steps > 0) launch_pack_tangent(t, K, 0);
+        if (!continues) {
+            TgParams L = P;
+            L.dt_step = H.dt_macro[step];
+            launch_pack_tangent(t, L, 3);
+        }
         Q.dt_step = step >= P.n_pre ? H.dt_macro[step] : 0.;
         Q.r_step = (P.r_all && step >= P.r_first) ? step - P.r_first : -1;
         Q.r_count = steps - P.r_first;
@@ -818,6 +831,20 @@ static void benettin_device(const qgsb_tensor *t, long N, long member0, const do
     const int n = t->view.n, m = n_vec;
     const size_t nm = (size_t)n * m;
     const long steps = n_pre + n_rec;
+    // Micro steps of length exactly 0 are dropped: the reference's concatenate(arange(tt, tt + dt, mdt), [tt + dt])
+    // (lyapunov.py:598) often ends in two equal times when mdt divides dt (375 of the 1000 steps of arange(0, 100, 0.1)),
+    // and a Runge-Kutta step of length 0 leaves the state and the tangent matrix unchanged to the last bit
+    // (x + 0 * k = x), while costing a full step -- and hiding that the step is a single micro step of the macro length.
+    std::vector<long> f_ptr(steps + 1, 0);
+    std::vector<double> f_sub;
+    f_sub.reserve(sub_ptr[steps]);
+    for (long q = 0; q < steps; ++q) {
+        for (long e = sub_ptr[q]; e < sub_ptr[q + 1]; ++e)
+            if (sub_dt[e] != 0.) f_sub.push_back(sub_dt[e]);
+        f_ptr[q + 1] = (long)f_sub.size();
+    }
+    sub_ptr = f_ptr.data();
+    sub_dt = f_sub.data();
     const long n_sub = sub_ptr[steps];
     PoolBuf<double> d_y((size_t)N * n), d_q((size_t)N * nm), d_dtm(std::max<long>(steps, 1)), d_sub(std::max<long>(n_sub, 1));
     PoolBuf<long> d_ptr(steps + 1), d_idx(std::max<long>(steps, 1));

@@ -817,6 +817,33 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
     }
 }
 
+// ---- one nonlinear step of every member (split Benettin loop: the stored-trajectory point of lyapunov.py:601 / :622 when
+// the tangent model took several micro steps) -- the very nl_step of the fused kernel, so the results are bitwise its own
+template <int N>
+__global__ void __launch_bounds__(MAX_THREADS, 1)
+nl_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride)
+{
+    extern __shared__ __align__(16) double smem_pack[];
+    const ShTab tab = stage_tables(tab_g, smem_pack + (size_t)G * stride, N);
+    const int m = P.m, t = threadIdx.x;
+    const int g = t / m, c = t - g * m;
+    const long member = (long)blockIdx.x * G + g;
+    const bool live = g < G && member < P.n_members;
+    const Mem<N> S = carve<N>(smem_pack + (size_t)(live ? g : 0) * stride, 0, m);
+    if (live) {
+        for (int r = c; r < N; r += m) {
+            S.Y[r] = P.y[member * N + r];
+            S.kst[r] = 0.;
+            S.yacc[r] = 0.;
+        }
+        if (c == 0) S.xs[0] = 1.;
+    }
+    __syncthreads();
+    nl_step<N>(T, tab, P, S, P.dt_step, c, live);
+    if (live)
+        for (int r = c; r < N; r += m) P.y[member * N + r] = S.Y[r];
+}
+
 // ---- Benettin loop (lyapunov.py:471-632) ---------------------------------------------------------------------------------
 // QRM: the re-orthonormalisation -- 0 unrolled with a block barrier per reflector (qr), 1 rolled (qr_rolled),
 // 2 pipelined: rolled, flags instead of barriers (qr_async)
@@ -1084,7 +1111,8 @@ inline size_t table_bytes(const PackTables &tab, int n)
 }
 
 // launches the packed kernel for one policy pair; returns cudaErrorInvalidValue when it does not fit.
-// mode 0: tangent-linear integration, 1: fused Benettin loop, 2: one re-orthonormalisation (qr_kernel)
+// mode 0: tangent-linear integration, 1: fused Benettin loop, 2: one re-orthonormalisation (qr_kernel),
+// 3: one nonlinear step (nl_kernel)
 template <int N, class Fwd, class Adj>
 inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTables &tables, int mode,
                           size_t smem_limit, cudaStream_t stream)
@@ -1122,6 +1150,17 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
         if (qmode == 2) return go_qr(qr_kernel<N, 2, 1>);
         if (qmode == 1) return go_qr(qr_kernel<N, 1, 1>);
         return go_qr(qr_kernel<N, 0, 1>);
+    }
+    if (mode == 3) {                       // one nonlinear step of length P.dt_step on P.y
+        const Geometry g3 = geometry<N>(0, P.m, smem_limit, table_bytes(tables, N));
+        if (g3.G < 1) return cudaErrorInvalidValue;
+        if (g3.smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(nl_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g3.smem);
+            if (e != cudaSuccess) return e;
+        }
+        nl_kernel<N><<<(unsigned)((P.n_members + g3.G - 1) / g3.G), g3.threads, g3.smem, stream>>>(T, P, tables, g3.G,
+                                                                                                  g3.stride);
+        return cudaGetLastError();
     }
     const Geometry geo = geometry<N>(Fwd::JV, P.m, smem_limit, table_bytes(tables, N));
     if (geo.G < 1) return cudaErrorInvalidValue;

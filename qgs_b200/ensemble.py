@@ -205,6 +205,13 @@ class DeviceEnsemble(object):
             mean, var = mean[::-1], var[::-1]
         return rec_time, mean, var
 
+    def set_states(self, states):
+        """Replace the resident members by ``states`` ``(n_local, n_dim)`` (same number of members)."""
+        states = _lib.f64(np.atleast_2d(states))
+        if states.shape != (self.n_traj, self.n_dim):
+            raise ValueError("states must have shape %s" % ((self.n_traj, self.n_dim),))
+        _lib.check(_lib.load().qgsb_ensemble_upload(self._handle, _lib.dptr(states)))
+
     def states(self):
         """This rank's members as a host array ``(n_local, n_dim)``."""
         out = np.empty((self.n_traj, self.n_dim))

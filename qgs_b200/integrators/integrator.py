@@ -4,8 +4,7 @@
 methods, attributes, shape conventions and quirks (integrator.py:27-450, :515-1100).  What is gone is
 the pool of ``multiprocessing`` workers fed one pickled message per trajectory
 (integrator.py:121-142, 388-395): ``integrate`` hands the whole ensemble to one fused CUDA launch.
-``num_threads`` is kept for signature parity; it only sets the batch size of ``initialize`` like in
-the reference (integrator.py:257-291).
+``num_threads`` is kept for signature parity; ``initialize`` batches by the size of the device, not by it.
 """
 import multiprocessing
 
@@ -129,57 +128,75 @@ class RungeKuttaIntegrator(_IntegratorBase):
             self.ic = None
         self.start()
 
+    #: members per batch of :meth:`initialize` when it reconverges perturbed copies; ``None``: one full wave of the
+    #: fused kernel (2 thread blocks of 128 members on every SM).  ``num_threads`` only sets a lower bound.
+    device_batch = None
+
+    def _initialize_batch(self):
+        if self.device_batch is not None:
+            return max(int(self.device_batch), 1)
+        return max(int(self.num_threads), 2 * 128 * _lib.device_info()["sm_count"])
+
     def initialize(self, convergence_time, dt, pert_size=0.01, reconvergence_time=None, forward=True,
                    number_of_trajectories=1, ic=None, reconverge=False):
-        """Converge to the attractor by integrating over a transient (integrator.py:198-295).  Semantics are the
-        reference's, including batches of ``num_threads`` members when reconverging."""
-        if reconverge is None:
-            reconverge = False
+        """Put ``number_of_trajectories`` members on the attractor (integrator.py:198-295) and store them in ``ic``.
+
+        Same arguments and the same scheme as the reference -- a first batch of members is integrated over
+        ``convergence_time``; with ``reconverge`` (forced when more members are asked for than one batch holds) every
+        further batch is the previous one plus a perturbation of size ``pert_size``, integrated over the shorter
+        ``reconvergence_time`` -- but the batch is sized for the device, not for the host: the reference's batch is
+        ``num_threads`` worker processes (integrator.py:257-291), here it is one full wave of thread blocks
+        (:attr:`device_batch`; ``num_threads`` is only a lower bound), so a million members are a few dozen launches
+        instead of tens of thousands.  The members never travel as trajectories: each batch lives in a resident
+        ensemble (``qgsb_ensemble_*``), only its end state is read back to be perturbed for the next batch."""
+        from qgs_b200.ensemble import DeviceEnsemble
+        if self.func is None:
+            print('No function to integrate defined!')
+            return 0
+        reconverge = bool(reconverge)
+        batch = self._initialize_batch()
 
         if ic is None:
-            i = self._infer_ndim()
-
-            if number_of_trajectories > self.num_threads:
+            n_dim = self._infer_ndim()
+            n_total = int(number_of_trajectories)
+            if n_total > batch:
                 reconverge = True
-                tmp_ic = np.zeros((number_of_trajectories, i))
-                tmp_ic[:self.num_threads] = np.random.randn(self.num_threads, i)
-            else:
-                tmp_ic = np.random.randn(number_of_trajectories, i)
+            first = np.random.randn(min(n_total, batch) if reconverge else n_total, n_dim)
         else:
-            tmp_ic = ic.copy()
-            if len(tmp_ic.shape) > 1:
-                number_of_trajectories = tmp_ic.shape[0]
+            first = np.atleast_2d(np.array(ic, dtype=np.float64))
+            n_total = first.shape[0]
+            n_dim = first.shape[1]
+            if reconverge and reconvergence_time is not None:
+                first = first[:batch]          # the reference keeps the first batch only (integrator.py:236-238)
 
-        if reconverge and reconvergence_time is not None:
-            self.integrate(0., convergence_time, dt, ic=tmp_ic[:self.num_threads], write_steps=0, forward=forward)
-            t, x = self.get_trajectories()
-            x = np.atleast_2d(x)
-            tmp_ic[:self.num_threads] = x
-            if number_of_trajectories - self.num_threads > self.num_threads:
-                next_len = self.num_threads
+        ens = DeviceEnsemble(self.func, first)
+        try:
+            ens.integrate(0., convergence_time, dt, forward=forward, b=self.b, c=self.c, a=self.a)
+            x = ens.states()
+            if not (reconverge and reconvergence_time is not None) or x.shape[0] >= n_total:
+                out = x
             else:
-                next_len = number_of_trajectories - self.num_threads
-
-            index = self.num_threads
-            while True:
-                perturbation = pert_size * np.random.randn(next_len, x.shape[1])
-                self.integrate(0., reconvergence_time, dt, ic=x[:next_len] + perturbation, write_steps=0,
-                               forward=forward)
-                t, x = self.get_trajectories()
-                x = np.atleast_2d(x)
-                tmp_ic[index:index + next_len] = x
-                index += next_len
-                if number_of_trajectories - index > self.num_threads:
-                    next_len = self.num_threads
-                else:
-                    next_len = number_of_trajectories - index
-                if next_len <= 0:
-                    break
-            self.ic = tmp_ic
-        else:
-            self.integrate(0., convergence_time, dt, ic=tmp_ic, write_steps=0, forward=forward)
-            t, x = self.get_trajectories()
-            self.ic = x
+                out = np.empty((n_total, n_dim))
+                out[:x.shape[0]] = x
+                index = x.shape[0]
+                while index < n_total:
+                    count = min(x.shape[0], n_total - index)
+                    x = x[:count] + pert_size * np.random.randn(count, n_dim)
+                    if count != ens.n_traj:
+                        ens.close()
+                        ens = DeviceEnsemble(self.func, x)
+                    else:
+                        ens.set_states(x)
+                    ens.integrate(0., reconvergence_time, dt, forward=forward, b=self.b, c=self.c, a=self.a)
+                    x = ens.states()
+                    out[index:index + count] = x
+                    index += count
+        finally:
+            ens.close()
+        self.n_traj = out.shape[0]
+        self.n_dim = n_dim
+        # like the reference, ic ends up as what get_trajectories() returns: squeezed for a single member
+        self.ic = np.squeeze(out) if out.shape[0] == 1 else out
 
     def integrate(self, t0, t, dt, ic=None, forward=True, write_steps=1):
         """Integrate the ensemble from ``t0`` to ``t`` (integrator.py:297-395).  Results via ``get_trajectories``."""

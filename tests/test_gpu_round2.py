@@ -290,3 +290,52 @@ def test_split_benettin_loop_follows_micro_steps_in_ginelli_mode():
             split = _benettin("maooam36", 20, 36, None, None, seed=3, mode=mode, mdt=mdt)
         for x, y in zip(fused, split):
             assert np.array_equal(x, y), (mode, mdt)
+
+
+# ---- initialize() on resident device batches ------------------------------------------------------------------------------
+def test_initialize_in_device_batches_matches_an_oracle_replay_of_the_same_draws():
+    """RungeKuttaIntegrator.initialize (integrator.py:198-295): first batch converged over the long transient, every
+    further batch = previous batch + pert_size * randn, reconverged over the short one.  The batch is the device's
+    (here forced to 64), num_threads is only a hint.  Replaying the SAME numpy draws through the CPU oracle must give
+    the same members (transients short against the Lyapunov time, so the comparison is a trajectory comparison)."""
+    import oracle
+    from qgs_b200.integrators.integrator import RungeKuttaIntegrator
+    f, Df, T = model("maooam36")
+    b, c, a = oracle.rk4_tableau()
+    integ = RungeKuttaIntegrator(num_threads=3)
+    integ.set_func(f)
+    integ.device_batch = 64
+    N, conv, reconv, pert = 150, 6., 2., 1e-3
+
+    def scaled_randn(*shape):                    # N(0, 1) initial conditions blow MAOOAM up: scale the draws
+        return 0.01 * base_randn(*shape)
+
+    base_randn = np.random.randn
+    np.random.seed(5)
+    np.random.randn = scaled_randn
+    try:
+        integ.initialize(conv, 0.1, pert_size=pert / 0.01, reconvergence_time=reconv, number_of_trajectories=N)
+    finally:
+        np.random.randn = base_randn
+    got = integ.get_ic()
+    assert got.shape == (N, 36) and integ.n_traj == N
+    # replay
+    np.random.seed(5)
+    tv = lambda t1: np.concatenate((np.arange(0., t1, 0.1), [t1]))
+    x = oracle.integrate_runge_kutta_jit(T, tv(conv), 0.01 * np.random.randn(64, 36), 1, 0, b, c, a)[:, :, 0]
+    ref = np.empty((N, 36))
+    ref[:64] = x
+    index = 64
+    while index < N:
+        count = min(64, N - index)
+        x = oracle.integrate_runge_kutta_jit(T, tv(reconv), x[:count] + pert * np.random.randn(count, 36), 1, 0,
+                                             b, c, a)[:, :, 0]
+        ref[index:index + count] = x
+        index += count
+    assert np.max(np.abs(got - ref)) < 1e-10 * np.max(np.abs(ref))
+    # a single member: ic is squeezed like get_trajectories() squeezes it; given ics are converged as they are
+    integ.initialize(1., 0.1, ic=ref[0])
+    assert integ.get_ic().shape == (36,)
+    integ.initialize(1., 0.1, ic=ref[:5])
+    one = oracle.integrate_runge_kutta_jit(T, tv(1.), ref[:5], 1, 0, b, c, a)[:, :, 0]
+    assert np.max(np.abs(integ.get_ic() - one)) < 1e-10 * np.max(np.abs(one))
