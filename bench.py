@@ -25,6 +25,9 @@ STEPS_PER_LAUNCH classic-RK4 time steps of dt = 0.1 with write_steps = 0 -- one 
             its own FP64 roofline (525 532 flops per member-step), e2e through the Python class
             (host arrays in, trajectory + exponents out), and the reference's LyapunovsEstimator on all host cores.
   strong    the SAME total ensemble (2^20 members) split over the N GPUs: whole-job member-steps/s, device-timed.
+  suite     the other configurations of BASELINE.json (RP-20, dynamic-T, T4, 6x6 large basis) on ONE GPU (rank 0):
+            device-timed RK4 member-steps/s and the FP64 roofline fraction with each tensor's own algorithmic flops
+            (SURVEY.md section 8d).  Parity of these configurations is what tests/test_gpu_parity.py checks.
 
 --impl reference times the reference's own CPU implementation of the path: RungeKuttaIntegrator from
 baseline/_ref through its public API (else the oracle port).  Under torchrun rank 0 alone runs it.
@@ -441,6 +444,47 @@ def lyapunov_leg(lib, _lib, f, Df, rank, world, barrier, repeats):
     return dev_s, e2e_s, launches, finite, spectrum, (N * NDIM * 8, N * (NDIM + LYAP_NVEC) * R * 8)
 
 
+# BASELINE.json configs[0], [2], [3]: tensor fixture, members, steps per launch, flops per member-step
+SUITE = (("rp", "qgs_rp.py 2-layer channel + orography, 20 variables", 1 << 20, 500, 2620),
+         ("dynT", "MAOOAM with dynamic temperatures, 38 variables, rank-5 tensor", 1 << 20, 200, 5748),
+         ("T4", "MAOOAM with T^4 radiation, 38 variables, 5340 rank-5 entries", 148 * 2 * 128 * 4, 50, 103468),
+         ("atm6x6", "6x6 large-basis atmosphere, 228 variables (test_aotensor_6x6)", 148 * 96 * 4, 20, 329488))
+
+
+def suite_leg(lib, _lib, peak):
+    """Device-timed RK4 throughput of the secondary configurations on this GPU (best of three launches)."""
+    import ctypes
+    from qgs_b200.functions.tendencies import tendencies_from_tensor
+    from qgs_b200.integrators.integrate import rk4_tableau
+    b, c, a = rk4_tableau()
+    out = {}
+    for name, what, members, steps, flops in SUITE:
+        z = np.load(os.path.join(REPO, "tests", "golden", "tensor_%s.npz" % name))
+        f, _ = tendencies_from_tensor(int(z["ndim"]), z["coo"], z["val"], z["jcoo"], z["jval"])
+        ens = ctypes.c_void_p()
+        _lib.check(lib.qgsb_ensemble_create(f.tensor.handle, members, ctypes.byref(ens)))
+        ic = np.random.default_rng(1).random((members, f.ndim)) * (0.1 if name == "rp" else 0.01)
+        _lib.check(lib.qgsb_ensemble_upload(ens, _lib.dptr(ic)))
+        dt = np.full(steps, DT)
+        ms = ctypes.c_double()
+        best = 1e30
+        for _ in range(4):
+            _lib.check(lib.qgsb_ensemble_integrate(ens, steps, _lib.dptr(dt), 4, _lib.dptr(a), _lib.dptr(b),
+                                                   _lib.dptr(c), ctypes.byref(ms)))
+            best = min(best, ms.value)
+        s1, s2 = np.empty(f.ndim), np.empty(f.ndim)
+        _lib.check(lib.qgsb_ensemble_moments(ens, _lib.dptr(s1), _lib.dptr(s2)))
+        lib.qgsb_ensemble_destroy(ens)
+        rate = members * steps / (best * 1e-3)
+        out[name] = {"workload": "%s; %d members x %d RK4 steps, dt=0.1, write_steps=0" % (what, members, steps),
+                     "value": rate, "unit": UNIT, "ms_per_launch": best, "kernel_kind": f.tensor.kernel_kind,
+                     "roofline": {"bound": "fp64", "achieved": rate * flops / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                  "frac": rate * flops / 1e12 / peak, "flops_per_member_step": flops},
+                     "finite": bool(np.all(np.isfinite(s1)))}
+        del f
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import ctypes
 
@@ -577,6 +621,7 @@ def run_ours(args, rank, world, local_rank):
         member_steps = float(members) * n_steps * args.steps * world
         value = member_steps / (total_ms * 1e-3)
         peak = _lib.fp64_peak()
+        suite = suite_leg(lib, _lib, peak)
         ach = FLOPS_PER_MEMBER_STEP * float(members) * n_steps / (total_ms / args.steps * 1e-3) / 1e12
         traffic = None
         prof = os.path.join(REPO, "profiles", "r01_rk_chain_ncu_200steps.json")
@@ -623,6 +668,7 @@ def run_ours(args, rank, world, local_rank):
                                     "numpy arrays in and out"},
                     "cpu_baseline": lyap_cpu, "gpu_launches": int(ly_launches), "exponents_finite": ly_finite,
                     "leading_exponents": [float(v) for v in spectrum[:4]]},
+                "suite": suite,
                 "gpu_launches": int(n_launches), "clocks": clocks,
                 "wall_s_timed_region": wall_s, "ensemble_mean_finite": finite}
         print(json.dumps(line), flush=True)

@@ -19,7 +19,7 @@ struct PackTables;   // tgls_shared.cuh
 // Layout version of SpecKernels / TgParams / PackTables / the packed kernels' shared-memory carve-up as a module was
 // compiled against them.  Bump it whenever one of those changes: qgsb_load_plugin refuses a module built against
 // another version instead of reading its table with the wrong layout (modules cached on disk outlive a library).
-#define QGSB_SPEC_ABI 4u
+#define QGSB_SPEC_ABI 5u
 
 struct SpecKernels {
     uint32_t abi;   // QGSB_SPEC_ABI of the headers the module was compiled with -- must stay the FIRST member
@@ -37,8 +37,7 @@ struct SpecKernels {
                               cudaStream_t stream);
     // packed tangent-linear / Benettin kernels (tgls_pack.cuh) with the product J @ X emitted over the literal
     // list of Jacobian positions; null when the module was generated without a Jacobian tensor.
-    // lyap = 0: integrate.py:555-614, 1: lyapunov.py:471-632 as one launch, 2: one Householder QR of every member's
-    // matrix (the re-orthonormalisation of lyapunov.py:602-604 as its own launch).
+    // lyap = 0: integrate.py:555-614, 1: lyapunov.py:471-632.
     cudaError_t (*tangent)(const TensorView &T, const TgParams &P, const PackTables &tables, int lyap,
                            size_t smem_limit, cudaStream_t stream);
     int jac_slots;                 // doubles of shared memory holding the position values of one member

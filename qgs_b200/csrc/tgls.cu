@@ -536,126 +536,13 @@ static void set_smem_attr(K kernel, size_t bytes)
         QGSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
-// ---- Benettin loop as two launches per step (large ensembles on the packed kernels) ---------------------------------
-// records of the split loop: state, basis and local exponents of one record, and / or the basis of one q_all slot
-__global__ void benettin_record_kernel(const double *__restrict__ y, const double *__restrict__ fm,
-                                       const double *__restrict__ rdiag, const double *__restrict__ mexp, double dt,
-                                       long N, int n, int m, double *rec_y, double *rec_fm, double *rec_exp,
-                                       double *q_slot, long q_stride)
-{
-    const long member = blockIdx.x;
-    const int nm = n * m;
-    if (rec_y)
-        for (int r = threadIdx.x; r < n; r += blockDim.x) rec_y[member * n + r] = y[member * n + r];
-    if (rec_fm)
-        for (int q = threadIdx.x; q < nm; q += blockDim.x) rec_fm[member * nm + q] = fm[member * nm + q];
-    if (rec_exp)
-        for (int c = threadIdx.x; c < m; c += blockDim.x)
-            rec_exp[member * m + c] = dt != 0. ? log(fabs(rdiag[member * m + c])) / dt : mexp[member * m + c];
-    if (q_slot)
-        for (int q = threadIdx.x; q < nm; q += blockDim.x) q_slot[member * q_stride + q] = fm[member * nm + q];
-}
-
-__global__ void rdiag_init_kernel(const double *__restrict__ r0, long N, int m, double *rdiag, double *mexp)
-{
-    const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= N * m) return;
-    const long member = q / m;
-    const int c = (int)(q - member * m);
-    rdiag[q] = r0 ? r0[((size_t)member * m + c) * m + c] : 0.;
-    mexp[q] = 0.;
-}
-
-// QGSB_BENETTIN_SPLIT = 0: always the fused kernel; 1: the split loop whenever it applies; unset: the split loop for
-// ensembles of at least two waves of the packed tangent kernel (small runs keep one launch for the whole integration)
-static int split_policy()
-{
-    const char *e = getenv("QGSB_BENETTIN_SPLIT");
-    if (!e || !e[0]) return -1;
-    return atoi(e) != 0 ? 1 : 0;
-}
-
-static bool benettin_split(const qgsb_tensor *t, const Tableau &tab, TgParams &P, const BenettinHost &H)
-{
-    const int policy = split_policy();
-    if (policy == 0 || P.stored || P.forward == 1) return false;
-    if (!pack_tangent_supported(t, tab, P.m)) return false;
-    const long N = P.n_members, steps = P.n_pre + P.n_rec;
-    if (policy < 0 && N < 2L * ctx().sm_count * std::max(1, 256 / P.m)) return false;
-    cudaStream_t st = ctx().stream;
-    const int n = t->view.n, m = P.m;
-    const size_t nm = (size_t)n * m;
-    PoolBuf<double> d_rdiag((size_t)N * m), d_mexp((size_t)N * m), d_yw((size_t)N * n);
-    rdiag_init_kernel<<<(unsigned)((N * m + 255) / 256), 256, 0, st>>>(P.r0, N, m, d_rdiag.p, d_mexp.p);
-    count_launch();
-    TgParams Q = P;                     // the factorisation launches
-    Q.rdiag_g = d_rdiag.p;
-    Q.mexp_g = d_mexp.p;
-    TgParams K = P;                     // the propagation launches: plain tangent-linear integration, no records
-    K.rec_y = nullptr;
-    K.rec_fm = nullptr;
-    K.write_steps = 0;
-    K.n_records = 1;
-    auto record = [&](long rc, double dt, long q_index) {
-        benettin_record_kernel<<<(unsigned)N, 128, 0, st>>>(
-            P.y, P.fm, d_rdiag.p, d_mexp.p, dt, N, n, m, rc >= 0 ? P.rec_y + (size_t)rc * N * n : nullptr,
-            (rc >= 0 && P.rec_fm) ? P.rec_fm + (size_t)rc * N * nm : nullptr,
-            rc >= 0 ? P.rec_exp + (size_t)rc * N * m : nullptr,
-            (q_index >= 0 && P.q_all) ? P.q_all + (size_t)q_index * nm : nullptr, (long)((P.n_rec + 1) * nm));
-        count_launch();
-    };
-    if (P.qr_at_start) {
-        Q.dt_step = 0.;
-        Q.r_step = -1;
-        launch_pack_tangent(t, Q, 2);
-    }
-    long iw = 0;
-    for (long step = 0; step < steps; ++step) {
-        if (step >= P.n_pre) {
-            const long ti = step - P.n_pre;
-            const bool rec = P.write_steps > 0 && ti % P.write_steps == 0;
-            if (rec || P.q_all) record(rec ? iw : -1, H.dt_macro[step], P.q_all ? ti : -1);
-            if (rec) ++iw;
-        }
-        const long q0 = H.sub_ptr[step], q1 = H.sub_ptr[step + 1];
-        K.n_steps = q1 - q0;
-        K.dt = P.sub_dt + q0;
-        // BLV mode (lyapunov.py:598-601, :622): the tangent model starts from the stored trajectory point and takes the
-        // micro steps; the next stored point is ONE nonlinear step of the macro length.  With a single micro step of
-        // that length the two coincide bit for bit and the state simply continues; else the tangent launch works on a
-        // copy and a separate launch advances the stored point.  Ginelli mode (:1212-1218) follows the micro steps.
-        const bool continues = P.forward == 2 || (q1 - q0 == 1 && H.sub_dt[q0] == H.dt_macro[step]);
-        if (continues) {
-            K.y = P.y;
-        } else {
-            QGSB_CUDA(cudaMemcpyAsync(d_yw.p, P.y, sizeof(double) * N * n, cudaMemcpyDeviceToDevice, st));
-            K.y = d_yw.p;
-        }
-        if (K.n_steps > 0) launch_pack_tangent(t, K, 0);
-        if (!continues) {
-            TgParams L = P;
-            L.dt_step = H.dt_macro[step];
-            launch_pack_tangent(t, L, 3);
-        }
-        Q.dt_step = step >= P.n_pre ? H.dt_macro[step] : 0.;
-        Q.r_step = (P.r_all && step >= P.r_first) ? step - P.r_first : -1;
-        Q.r_count = steps - P.r_first;
-        launch_pack_tangent(t, Q, 2);
-    }
-    record(P.n_records - 1, 0., P.q_all ? P.n_rec : -1);       // lyapunov.py:628-630: the last exponents computed
-    QGSB_CUDA(cudaGetLastError());
-    return true;
-}
-
-// picks the Benettin kernel(s) for a filled parameter block (device pointers)
-void benettin_dispatch(const qgsb_tensor *t, const Tableau &tab, TgParams &P, DevBuf<double> &scratch,
-                       const BenettinHost *host)
+// picks the Benettin kernel for a filled parameter block (device pointers)
+void benettin_dispatch(const qgsb_tensor *t, const Tableau &tab, TgParams &P, DevBuf<double> &scratch)
 {
     const int m = P.m;
     cudaStream_t st = ctx().stream;
-    if (host != nullptr && benettin_split(t, tab, P, *host)) return;
     if (pack_tangent_supported(t, tab, m)) {
-        launch_pack_tangent(t, P, 1);
+        launch_pack_tangent(t, P, true);
     } else if (t->view.rank == 5) {
         const size_t bytes = place_matrices(t, P, scratch, 0);
         set_smem_attr(lyap_kernel<5>, bytes);
@@ -715,7 +602,7 @@ static void tgls_integrate_device(const qgsb_tensor *t, long N, const double *ic
     P.rec_fm = d_rf.p;
     QGSB_CUDA(cudaEventRecord(cx.ev0, st));
     if (pack_tangent_supported(t, tab, m)) {
-        launch_pack_tangent(t, P, 0);
+        launch_pack_tangent(t, P, false);
     } else if (t->view.rank == 5) {
         const size_t bytes = place_matrices(t, P, scratch, 0);
         set_smem_attr(tgls_kernel<5>, bytes);
@@ -917,11 +804,7 @@ static void benettin_device(const qgsb_tensor *t, long N, long member0, const do
         P.final_idx = steps > 0 ? idx[steps - 1] : 0;   // lyapunov.py:549: y[0] of the last pass
         QGSB_CUDA(cudaStreamSynchronize(st));           // fdt / idx host vectors must outlive the copies
     }
-    BenettinHost host;
-    host.dt_macro = dt_macro;
-    host.sub_ptr = sub_ptr;
-    host.sub_dt = sub_dt;
-    benettin_dispatch(t, tab, P, scratch, &host);
+    benettin_dispatch(t, tab, P, scratch);
     QGSB_CUDA(cudaGetLastError());
     QGSB_CUDA(cudaEventRecord(cx.ev1, st));
     launch_transpose_rec(d_ry.p, d_oy.p, R, (long)N * n, 0);

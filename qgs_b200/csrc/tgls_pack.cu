@@ -25,9 +25,9 @@ static int forced_kernel()
 }
 
 template <int N>
-static cudaError_t launch_dense(const TensorView &T, const TgParams &P, const PackTables &tab, int mode)
+static cudaError_t launch_dense(const TensorView &T, const TgParams &P, const PackTables &tab, bool lyap)
 {
-    return pack::launch<N, pack::DenseProduct<N, false>, pack::DenseProduct<N, true>>(T, P, tab, mode, ctx().smem_optin,
+    return pack::launch<N, pack::DenseProduct<N, false>, pack::DenseProduct<N, true>>(T, P, tab, lyap, ctx().smem_optin,
                                                                                        ctx().stream);
 }
 
@@ -168,17 +168,17 @@ const PackTables &pack_tables(const qgsb_tensor *t, bool spec)
     return pc->tab;
 }
 
-void launch_pack_tangent(const qgsb_tensor *t, const TgParams &P, int mode)
+void launch_pack_tangent(const qgsb_tensor *t, const TgParams &P, bool lyap)
 {
     cudaError_t err;
     if (spec_tangent_usable(t) && forced_kernel() != 2) {
-        err = t->spec->tangent(t->view, P, pack_tables(t, true), mode, ctx().smem_optin, ctx().stream);
+        err = t->spec->tangent(t->view, P, pack_tables(t, true), lyap ? 1 : 0, ctx().smem_optin, ctx().stream);
     } else {
         const PackTables &tab = pack_tables(t, false);
         switch (t->view.n) {
-            case 20: err = launch_dense<20>(t->view, P, tab, mode); break;
-            case 36: err = launch_dense<36>(t->view, P, tab, mode); break;
-            case 38: err = launch_dense<38>(t->view, P, tab, mode); break;
+            case 20: err = launch_dense<20>(t->view, P, tab, lyap); break;
+            case 36: err = launch_dense<36>(t->view, P, tab, lyap); break;
+            case 38: err = launch_dense<38>(t->view, P, tab, lyap); break;
             default: err = cudaErrorInvalidValue;
         }
     }

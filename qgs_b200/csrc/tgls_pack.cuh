@@ -61,8 +61,7 @@ struct Carve {
     __host__ __device__ int o_rdiag() const { return o_yacc() + even(N); }
     __host__ __device__ int o_tau() const { return o_rdiag() + mp; }
     __host__ __device__ int o_scal() const { return o_tau() + mp; }
-    __host__ __device__ int o_flag() const { return o_scal() + mp; }           // 2 doubles: progress counter of qr_async
-    __host__ __device__ int o_fm() const { return o_flag() + 2; }
+    __host__ __device__ int o_fm() const { return o_scal() + mp; }
     __host__ __device__ int o_facc() const { return o_fm() + nm; }
     __host__ __device__ int total() const
     {
@@ -77,7 +76,6 @@ struct Carve {
 template <int N>
 struct Mem {
     double *jv, *xs, *xs2, *y, *Y, *kst, *yacc, *rdiag, *tau, *scal, *fm, *facc;
-    int *flag;
     int m;
 };
 
@@ -96,7 +94,6 @@ __device__ __forceinline__ Mem<N> carve(double *base, int jv, int m)
     S.rdiag = base + c.o_rdiag();
     S.tau = base + c.o_tau();
     S.scal = base + c.o_scal();
-    S.flag = reinterpret_cast<int *>(base + c.o_flag());
     S.fm = base + c.o_fm();
     S.facc = base + c.o_facc();
     S.m = m;
@@ -456,7 +453,7 @@ __device__ __forceinline__ void qr(const Mem<N> &S, int c, bool live, double (&c
             }
         }
     }
-    if (live && S.fm != nullptr) {
+    if (live) {
         double *fmc = S.fm + c;
 #pragma unroll
         for (int i = 0; i < N; ++i) fmc[i * m] = col[i];
@@ -615,132 +612,7 @@ __device__ __forceinline__ void qr_rolled(const Mem<N> &S, int c, bool live, dou
     qr_formq_group<N, B2, N>(S, c, live, col);
     qr_formq_group<N, B1, B2>(S, c, live, col);
     qr_formq_group<N, 0, B1>(S, c, live, col);
-    if (live && S.fm != nullptr) {
-        double *fmc = S.fm + c;
-#pragma unroll
-        for (int i = 0; i < N; ++i) fmc[i * m] = col[i];
-    }
-}
-
-// ---- the same factorisation PIPELINED: flags instead of block barriers ------------------------------------------------
-// qr / qr_rolled march all warps of the block through the reflectors in lockstep: publish, __syncthreads, consume --
-// 36 times per step, and between two barriers every warp walks the same latency chain (broadcast loads -> dot
-// products -> square root -> reciprocals -> update -> publish), so the FP64 pipe idles most of the time (ncu, round 1:
-// barrier + wait are the top stalls of this phase, 31 % of the samples for 20 % of the instructions).  Here a column's
-// owner publishes its reflector and bumps the member's progress counter in shared memory; a consumer waits only for
-// the counter of ITS member to pass j.  With the columns dealt member-index-fastest a warp holds a few consecutive
-// columns of all members: the chain of owners runs through one warp at a time while the other warps apply the
-// reflectors already published to their own columns at their own pace, and a warp whose columns are all finished
-// leaves the loop.  Same arithmetic as qr_rolled (reflector groups, masked rows).
-template <int N, int JB, int JE>
-__device__ __forceinline__ void qr_factor_group_async(const Mem<N> &S, int c, bool live, double (&col)[N], double *Rout)
-{
-    constexpr int RB = JB & ~1;
-    constexpr int NP = (N - RB) / 2;
-    const int m = S.m;
-    double *V = S.facc;
-    volatile int *pub = S.flag;
-    const int jend = JE < m ? JE : m;
-#pragma unroll 1
-    for (int j = JB; j < jend; ++j) {
-        const bool part = live && c >= j;
-        if (!__any_sync(0xffffffffu, part)) break;         // every column of this warp is finished (c only matters >= j)
-        double *x = V + j * N;
-        if (part && c == j) {
-#pragma unroll
-            for (int i = RB; i < N; i += 2) *reinterpret_cast<double2 *>(x + i) = make_double2(col[i], col[i + 1]);
-            __threadfence_block();
-            *pub = j + 1;
-        }
-        __syncwarp();
-        if (part) {
-            if (c != j) {
-                while (*pub <= j) {
-                }
-                __threadfence_block();
-            }
-            double2 xr[NP];
-#pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                const int i = RB + 2 * q;
-                xr[q] = *reinterpret_cast<const double2 *>(x + i);
-                if (i < JE) {                                  // rows that can be <= j in this group
-                    if (i <= j) xr[q].x = 0.;
-                    if (i + 1 <= j) xr[q].y = 0.;
-                }
-            }
-            double d0 = 0., d1 = 0., d2 = 0., d3 = 0., n0 = 0., n1 = 0., n2 = 0., n3 = 0.;
-#pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                const int i = RB + 2 * q;
-                if (q & 1) {
-                    d0 = fma(xr[q].x, col[i], d0);
-                    n0 = fma(xr[q].x, xr[q].x, n0);
-                    d1 = fma(xr[q].y, col[i + 1], d1);
-                    n1 = fma(xr[q].y, xr[q].y, n1);
-                } else {
-                    d2 = fma(xr[q].x, col[i], d2);
-                    n2 = fma(xr[q].x, xr[q].x, n2);
-                    d3 = fma(xr[q].y, col[i + 1], d3);
-                    n3 = fma(xr[q].y, xr[q].y, n3);
-                }
-            }
-            const double alpha = x[j];
-            const double nrm2 = (n0 + n1) + (n2 + n3), dot = (d0 + d1) + (d2 + d3);
-            double beta = alpha, tau = 0., scal = 0.;
-            if (nrm2 != 0.) {
-                beta = -copysign(sqrt(fma(alpha, alpha, nrm2)), alpha);
-                tau = (beta - alpha) * fast_rcp(beta);
-                scal = fast_rcp(alpha - beta);
-            }
-            double cj = 0.;
-#pragma unroll
-            for (int i = JB; i < JE; ++i)
-                if (i == j) cj = col[i];
-            if (c == j) {
-                cj = beta;
-                S.rdiag[j] = beta;
-                S.tau[j] = tau;
-                S.scal[j] = scal;
-            } else {
-                const double w = tau * fma(dot, scal, cj);
-                cj -= w;
-                const double ws = -(w * scal);
-#pragma unroll
-                for (int q = 0; q < NP; ++q) {
-                    const int i = RB + 2 * q;
-                    col[i] = fma(ws, xr[q].x, col[i]);
-                    col[i + 1] = fma(ws, xr[q].y, col[i + 1]);
-                }
-            }
-#pragma unroll
-            for (int i = JB; i < JE; ++i)
-                if (i == j) col[i] = cj;
-            if (Rout != nullptr) Rout[j * m + c] = cj;
-        }
-    }
-}
-
-template <int N>
-__device__ __forceinline__ void qr_async(const Mem<N> &S, int c, bool live, double (&col)[N], double *Rout)
-{
-    static_assert(N % 2 == 0, "rows are processed in aligned pairs");
-    constexpr int B1 = (N / 3) & ~1, B2 = (2 * N / 3) & ~1;
-    const int m = S.m;
-    if (live && c == 0) *S.flag = 0;
-    __syncthreads();                       // every thread is done with its private facc column; counters are reset
-    qr_factor_group_async<N, 0, B1>(S, c, live, col, Rout);
-    qr_factor_group_async<N, B1, B2>(S, c, live, col, Rout);
-    qr_factor_group_async<N, B2, N>(S, c, live, col, Rout);
-    if (Rout != nullptr && live)
-        for (int i = c + 1; i < m; ++i) Rout[i * m + c] = 0.;   // strictly lower part of column c
-    __syncthreads();                       // every reflector, tau and scal are published
-#pragma unroll
-    for (int i = 0; i < N; ++i) col[i] = i == c ? 1. : 0.;
-    qr_formq_group<N, B2, N>(S, c, live, col);
-    qr_formq_group<N, B1, B2>(S, c, live, col);
-    qr_formq_group<N, 0, B1>(S, c, live, col);
-    if (live && S.fm != nullptr) {
+    if (live) {
         double *fmc = S.fm + c;
 #pragma unroll
         for (int i = 0; i < N; ++i) fmc[i * m] = col[i];
@@ -817,37 +689,8 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
     }
 }
 
-// ---- one nonlinear step of every member (split Benettin loop: the stored-trajectory point of lyapunov.py:601 / :622 when
-// the tangent model took several micro steps) -- the very nl_step of the fused kernel, so the results are bitwise its own
-template <int N>
-__global__ void __launch_bounds__(MAX_THREADS, 1)
-nl_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride)
-{
-    extern __shared__ __align__(16) double smem_pack[];
-    const ShTab tab = stage_tables(tab_g, smem_pack + (size_t)G * stride, N);
-    const int m = P.m, t = threadIdx.x;
-    const int g = t / m, c = t - g * m;
-    const long member = (long)blockIdx.x * G + g;
-    const bool live = g < G && member < P.n_members;
-    const Mem<N> S = carve<N>(smem_pack + (size_t)(live ? g : 0) * stride, 0, m);
-    if (live) {
-        for (int r = c; r < N; r += m) {
-            S.Y[r] = P.y[member * N + r];
-            S.kst[r] = 0.;
-            S.yacc[r] = 0.;
-        }
-        if (c == 0) S.xs[0] = 1.;
-    }
-    __syncthreads();
-    nl_step<N>(T, tab, P, S, P.dt_step, c, live);
-    if (live)
-        for (int r = c; r < N; r += m) P.y[member * N + r] = S.Y[r];
-}
-
 // ---- Benettin loop (lyapunov.py:471-632) ---------------------------------------------------------------------------------
-// QRM: the re-orthonormalisation -- 0 unrolled with a block barrier per reflector (qr), 1 rolled (qr_rolled),
-// 2 pipelined: rolled, flags instead of barriers (qr_async)
-template <int N, class Prod, int QRM>
+template <int N, class Prod, bool ROLLED>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride, int qr_remap)
 {
@@ -940,9 +783,7 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
                     for (int i = 0; i < N; ++i) col[i] = Sq.fm[i * m + cq];
                 }
             }
-            if (QRM == 2)
-                qr_async<N>(Sq, cq, liveq, col, Rout);
-            else if (QRM == 1)
+            if (ROLLED)
                 qr_rolled<N>(Sq, cq, liveq, col, Rout);
             else
                 qr<N>(Sq, cq, liveq, col, Rout);
@@ -990,98 +831,6 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
     }
 }
 
-// ---- the re-orthonormalisation as its own launch ---------------------------------------------------------------------
-// One Benettin step = tangent propagation (tgls_kernel, one launch) + this kernel.  Why two launches beat the fused
-// lyap_kernel for large ensembles: inside the fused kernel the tangent phase costs 84k cycles per block and step where
-// tgls_kernel alone needs 38k -- the fused step body (product + 186 KB of unrolled reflectors) is streamed from L2 by
-// every warp once per step (stall "no instruction" 1.1 per issue), and 255 registers allow ONE block per SM, so the
-// latency chain of the factorisation (36 reflectors x ~45 dependent FP64 instructions) idles the whole SM.  Here the
-// code of a launch is resident, the kernel needs half the registers, and two blocks per SM overlap their chains.
-// The state crosses L2 / HBM between the launches: 2 x 8 n m bytes per member and launch, read and written as whole
-// contiguous blocks of G matrices.
-// Shared memory per member: the n x m matrix area (input staging, then the published reflectors, then output staging)
-// and the three scalar arrays.
-template <int N>
-struct QrCarve {
-    int nm, mp;
-    __host__ __device__ QrCarve(int m) : nm(even(N * m)), mp(even(m)) {}
-    __host__ __device__ int o_v() const { return 0; }
-    __host__ __device__ int o_rdiag() const { return nm; }
-    __host__ __device__ int o_tau() const { return o_rdiag() + mp; }
-    __host__ __device__ int o_scal() const { return o_tau() + mp; }
-    __host__ __device__ int o_flag() const { return o_scal() + mp; }
-    __host__ __device__ int total() const
-    {
-        int t = o_flag() + 2;
-        while (t % 16 != 2) t += 2;      // members of one warp read the same offset of their own area: spread the banks
-        return t;
-    }
-};
-
-template <int N, int QRM, int BLOCKS>
-__global__ void __launch_bounds__(MAX_THREADS, BLOCKS)
-qr_kernel(const __grid_constant__ TgParams P, int G, int stride)
-{
-    extern __shared__ __align__(16) double smem_pack[];
-    const int m = P.m, t = threadIdx.x, nm = N * m;
-    const long member0 = (long)blockIdx.x * G;
-    const int members = (int)min((long)G, P.n_members - member0);
-    // the block's matrices are contiguous in HBM: coalesced copy into the members' areas (row-major n x m each)
-    {
-        const double *src = P.fm + (size_t)member0 * nm;
-        const int total = members * nm;
-        for (int q = t; q < total; q += blockDim.x) {
-            const int g = q / nm;
-            smem_pack[(size_t)g * stride + (q - g * nm)] = src[q];
-        }
-    }
-    // columns dealt member-index-fastest: a warp holds the same few columns of all members (see lyap_kernel)
-    const int c = t / G, g = t - c * G;
-    const bool live = c < m && g < members;
-    const long member = member0 + g;
-    const QrCarve<N> cv(m);
-    double *base = smem_pack + (size_t)(live ? g : 0) * stride;
-    Mem<N> S;
-    S.jv = S.xs = S.xs2 = S.y = S.Y = S.kst = S.yacc = nullptr;
-    S.facc = base + cv.o_v();
-    S.fm = nullptr;                       // the factorisations keep Q in registers; it is staged out below
-    S.rdiag = base + cv.o_rdiag();
-    S.tau = base + cv.o_tau();
-    S.scal = base + cv.o_scal();
-    S.flag = reinterpret_cast<int *>(base + cv.o_flag());
-    S.m = m;
-    __syncthreads();
-    double col[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) col[i] = live ? S.facc[i * m + c] : 0.;
-    if (live && P.mexp_g != nullptr && P.dt_step != 0.)                   // lyapunov.py:611 / :531
-        P.mexp_g[member * m + c] = log(fabs(P.rdiag_g[member * m + c])) / P.dt_step;
-    double *Rout = (P.r_all != nullptr && P.r_step >= 0 && live)
-                       ? P.r_all + ((size_t)member * P.r_count + P.r_step) * m * m : nullptr;
-    // (the factorisations start with a barrier: every column is in registers before the area is overwritten)
-    if (QRM == 2)
-        qr_async<N>(S, c, live, col, Rout);
-    else if (QRM == 1)
-        qr_rolled<N>(S, c, live, col, Rout);
-    else
-        qr<N>(S, c, live, col, Rout);
-    __syncthreads();                       // every thread is done reading the reflectors
-    if (live) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) S.facc[i * m + c] = col[i];
-        P.rdiag_g[member * m + c] = S.rdiag[c];
-    }
-    __syncthreads();
-    {
-        double *dst = P.fm + (size_t)member0 * nm;
-        const int total = members * nm;
-        for (int q = t; q < total; q += blockDim.x) {
-            const int gg = q / nm;
-            dst[q] = smem_pack[(size_t)gg * stride + (q - gg * nm)];
-        }
-    }
-}
-
 // ---- host side ----------------------------------------------------------------------------------------------------------
 // table_bytes: size of the ELL tables, which are always staged in shared memory behind the members' areas
 template <int N>
@@ -1110,58 +859,13 @@ inline size_t table_bytes(const PackTables &tab, int n)
     return b;
 }
 
-// launches the packed kernel for one policy pair; returns cudaErrorInvalidValue when it does not fit.
-// mode 0: tangent-linear integration, 1: fused Benettin loop, 2: one re-orthonormalisation (qr_kernel),
-// 3: one nonlinear step (nl_kernel)
+// launches the packed kernel for one policy pair; returns cudaErrorInvalidValue when it does not fit
 template <int N, class Fwd, class Adj>
-inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTables &tables, int mode,
+inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTables &tables, bool lyap,
                           size_t smem_limit, cudaStream_t stream)
 {
     static_assert(Fwd::JV == Adj::JV, "both directions of a product share one Jacobian layout");
     if (P.m < 1 || P.m > MAX_THREADS) return cudaErrorInvalidValue;
-    // QGSB_QR_MODE = 0 (unrolled, a block barrier per reflector) | 1 (rolled) | 2 (pipelined: flags instead of
-    // barriers); see the comments at qr / qr_rolled / qr_async and profiles/ for the A/B measurements
-    const char *qenv = getenv("QGSB_QR_MODE");
-    if (mode == 2) {
-        const QrCarve<N> cv(P.m);
-        const size_t per_member = (size_t)cv.total() * sizeof(double);
-        int G = MAX_THREADS / P.m;
-        if (const char *env = getenv("QGSB_QR_G")) G = std::max(1, std::min(G, atoi(env)));      // A/B measurements
-        G = std::min<int>(G, (int)(smem_limit / per_member));
-        if (G < 1) return cudaErrorInvalidValue;
-        const int threads = ((G * P.m + 31) / 32) * 32;
-        const size_t smem = (size_t)G * per_member;
-        const unsigned blocks = (unsigned)((P.n_members + G - 1) / G);
-        const int qmode = qenv ? atoi(qenv) : (3 * P.m <= N ? 1 : 0);
-        auto go_qr = [&](auto kernel) -> cudaError_t {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            kernel<<<blocks, threads, smem, stream>>>(P, G, cv.total());
-            return cudaGetLastError();
-        };
-        // two blocks per SM (128 registers: the unrolled factorisation spills) or one (no spills, one chain per SM)
-        const char *benv = getenv("QGSB_QR_BLOCKS");
-        const int per_sm = benv ? atoi(benv) : 2;
-        if (per_sm >= 2) {
-            if (qmode == 2) return go_qr(qr_kernel<N, 2, 2>);
-            if (qmode == 1) return go_qr(qr_kernel<N, 1, 2>);
-            return go_qr(qr_kernel<N, 0, 2>);
-        }
-        if (qmode == 2) return go_qr(qr_kernel<N, 2, 1>);
-        if (qmode == 1) return go_qr(qr_kernel<N, 1, 1>);
-        return go_qr(qr_kernel<N, 0, 1>);
-    }
-    if (mode == 3) {                       // one nonlinear step of length P.dt_step on P.y
-        const Geometry g3 = geometry<N>(0, P.m, smem_limit, table_bytes(tables, N));
-        if (g3.G < 1) return cudaErrorInvalidValue;
-        if (g3.smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(nl_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g3.smem);
-            if (e != cudaSuccess) return e;
-        }
-        nl_kernel<N><<<(unsigned)((P.n_members + g3.G - 1) / g3.G), g3.threads, g3.smem, stream>>>(T, P, tables, g3.G,
-                                                                                                  g3.stride);
-        return cudaGetLastError();
-    }
     const Geometry geo = geometry<N>(Fwd::JV, P.m, smem_limit, table_bytes(tables, N));
     if (geo.G < 1) return cudaErrorInvalidValue;
     const PackTables &tab = tables;
@@ -1184,13 +888,18 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
         kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, tab, geo.G, geo.stride, remap);
         return cudaGetLastError();
     };
-    if (mode == 1) {
+    if (lyap) {
         // few vectors: the rolled factorisation (one resident loop body instead of n_vec unrolled reflectors) is faster
-        // [B200: MAOOAM-36, 10 vectors +12 %; 36 vectors -9 %]
-        const int qmode = qenv ? atoi(qenv) : (3 * P.m <= N ? 1 : 0);
-        if (qmode == 2) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 2>) : go_lyap(lyap_kernel<N, Fwd, 2>);
-        if (qmode == 1) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 1>) : go_lyap(lyap_kernel<N, Fwd, 1>);
-        return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 0>) : go_lyap(lyap_kernel<N, Fwd, 0>);
+        // [B200: MAOOAM-36, 10 vectors +19 %; 36 vectors -8 %]; QGSB_QR_ROLLED=0/1 forces one of them.
+        // Two other forms were measured in round 2 and removed (profiles/r02_benettin_qr_pipelined_ab.log,
+        // r02_benettin_split_ab.log): reflectors handed over through progress flags instead of block barriers
+        // (-16 %: the factorisation is ONE dependent chain per block, the other warps have nothing to overlap it with),
+        // and the step as two launches, propagation + stand-alone QR with two blocks per SM (-15 %: 26 % / 33 % of
+        // the two kernels go into moving the state through L2, and at 128 registers the factorisation spills).
+        const char *env = getenv("QGSB_QR_ROLLED");
+        const bool rolled = env ? (env[0] != '0') : (3 * P.m <= N);
+        if (rolled) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, true>) : go_lyap(lyap_kernel<N, Fwd, true>);
+        return P.adjoint ? go_lyap(lyap_kernel<N, Adj, false>) : go_lyap(lyap_kernel<N, Fwd, false>);
     }
     return P.adjoint ? go(tgls_kernel<N, Adj>) : go(tgls_kernel<N, Fwd>);
 }

@@ -40,11 +40,6 @@ struct TgParams {
     long r_first;
     double *q_all;            // (N, n_rec + 1, n, m) or null
     int qr_at_start;          // != 0: fm holds a raw start matrix; factorise it before the first step (lyapunov.py:592-593)
-    // --- split Benettin step: the re-orthonormalisation as its own launch (pack::qr_kernel) ---
-    double *rdiag_g;          // (N, m) diagonal of R of the last factorisation, in / out
-    double *mexp_g;           // (N, m) or null: local exponents log|rdiag_in| / dt_step of the step being closed
-    double dt_step;           // macro step length of the step being closed (0: do not touch mexp_g)
-    long r_step, r_count;     // r_all: R of this launch goes to r_all[(member * r_count + r_step) m m] when r_step >= 0
     // --- placement of the big matrices ---
     double *scratch;          // global scratch when shared memory is too small, else null
     size_t scratch_per_member;
@@ -111,22 +106,13 @@ struct PackTables {
 // slot order of the handle's generated module instead of the dense n x n layout
 const PackTables &pack_tables(const qgsb_tensor *t, bool spec);
 
-// Benettin plumbing shared with clv.cu (tgls.cu).  host: the step tables as HOST arrays (the same values P's device
-// pointers dt_macro / sub_ptr / sub_dt refer to); with them the dispatcher may run the loop as two resident-code
-// launches per step (tangent propagation, re-orthonormalisation) instead of one fused launch, see benettin_split.
-struct BenettinHost {
-    const double *dt_macro = nullptr;
-    const long *sub_ptr = nullptr;
-    const double *sub_dt = nullptr;
-};
-void benettin_dispatch(const qgsb_tensor *t, const Tableau &tab, TgParams &P, DevBuf<double> &scratch,
-                       const BenettinHost *host = nullptr);
+// Benettin plumbing shared with clv.cu (tgls.cu)
+void benettin_dispatch(const qgsb_tensor *t, const Tableau &tab, TgParams &P, DevBuf<double> &scratch);
 void benettin_fill_common(TgParams &P, const Tableau &tab, long N, int m, int adjoint, double inverse);
 void launch_transpose_records(const double *d_in, double *d_out, long R, long inner, int flip);
 
 // packed kernels (tgls_pack.cu / tgls_pack.cuh)
 bool pack_tangent_supported(const qgsb_tensor *t, const Tableau &tab, int m);
-// mode 0: tangent-linear integration (integrate.py:555-614), 1: fused Benettin loop, 2: one re-orthonormalisation
-void launch_pack_tangent(const qgsb_tensor *t, const TgParams &P, int mode);
+void launch_pack_tangent(const qgsb_tensor *t, const TgParams &P, bool lyap);
 
 }  // namespace qgsb

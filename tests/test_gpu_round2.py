@@ -59,30 +59,25 @@ def _benettin(name, N, n_vec, q0, r0, seed=None, vectors=True, mode=0, mdt=0.1, 
     return benettin(f, Df, ic, mode, n_vec, q0, r0, pre, tim, mdt, 3, False, 1., b, c, a, want_vectors=vectors, seed=seed)
 
 
-# ---- the three re-orthonormalisations are the same arithmetic ------------------------------------------------------------
+# ---- the re-orthonormalisations are the same arithmetic -----------------------------------------------------------------
 @pytest.mark.parametrize("name,n_vec", [("maooam36", 36), ("maooam36", 10), ("rp", 20), ("dynT", 38)])
-def test_pipelined_qr_is_bitwise_the_barrier_qr(name, n_vec):
-    """QGSB_QR_MODE 0 (unrolled, one block barrier per reflector), 1 (rolled) and 2 (pipelined: flags instead of
-    barriers, the default) differ in synchronisation and in rows that are multiplied by an explicit zero, never in a
-    value: trajectories, exponents and vectors must be IDENTICAL.  (The default mode is the one the golden tests of
-    test_gpu_parity.py compare with the reference's np.linalg.qr.)"""
+def test_rolled_and_unrolled_qr_are_bitwise_equal(name, n_vec):
+    """The unrolled Householder factorisation (one code block per reflector) and the rolled one (three reflector groups,
+    rows <= j multiplied by an explicit zero) differ in instruction bytes, never in a value; neither does the way the
+    columns are dealt to the threads (QGSB_QR_REMAP).  Trajectories, exponents and vectors must be IDENTICAL.  (The
+    defaults are what the golden tests of test_gpu_parity.py compare with the reference's np.linalg.qr.)"""
     f, Df, T = model(name)
     n = f.ndim
     N = 23                                     # not a multiple of the members per block: partially filled last block
     rng = np.random.default_rng(8)
     q0 = np.stack([np.linalg.qr(rng.random((n, n_vec)))[0] for _ in range(N)])
     out = []
-    for mode in ("0", "1", "2"):
-        with env(QGSB_QR_MODE=mode):
+    for rolled, remap in (("0", "1"), ("1", "1"), ("0", "0"), ("1", "0")):
+        with env(QGSB_QR_ROLLED=rolled, QGSB_QR_REMAP=remap):
             out.append(_benettin(name, N, n_vec, q0, None))
     for other in out[1:]:
         for x, y in zip(out[0], other):
             assert np.array_equal(x, y)
-    # and with the other dealing of the columns to threads (member-consecutive instead of member-fastest)
-    with env(QGSB_QR_MODE="2", QGSB_QR_REMAP="0"):
-        alt = _benettin(name, N, n_vec, q0, None)
-    for x, y in zip(out[0], alt):
-        assert np.array_equal(x, y)
 
 
 # ---- start bases drawn on the device -------------------------------------------------------------------------------------
@@ -253,43 +248,6 @@ def test_maooam36_long_run_moments_and_leading_exponents_match_the_oracle():
     ze = np.abs(ge.mean(axis=0) - oe.mean(axis=0)) / np.maximum(se_e, 1e-6)
     assert np.all(ze[:6] < 4.), (ze, ge.mean(axis=0), oe.mean(axis=0))
     assert ge.mean(axis=0)[0] > 0.                                # MAOOAM at these parameters is chaotic
-
-
-# ---- one Benettin step as two launches -----------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,n_vec", [("maooam36", 36), ("maooam36", 10), ("rp", 20), ("dynT", 38)])
-def test_split_benettin_loop_is_bitwise_the_fused_kernel(name, n_vec):
-    """Large ensembles run a Benettin step as two launches (tangent propagation; batched Householder QR, two blocks per
-    SM) instead of one fused kernel.  Same device functions, same arithmetic: trajectories, exponents and vectors are
-    IDENTICAL -- with a host start basis, with a device-drawn one, with and without vector records, for every QR mode
-    and block count of the stand-alone factorisation."""
-    f, Df, T = model(name)
-    n = f.ndim
-    N = 45
-    rng = np.random.default_rng(8)
-    q0 = np.stack([np.linalg.qr(rng.random((n, n_vec)))[0] for _ in range(N)])
-    r0 = np.stack([np.triu(rng.random((n_vec, n_vec))) + np.eye(n_vec) for _ in range(N)])
-    for start in ((q0, r0), (None, None)):
-        for vectors in (True, False):
-            with env(QGSB_BENETTIN_SPLIT="0"):
-                fused = _benettin(name, N, n_vec, start[0], start[1], seed=31, vectors=vectors)
-            for blocks, mode in (("2", None), ("1", None), ("2", "1"), ("2", "2"), ("1", "0")):
-                with env(QGSB_BENETTIN_SPLIT="1", QGSB_QR_BLOCKS=blocks, QGSB_QR_MODE=mode):
-                    split = _benettin(name, N, n_vec, start[0], start[1], seed=31, vectors=vectors)
-                for x, y in zip(fused, split):
-                    assert (x is None and y is None) or np.array_equal(x, y), (blocks, mode, vectors)
-
-
-def test_split_benettin_loop_follows_micro_steps_in_ginelli_mode():
-    """Mode 2 (the Ginelli forward pass: the trajectory follows the micro steps, lyapunov.py:1212-1218) with several
-    micro steps per step runs split too; mode 0 with micro steps keeps the fused kernel (the stored trajectory point is
-    a separate nonlinear step there).  Both must equal the fused results."""
-    for mode, mdt in ((2, 0.05), (0, 0.05), (2, 0.1)):
-        with env(QGSB_BENETTIN_SPLIT="0"):
-            fused = _benettin("maooam36", 20, 36, None, None, seed=3, mode=mode, mdt=mdt)
-        with env(QGSB_BENETTIN_SPLIT="1"):
-            split = _benettin("maooam36", 20, 36, None, None, seed=3, mode=mode, mdt=mdt)
-        for x, y in zip(fused, split):
-            assert np.array_equal(x, y), (mode, mdt)
 
 
 # ---- initialize() on resident device batches ------------------------------------------------------------------------------
