@@ -23,6 +23,13 @@ import numpy as np
 
 __all__ = ["COO", "DOK", "zeros", "tensordot"]
 
+# Arrays up to this many elements (32 MB dense) are sliced and multiplied through a dense copy built once: numpy's
+# BLAS-backed products then give what qgs gets from its small dense inverse matrices (and what the tensor fixtures under
+# tests/golden were built with), and the hundreds of thousands of slices qgs takes of its inner-product arrays cost
+# O(slice).  Larger arrays -- the model tensors themselves, (ndim + 1)**3 or **5 elements -- only ever exist as
+# coordinate lists.
+DENSE_LIMIT = 1 << 22
+
 
 def _canonical(coords, data, shape):
     """Lexicographic order, duplicates summed (in input order, like ``np.add.at``), zeros dropped."""
@@ -48,8 +55,12 @@ def _canonical(coords, data, shape):
         flat, coords, data = flat[order], coords[:, order], data[order]
         new = np.concatenate(([True], flat[1:] != flat[:-1]))
     if not new.all():
+        # strictly sequential sums in input order (what np.add.at into a dense array does, and what the fixtures under
+        # tests/golden were built with): np.add.reduceat would sum long runs pairwise and differ in the last bit
         starts = np.flatnonzero(new)
-        data = np.add.reduceat(data, starts)
+        summed = np.zeros(len(starts))
+        np.add.at(summed, np.cumsum(new) - 1, data)
+        data = summed
         coords = coords[:, starts]
     keep = data != 0.
     if not keep.all():
@@ -130,10 +141,20 @@ class COO(object):
         return "<COO: shape=%s, nnz=%d>" % (self.shape, self.nnz)
 
     def todense(self):
-        out = np.zeros(self.shape)
-        if self.nnz:
-            out[tuple(self.coords)] = self.data
-        return out
+        return self._dense().copy()
+
+    def _dense(self):
+        """Dense view of a SMALL array, built once (the object is immutable).  qgs slices its inner-product arrays
+        hundreds of thousands of times (``aips._b[offset:, jo, ko]`` for every j, k): slicing a dense copy is O(slice),
+        masking the coordinate list would be O(nnz) per call."""
+        cached = getattr(self, "_dense_cache", None)
+        if cached is None:
+            cached = np.zeros(self.shape)
+            if self.nnz:
+                cached[tuple(self.coords)] = self.data
+            if self.size <= DENSE_LIMIT:
+                self._dense_cache = cached
+        return cached
 
     def __array__(self, dtype=None, copy=None):
         return self.todense() if dtype is None else self.todense().astype(dtype)
@@ -171,6 +192,12 @@ class COO(object):
         if len(key) > self.ndim:
             raise IndexError("too many indices for a %d-dimensional array" % self.ndim)
         key = key + (slice(None),) * (self.ndim - len(key))
+        if self.size <= DENSE_LIMIT:
+            for k in key:
+                if isinstance(k, slice) and k.step not in (None, 1):
+                    raise NotImplementedError("only unit-step slices are supported")
+            part = self._dense()[key]
+            return COO(part) if isinstance(part, np.ndarray) and part.ndim > 0 else float(part)
         mask = np.ones(self.nnz, dtype=bool)
         kept, shape, shift = [], [], []
         for axis, k in enumerate(key):
@@ -300,12 +327,6 @@ def _contract(a, b, axis_a, axis_b):
     return COO(coords, data, shape=shape)
 
 
-# Operands up to this many elements are multiplied as dense arrays: numpy's BLAS-backed products then give, bit for bit,
-# what qgs gets from its small dense inverse matrices (and what the tensor fixtures under tests/golden were built with);
-# larger operands -- only the rank-5 tensors of big bases -- go through the coordinate join of _contract.
-DENSE_LIMIT = 1 << 22
-
-
 def _wrap(result):
     if isinstance(result, np.ndarray) and result.ndim > 0:
         return COO(result)
@@ -317,7 +338,7 @@ def _matmul(a, b):
     if a.ndim == 0 or b.ndim == 0:
         raise ValueError("matmul: scalar operands are not allowed")
     if a.size <= DENSE_LIMIT and b.size <= DENSE_LIMIT and a.ndim <= 2 and b.ndim <= 2:
-        return _wrap(np.matmul(a.todense(), b.todense()))
+        return _wrap(np.matmul(a._dense(), b._dense()))
     return _contract(a, b, a.ndim - 1, 0 if b.ndim == 1 else b.ndim - 2)
 
 
@@ -329,7 +350,7 @@ def tensordot(a, b, axes=2):
             raise NotImplementedError("tensordot over %d axes" % axes)
         a, b = _as_coo(a), _as_coo(b)
         if a.size <= DENSE_LIMIT and b.size <= DENSE_LIMIT:
-            return _wrap(np.tensordot(a.todense(), b.todense(), axes=1))
+            return _wrap(np.tensordot(a._dense(), b._dense(), axes=1))
         return _contract(a, b, a.ndim - 1, 0)
     ax_a, ax_b = axes
     if not isinstance(ax_a, (int, np.integer)):
