@@ -1064,6 +1064,17 @@ void rk_advance(const qgsb_tensor *t, double *d_y, long ld, long N, long n_steps
         count_launch();
         return;
     }
+    if (t->spec && t->use_spec && !tab.chain && tab.s <= 8 && t->spec->rk_general) {
+        // any other explicit tableau on the tensor-specialised code (stage derivatives in shared memory)
+        const cudaError_t e = t->spec->rk_general(d_y, ld, N, n_steps, d_dt, tab.s, tab.a.data(), tab.b.data(),
+                                                  write_steps, R, d_rec, ctx().smem_optin, ctx().stream);
+        if (e == cudaSuccess) {
+            count_launch();
+            return;
+        }
+        QGSB_REQUIRE(e == cudaErrorInvalidValue, "specialised Runge-Kutta launch failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();                 // too many stages for shared memory: the generic kernel below serves
+    }
     RkParams P;
     fill_params(P, tab, d_y, ld, N, n_steps, d_dt, write_steps, R, d_rec);
     const int n = t->view.n;

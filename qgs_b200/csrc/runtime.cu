@@ -280,6 +280,7 @@ void register_spec(const SpecKernels *k)
     }
     SpecKernels &m = it->second;
     if (k->rk_chain) m.rk_chain = k->rk_chain;
+    if (k->rk_general) m.rk_general = k->rk_general;
     if (k->tendencies) m.tendencies = k->tendencies;
     if (k->tangent) {
         m.tangent = k->tangent;

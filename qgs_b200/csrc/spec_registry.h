@@ -19,7 +19,7 @@ struct PackTables;   // tgls_shared.cuh
 // Layout version of SpecKernels / TgParams / PackTables / the packed kernels' shared-memory carve-up as a module was
 // compiled against them.  Bump it whenever one of those changes: qgsb_load_plugin refuses a module built against
 // another version instead of reading its table with the wrong layout (modules cached on disk outlive a library).
-#define QGSB_SPEC_ABI 5u
+#define QGSB_SPEC_ABI 7u
 
 struct SpecKernels {
     uint32_t abi;   // QGSB_SPEC_ABI of the headers the module was compiled with -- must stay the FIRST member
@@ -44,6 +44,12 @@ struct SpecKernels {
     const short *jac_slot_table;   // (n, n) row-major: slot of position (i, j), -1 where J_ij is structurally zero
     uint64_t jac_hash;             // != 0: the tangent product has the Jacobian tensor's VALUES baked in (bilinear
                                    // form); FNV-1a over its (i, j)-sorted entries -- see jacobian_hash()
+    // Runge-Kutta with ANY explicit tableau (a (s, s) row-major, j < i read; integrate.py:214-219): the stage
+    // derivatives live in shared memory.  Null in modules too large to carry a second copy of f; returns
+    // cudaErrorInvalidValue when s + 1 state sets exceed smem_limit (the caller then uses the generic kernel).
+    cudaError_t (*rk_general)(double *d_y, long ld, long n_members, long n_steps, const double *d_dt, int s,
+                              const double *a, const double *beta, long write_steps, long n_records, double *d_rec,
+                              size_t smem_limit, cudaStream_t stream);
 };
 
 void register_spec(const SpecKernels *k);

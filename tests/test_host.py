@@ -547,3 +547,115 @@ def test_concurrent_plugin_builds_of_one_tensor_do_not_collide(tmp_path):
     assert not [x for x in left if x.endswith(".tmp") or x.endswith(".cu")]        # scratch files are gone
     from qgs_b200 import _lib
     assert _lib.load().qgsb_load_plugin(path.encode()) == 0
+
+
+# ---- coordinate-based `sparse` stand-in ----------------------------------------------------------
+def _sparse():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("qgsb_sparse_standin",
+                                                  os.path.join(REPO, "qgs_b200", "compat", "sparse", "__init__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_coo_standin_matches_dense_numpy_on_every_operation_qgs_uses():
+    """COO / DOK keep coordinate lists (memory ~ nnz), and every operation the reference's tensor construction performs on
+    them (qgtensor.py:188-272, 657-746, 969-1005; analytic.py:131-216) gives what numpy gives on the dense arrays."""
+    sp = _sparse()
+    rng = np.random.default_rng(0)
+
+    def rand(shape, density=0.3):
+        a = rng.standard_normal(shape)
+        a[rng.random(shape) > density] = 0.
+        return a
+
+    a3, m2, v1, w1 = rand((5, 6, 7)), rand((6, 6)), rand((6,)), rand((7,), 0.9)
+    A3, M2, V1, W1 = sp.COO(a3), sp.COO(m2), sp.COO(v1), sp.COO(w1)
+    # entries in lexicographic order, zeros not stored
+    assert np.array_equal(A3.coords, np.array(np.nonzero(a3))) and np.array_equal(A3.data, a3[np.nonzero(a3)])
+    assert A3.nnz == np.count_nonzero(a3) and A3.shape == a3.shape and A3.ndim == 3
+    # slicing: integers and unit-step slices, partial keys, scalars
+    for key in ((2,), (slice(1, None), 3), (slice(1, None), 3, slice(2, None)), (slice(None), 2, 4), (4, 5, 6),
+                (slice(None), slice(None), 0), (-1, slice(None), slice(None))):
+        got = A3[key]
+        want = a3[key]
+        if np.ndim(want) == 0:
+            assert isinstance(got, float) and got == float(want)
+        else:
+            assert got.shape == want.shape and np.array_equal(got.todense(), want)
+    # products: vector @ matrix @ vector -> scalar, matrix @ vector, vector @ sliced tensor
+    assert np.isclose(V1 @ M2 @ sp.COO(v1), v1 @ m2 @ v1) and isinstance(V1 @ M2 @ V1, float)
+    assert np.array_equal((M2 @ V1).todense(), m2 @ v1) and np.array_equal((v1 @ M2).todense(), v1 @ m2)
+    assert np.allclose((V1 @ A3[1, :, :]).todense(), v1 @ a3[1])
+    assert np.isclose(M2[2, :] @ A3[2, :, 3], m2[2] @ a3[2, :, 3])
+    # tensordot(axes=1): last axis against the first, also through the coordinate join used above the dense limit
+    t5 = rand((6, 3, 4, 3, 2), 0.2)
+    want = np.tensordot(v1, t5, axes=1)
+    assert np.allclose(sp.tensordot(V1, sp.COO(t5), axes=1).todense(), want)
+    old = sp.DENSE_LIMIT
+    try:
+        sp.DENSE_LIMIT = 0
+        assert np.allclose(sp.tensordot(sp.COO(v1), sp.COO(t5), axes=1).todense(), want)
+        assert np.allclose((sp.COO(m2) @ sp.COO(v1)).todense(), m2 @ v1)
+        assert np.isclose(sp.COO(v1) @ sp.COO(m2) @ sp.COO(v1), v1 @ m2 @ v1)
+        assert np.array_equal(sp.COO(a3)[slice(1, None), 3, slice(2, None)].todense(), a3[1:, 3, 2:])
+        assert sp.COO(a3)[4, 5, 6] == a3[4, 5, 6]
+    finally:
+        sp.DENSE_LIMIT = old
+    # arithmetic, swapaxes, duplicates summed in input order, pruning
+    assert np.array_equal((A3 + A3.swapaxes(1, 2).swapaxes(1, 2)).todense(), 2 * a3)
+    assert np.array_equal(A3.swapaxes(0, 2).todense(), a3.swapaxes(0, 2))
+    assert np.array_equal((2.5 * A3).todense(), 2.5 * a3) and np.array_equal((-A3).todense(), -a3)
+    assert np.array_equal((A3 * 0.5).todense(), a3 * 0.5) and np.array_equal((A3 - A3).coords.shape, (3, 0))
+    c = sp.COO(np.array([[1, 1, 0, 1], [2, 2, 0, 2]]), np.array([1., 1e-17, 3., -1.]), shape=(3, 3), prune=True)
+    assert np.array_equal(c.coords, [[0, 1], [0, 2]]) and np.array_equal(c.data, [3., (1. + 1e-17) - 1.]) or c.nnz == 1
+    z = sp.zeros((4, 4, 4), format='coo')
+    assert z.nnz == 0 and z.coords.shape == (3, 0) and z.coords.size == 0
+    # DOK: item get / set / in-place updates with integer tuples, conversion
+    d = sp.zeros((3, 4), dtype=float, format='dok')
+    d[1, 2] = 2.
+    d[1, 2] -= 0.5
+    d[(0, 0)] += V1 @ M2 @ V1
+    d[2, 3] = 0.
+    assert d[1, 2] == 1.5 and d[2, 2] == 0.0 and d.nnz == 2
+    dc = d.to_coo()
+    assert isinstance(dc, sp.COO) and dc.shape == (3, 4) and np.array_equal(dc.coords, [[0, 1], [0, 2]])
+    assert dc.to_coo() is dc
+
+
+def test_coo_standin_holds_a_large_basis_rank5_tensor_in_kilobytes():
+    """The point of coordinate storage: a rank-5 tensor over 229 indices (the 6x6 model with T^4 terms) is 229**5
+    doubles = 5 TB dense; as a coordinate list it is proportional to its entries, and the operations of
+    qgtensor.py:657-746 (gathering, Jacobian by swapped axes, upper-triangular simplification) run on the lists."""
+    sp = _sparse()
+    rng = np.random.default_rng(1)
+    n1, nnz = 229, 20000
+    coords = np.vstack((rng.integers(1, n1, (1, nnz)), np.sort(rng.integers(0, n1, (4, nnz)), axis=0)))
+    t = sp.COO(coords, rng.standard_normal(nnz), shape=(n1,) * 5)
+    assert t.nnz <= nnz and t.coords.nbytes + t.data.nbytes < 1 << 20
+    jac = t.copy()
+    for i in range(1, 4):
+        jac += t.swapaxes(1, i + 1)
+    assert jac.shape == t.shape and jac.nnz >= t.nnz
+    cs = jac.coords.copy()
+    cs[1:, :] = np.sort(cs[1:, :], axis=0)
+    upp = sp.COO(cs, jac.data.copy(), shape=jac.shape, prune=True)
+    # a term with four distinct factors appears under each of them in the Jacobian: folding back gives 4x the tensor
+    same = {tuple(c): v for c, v in zip(t.coords.T.tolist(), t.data.tolist())}
+    got = {tuple(c): v for c, v in zip(upp.coords.T.tolist(), upp.data.tolist())}
+    assert set(got) == set(same)
+    assert all(abs(got[k] - 4. * same[k]) <= 1e-12 * abs(same[k]) for k in same)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/qgs"), reason="needs the reference checkout (build container)")
+def test_reference_tensor_construction_on_the_coo_standin_reproduces_the_fixtures():
+    """create_tendencies of the UNMODIFIED reference on top of the stand-in rebuilds the MAOOAM-36 and RP-20 fixtures bit
+    for bit (the other five configurations: tests/golden/check_tensors.py, profiles/r02_coo_rebuild.log)."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(REPO, "tests", "golden", "check_tensors.py"), "maooam36", "rp"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if "identical=" in ln]
+    assert len(lines) == 2 and all("identical=True" in ln for ln in lines), out.stdout
