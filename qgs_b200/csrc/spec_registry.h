@@ -19,7 +19,7 @@ struct PackTables;   // tgls_shared.cuh
 // Layout version of SpecKernels / TgParams / PackTables / the packed kernels' shared-memory carve-up as a module was
 // compiled against them.  Bump it whenever one of those changes: qgsb_load_plugin refuses a module built against
 // another version instead of reading its table with the wrong layout (modules cached on disk outlive a library).
-#define QGSB_SPEC_ABI 7u
+#define QGSB_SPEC_ABI 8u
 
 struct SpecKernels {
     uint32_t abi;   // QGSB_SPEC_ABI of the headers the module was compiled with -- must stay the FIRST member

@@ -61,8 +61,7 @@ struct Carve {
     __host__ __device__ int o_rdiag() const { return o_yacc() + even(N); }
     __host__ __device__ int o_tau() const { return o_rdiag() + mp; }
     __host__ __device__ int o_scal() const { return o_tau() + mp; }
-    __host__ __device__ int o_coup() const { return o_scal() + mp; }           // panel coupling coefficients of qr2
-    __host__ __device__ int o_fm() const { return o_coup() + mp; }
+    __host__ __device__ int o_fm() const { return o_scal() + mp; }
     __host__ __device__ int o_facc() const { return o_fm() + nm; }
     __host__ __device__ int total() const
     {
@@ -76,7 +75,7 @@ struct Carve {
 
 template <int N>
 struct Mem {
-    double *jv, *xs, *xs2, *y, *Y, *kst, *yacc, *rdiag, *tau, *scal, *coup, *fm, *facc;
+    double *jv, *xs, *xs2, *y, *Y, *kst, *yacc, *rdiag, *tau, *scal, *fm, *facc;
     int m;
 };
 
@@ -95,7 +94,6 @@ __device__ __forceinline__ Mem<N> carve(double *base, int jv, int m)
     S.rdiag = base + c.o_rdiag();
     S.tau = base + c.o_tau();
     S.scal = base + c.o_scal();
-    S.coup = base + c.o_coup();
     S.fm = base + c.o_fm();
     S.facc = base + c.o_facc();
     S.m = m;
@@ -462,186 +460,6 @@ __device__ __forceinline__ void qr(const Mem<N> &S, int c, bool live, double (&c
     }
 }
 
-// ---- the same factorisation, TWO reflectors per barrier ------------------------------------------------------------------
-// qr<N> above is a chain of m links: publish column j -> barrier -> dot products -> square root, reciprocals -> update ->
-// publish column j + 1 ...; ncu (profiles/r02_lyap_fused_phases.txt) shows ~1000 cycles per link of which the 45
-// dependent FP64 instructions of the scalars are two thirds, with the FP64 pipe mostly idle.  Here the owners of columns
-// j and j + 1 (j even) publish their RAW columns x, y together; every thread forms the five sums
-// x.x, x.y, y.y, x.c, y.c over the rows below j + 1 in one pass (ten independent chains), derives reflector j from x,
-// applies it to y ALGEBRAICALLY (y' = y - a x, so |y'|^2 and y'.c' follow from the five sums), derives reflector j + 1,
-// and updates its own column with both reflectors in one sweep: c'' = c - (b - e a) x - e y.  Half the barriers, half
-// the publish / load round trips, and the dot products of the second reflector no longer wait for the first update.
-// Same reflectors as dgeqr2 (signs, tau, R) up to rounding: the sums are expanded instead of formed from updated
-// vectors; |y'|^2 falls back to the direct sum when the expansion cancels.  For dorg2r the pair (H_j, H_j+1) is applied in
-// one sweep as well, from the raw columns and the coupling coefficient a kept in S.coup[j + 1] (S.coup[j] = x.y' below
-// row j + 1, which the second application needs).
-template <int N>
-__device__ __forceinline__ void qr2(const Mem<N> &S, int c, bool live, double (&col)[N], double *Rout)
-{
-    static_assert(N % 2 == 0, "rows are processed in aligned pairs");
-    const int m = S.m;
-    double *V = S.facc;
-    __syncthreads();                       // every thread is done with its private facc column
-#pragma unroll
-    for (int j = 0; j < N; j += 2) {
-        if (j < m) {                       // uniform
-            const bool two = j + 1 < m;    // uniform: an odd number of vectors ends on a single reflector
-            double *x = V + j * N;
-            double *y = two ? V + (j + 1) * N : x;
-            if (live && (c == j || c == j + 1)) {
-                double *dst = c == j ? x : y;
-#pragma unroll
-                for (int i = j; i < N; i += 2) *reinterpret_cast<double2 *>(dst + i) = make_double2(col[i], col[i + 1]);
-            }
-            __syncthreads();
-            if (live && c >= j) {
-                const double2 xh = *reinterpret_cast<const double2 *>(x + j);      // x_j (alpha), x_j+1
-                const double2 yh = *reinterpret_cast<const double2 *>(y + j);      // y_j, y_j+1 (alpha' before H_j)
-                // the five sums over the rows below j + 1, two chains each
-                double xx0 = 0., xx1 = 0., xy0 = 0., xy1 = 0., yy0 = 0., yy1 = 0., xc0 = 0., xc1 = 0., yc0 = 0., yc1 = 0.;
-#pragma unroll
-                for (int i = j + 2; i < N; i += 2) {
-                    const double2 xi = *reinterpret_cast<const double2 *>(x + i);
-                    const double2 yi = *reinterpret_cast<const double2 *>(y + i);
-                    xx0 = fma(xi.x, xi.x, xx0);
-                    xx1 = fma(xi.y, xi.y, xx1);
-                    xy0 = fma(xi.x, yi.x, xy0);
-                    xy1 = fma(xi.y, yi.y, xy1);
-                    yy0 = fma(yi.x, yi.x, yy0);
-                    yy1 = fma(yi.y, yi.y, yy1);
-                    xc0 = fma(xi.x, col[i], xc0);
-                    xc1 = fma(xi.y, col[i + 1], xc1);
-                    yc0 = fma(yi.x, col[i], yc0);
-                    yc1 = fma(yi.y, col[i + 1], yc1);
-                }
-                const double Sxx2 = xx0 + xx1, Sxy2 = xy0 + xy1, Syy2 = yy0 + yy1, Sxc2 = xc0 + xc1, Syc2 = yc0 + yc1;
-                // reflector j (dlarfg on x)
-                const double nx = fma(xh.y, xh.y, Sxx2);
-                double beta1 = xh.x, tau1 = 0., scal1 = 0.;
-                if (nx != 0.) {
-                    beta1 = -copysign(sqrt(fma(xh.x, xh.x, nx)), xh.x);
-                    tau1 = (beta1 - xh.x) * fast_rcp(beta1);
-                    scal1 = fast_rcp(xh.x - beta1);
-                }
-                // H_j applied to y: y' = y - a x below row j
-                const double wy = tau1 * fma(scal1, fma(xh.y, yh.y, Sxy2), yh.x);
-                const double a = wy * scal1;
-                const double yj = yh.x - wy;                       // R[j][j + 1]
-                const double alpha2 = fma(-a, xh.y, yh.y);
-                // |y'|^2 below row j + 1 from the expanded form; the direct sum when the expansion cancels
-                const double big = fma(a * a, Sxx2, Syy2);
-                double ny = fma(a, fma(a, Sxx2, -2. * Sxy2), Syy2);
-                if (ny < 1e-6 * big) {
-                    double d0 = 0., d1 = 0.;
-#pragma unroll
-                    for (int i = j + 2; i < N; i += 2) {
-                        const double2 xi = *reinterpret_cast<const double2 *>(x + i);
-                        const double2 yi = *reinterpret_cast<const double2 *>(y + i);
-                        const double u0 = fma(-a, xi.x, yi.x), u1 = fma(-a, xi.y, yi.y);
-                        d0 = fma(u0, u0, d0);
-                        d1 = fma(u1, u1, d1);
-                    }
-                    ny = d0 + d1;
-                }
-                double beta2 = alpha2, tau2 = 0., scal2 = 0.;
-                if (two && ny != 0.) {
-                    beta2 = -copysign(sqrt(fma(alpha2, alpha2, ny)), alpha2);
-                    tau2 = (beta2 - alpha2) * fast_rcp(beta2);
-                    scal2 = fast_rcp(alpha2 - beta2);
-                }
-                // own column: H_j, then H_j+1, in one sweep
-                const double wc = tau1 * fma(scal1, fma(xh.y, col[j + 1], Sxc2), col[j]);
-                const double b = wc * scal1;
-                const double cj = col[j] - wc;                      // R[j][c]
-                const double cj1 = fma(-b, xh.y, col[j + 1]);
-                const double d2 = fma(a * b, Sxx2, fma(-a, Sxc2, fma(-b, Sxy2, Syc2)));
-                const double w2 = tau2 * fma(scal2, d2, cj1);
-                const double e = w2 * scal2;
-                const double fx = fma(e, a, -b);                    // c'' = c + fx x - e y below row j + 1
-                if (c == j) {
-                    col[j] = beta1;
-                    S.rdiag[j] = beta1;
-                    S.tau[j] = tau1;
-                    S.scal[j] = scal1;
-                    S.coup[j] = fma(-a, Sxx2, Sxy2);               // x . y' below row j + 1
-                } else if (c == j + 1) {
-                    col[j] = yj;
-                    col[j + 1] = beta2;
-                    S.rdiag[j + 1] = beta2;
-                    S.tau[j + 1] = tau2;
-                    S.scal[j + 1] = scal2;
-                    S.coup[j + 1] = a;
-                } else {
-                    col[j] = cj;
-                    col[j + 1] = cj1 - w2;
-#pragma unroll
-                    for (int i = j + 2; i < N; i += 2) {
-                        const double2 xi = *reinterpret_cast<const double2 *>(x + i);
-                        const double2 yi = *reinterpret_cast<const double2 *>(y + i);
-                        col[i] = fma(fx, xi.x, fma(-e, yi.x, col[i]));
-                        col[i + 1] = fma(fx, xi.y, fma(-e, yi.y, col[i + 1]));
-                    }
-                }
-                if (Rout != nullptr) {
-                    Rout[j * m + c] = col[j];
-                    if (two && c > j) Rout[(j + 1) * m + c] = col[j + 1];
-                }
-            }
-        }
-    }
-    if (Rout != nullptr && live)
-        for (int i = c + 1; i < m; ++i) Rout[i * m + c] = 0.;   // strictly lower part of column c
-    __syncthreads();                       // the last reflectors and the scalars are published
-    // dorg2r: Q[:, c] = H_0 ... H_{m-1} e_c; H_j e_c = e_c for j > c.  Pairs (H_j, H_j+1) from the back.
-#pragma unroll
-    for (int i = 0; i < N; ++i) col[i] = i == c ? 1. : 0.;
-#pragma unroll
-    for (int jj = 0; jj < N; jj += 2) {
-        const int j = N - 2 - jj;
-        if (j < m && live && j <= c) {
-            const bool two = j + 1 < m;
-            const double *x = V + j * N;
-            const double *y = two ? V + (j + 1) * N : x;
-            const double tau1 = S.tau[j], scal1 = S.scal[j], g = S.coup[j];
-            const double tau2 = two ? S.tau[j + 1] : 0., scal2 = two ? S.scal[j + 1] : 0., a = two ? S.coup[j + 1] : 0.;
-            const double xj1 = x[j + 1];
-            double dx0 = 0., dx1 = 0., dy0 = 0., dy1 = 0.;
-#pragma unroll
-            for (int i = j + 2; i < N; i += 2) {
-                const double2 xi = *reinterpret_cast<const double2 *>(x + i);
-                const double2 yi = *reinterpret_cast<const double2 *>(y + i);
-                dx0 = fma(xi.x, col[i], dx0);
-                dx1 = fma(xi.y, col[i + 1], dx1);
-                dy0 = fma(yi.x, col[i], dy0);
-                dy1 = fma(yi.y, col[i + 1], dy1);
-            }
-            const double Dx = dx0 + dx1, Dy = dy0 + dy1;
-            // H_j+1 first (v = e_j+1 + scal2 (y - a x) below), then H_j on the result
-            const double w2 = tau2 * fma(scal2, fma(-a, Dx, Dy), col[j + 1]);
-            const double e = w2 * scal2;
-            const double zj1 = col[j + 1] - w2;
-            const double Dx1 = fma(xj1, zj1, fma(-e, g, Dx));
-            const double w1 = tau1 * fma(scal1, Dx1, col[j]);
-            const double f = w1 * scal1;
-            col[j] -= w1;
-            col[j + 1] = fma(-f, xj1, zj1);
-            const double fx = fma(e, a, -f);                        // z'' = z + fx x - e y below row j + 1
-#pragma unroll
-            for (int i = j + 2; i < N; i += 2) {
-                const double2 xi = *reinterpret_cast<const double2 *>(x + i);
-                const double2 yi = *reinterpret_cast<const double2 *>(y + i);
-                col[i] = fma(fx, xi.x, fma(-e, yi.x, col[i]));
-                col[i + 1] = fma(fx, xi.y, fma(-e, yi.y, col[i + 1]));
-            }
-        }
-    }
-    if (live) {
-        double *fmc = S.fm + c;
-#pragma unroll
-        for (int i = 0; i < N; ++i) fmc[i * m] = col[i];
-    }
-}
-
 // ---- the same factorisation with the reflector loop ROLLED ------------------------------------------------------------
 // The fully unrolled qr<N> above is ~11.6k instructions (186 KB) that every warp streams from L2 once per step -- ncu
 // shows the Benettin kernel waiting for instruction fetch there (stall "no instruction" 1.1 per issue).  Here the
@@ -872,9 +690,7 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
 }
 
 // ---- Benettin loop (lyapunov.py:471-632) ---------------------------------------------------------------------------------
-// QRM: the re-orthonormalisation -- 0 one reflector per barrier, unrolled (qr), 1 rolled (qr_rolled), 2 two reflectors
-// per barrier (qr2)
-template <int N, class Prod, int QRM>
+template <int N, class Prod, bool ROLLED>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride, int qr_remap)
 {
@@ -967,9 +783,7 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
                     for (int i = 0; i < N; ++i) col[i] = Sq.fm[i * m + cq];
                 }
             }
-            if (QRM == 2)
-                qr2<N>(Sq, cq, liveq, col, Rout);
-            else if (QRM == 1)
+            if (ROLLED)
                 qr_rolled<N>(Sq, cq, liveq, col, Rout);
             else
                 qr<N>(Sq, cq, liveq, col, Rout);
@@ -1077,17 +891,18 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
     if (lyap) {
         // few vectors: the rolled factorisation (one resident loop body instead of n_vec unrolled reflectors) is faster
         // [B200: MAOOAM-36, 10 vectors +19 %; 36 vectors -8 %].
-        // Two other forms were measured in round 2 and removed (profiles/r02_benettin_qr_pipelined_ab.log,
-        // r02_benettin_split_ab.log): reflectors handed over through progress flags instead of block barriers
-        // (-16 %: the factorisation is ONE dependent chain per block, the other warps have nothing to overlap it with),
-        // and the step as two launches, propagation + stand-alone QR with two blocks per SM (-15 %: 26 % / 33 % of
-        // the two kernels go into moving the state through L2, and at 128 registers the factorisation spills).
-        // QGSB_QR_MODE = 0 | 1 | 2 forces a form (A/B measurements); default: rolled for few vectors, else panels of two
-        const char *env = getenv("QGSB_QR_MODE");
-        const int mode = env ? atoi(env) : (3 * P.m <= N ? 1 : 2);
-        if (mode == 2) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 2>) : go_lyap(lyap_kernel<N, Fwd, 2>);
-        if (mode == 1) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 1>) : go_lyap(lyap_kernel<N, Fwd, 1>);
-        return P.adjoint ? go_lyap(lyap_kernel<N, Adj, 0>) : go_lyap(lyap_kernel<N, Fwd, 0>);
+        // Three other forms were measured in round 2 and removed (profiles/r02_benettin_qr_pipelined_ab.log,
+        // r02_benettin_split_ab.log, r02_benettin_qr_panel2_ab.log): reflectors handed over through progress flags
+        // instead of block barriers (-16 %: the factorisation is ONE dependent chain per block, the other warps have
+        // nothing to overlap it with); the step as two launches, propagation + stand-alone QR with two blocks per SM
+        // (-15 %: 26 % / 33 % of the two kernels go into moving the state through L2, and at 128 registers the
+        // factorisation spills); two reflectors per barrier with the second one applied algebraically (-5 % at 36
+        // vectors, +5 % at 20: half the barriers, but the chain of dependent scalar instructions -- square root, two
+        // reciprocals, ~19 deep per reflector at 12-19 cycles each -- is what a reflector costs, and it stays).
+        const char *env = getenv("QGSB_QR_ROLLED");               // 0 / 1 forces one of them (A/B measurements)
+        const bool rolled = env ? (env[0] != '0') : (3 * P.m <= N);
+        if (rolled) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, true>) : go_lyap(lyap_kernel<N, Fwd, true>);
+        return P.adjoint ? go_lyap(lyap_kernel<N, Adj, false>) : go_lyap(lyap_kernel<N, Fwd, false>);
     }
     return P.adjoint ? go(tgls_kernel<N, Adj>) : go(tgls_kernel<N, Fwd>);
 }

@@ -61,30 +61,23 @@ def _benettin(name, N, n_vec, q0, r0, seed=None, vectors=True, mode=0, mdt=0.1, 
 
 # ---- the re-orthonormalisations are the same arithmetic -----------------------------------------------------------------
 @pytest.mark.parametrize("name,n_vec", [("maooam36", 36), ("maooam36", 10), ("rp", 20), ("dynT", 38)])
-def test_the_three_householder_forms_agree(name, n_vec):
+def test_rolled_and_unrolled_qr_are_bitwise_equal(name, n_vec):
     """The unrolled Householder factorisation (one code block per reflector) and the rolled one (three reflector groups,
     rows <= j multiplied by an explicit zero) differ in instruction bytes, never in a value; neither does the way the
-    columns are dealt to the threads (QGSB_QR_REMAP): trajectories, exponents and vectors are IDENTICAL.  The third form
-    (two reflectors per barrier, sums expanded instead of formed from updated vectors) is the same factorisation up to
-    rounding: 1e-11.  (The defaults are what the golden tests of test_gpu_parity.py compare with np.linalg.qr.)"""
+    columns are dealt to the threads (QGSB_QR_REMAP).  Trajectories, exponents and vectors must be IDENTICAL.  (The
+    defaults are what the golden tests of test_gpu_parity.py compare with the reference's np.linalg.qr.)"""
     f, Df, T = model(name)
     n = f.ndim
     N = 23                                     # not a multiple of the members per block: partially filled last block
     rng = np.random.default_rng(8)
     q0 = np.stack([np.linalg.qr(rng.random((n, n_vec)))[0] for _ in range(N)])
     out = []
-    for mode, remap in (("0", "1"), ("1", "1"), ("0", "0"), ("1", "0")):
-        with env(QGSB_QR_MODE=mode, QGSB_QR_REMAP=remap):
+    for rolled, remap in (("0", "1"), ("1", "1"), ("0", "0"), ("1", "0")):
+        with env(QGSB_QR_ROLLED=rolled, QGSB_QR_REMAP=remap):
             out.append(_benettin(name, N, n_vec, q0, None))
     for other in out[1:]:
         for x, y in zip(out[0], other):
             assert np.array_equal(x, y)
-    for remap in ("1", "0"):
-        with env(QGSB_QR_MODE="2", QGSB_QR_REMAP=remap):
-            pan = _benettin(name, N, n_vec, q0, None)
-        assert np.array_equal(pan[0], out[0][0])                                    # trajectories do not see the QR
-        assert np.max(np.abs(pan[1][:, :, 1:] - out[0][1][:, :, 1:])) < 1e-11 * np.max(np.abs(out[0][1][:, :, 1:]))
-        assert np.max(np.abs(pan[2] - out[0][2])) < 1e-11
 
 
 # ---- start bases drawn on the device -------------------------------------------------------------------------------------
