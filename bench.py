@@ -248,7 +248,7 @@ class ReferenceLyapunov(object):
         self.est.get_lyapunovs()
 
     def rate(self, members=None):
-        members = members or 4 * self.cores
+        members = members or 16 * self.cores
         ic = initial_conditions(0, members)
         t0 = time.perf_counter()
         self.est.compute_lyapunovs(*LYAP_ARGS, ic, write_steps=LYAP_WRITE_STEPS)

@@ -28,11 +28,28 @@ from qgs_b200.integrators.integrate import (_integrate_runge_kutta_jit, _integra
                                             n_records_of, rk4_tableau, tensor_of)
 
 
+_SUBTIMES_CACHE = {}
+
+
 def _subtimes(times, mdt, backward=False):
     """Micro-step lengths for every step of ``times`` (already directed).  Forward steps use
     ``concatenate(arange(tt, tt + dt, mdt), [tt + dt])`` (lyapunov.py:598), backward ones
     ``concatenate(arange(tt + dt, tt, mdt), [tt])`` walked in reverse (lyapunov.py:514 with
-    time_direction -1), reproducing numpy's arange rounding."""
+    time_direction -1), reproducing numpy's arange rounding -- which is why this is a Python loop over the steps
+    (tens of milliseconds for thousands of steps); chunked runs repeat the same time vectors, so the last few
+    results are kept."""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    key = (times.tobytes(), float(mdt), bool(backward))
+    hit = _SUBTIMES_CACHE.get(key)
+    if hit is not None:
+        return hit
+    if len(_SUBTIMES_CACHE) >= 8:
+        _SUBTIMES_CACHE.clear()
+    out = _SUBTIMES_CACHE[key] = _subtimes_uncached(times, mdt, backward)
+    return out
+
+
+def _subtimes_uncached(times, mdt, backward):
     ptr = [0]
     subs = []
     for tt, dt in zip(times[:-1], np.diff(times)):

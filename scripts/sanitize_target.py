@@ -13,7 +13,7 @@ from qgs_b200.integrators.integrator import RungeKuttaIntegrator, RungeKuttaTgls
 from qgs_b200.toolbox.lyapunov import CovariantLyapunovsEstimator, LyapunovsEstimator  # noqa: E402
 
 _lib.init(0)
-which = sys.argv[1:] or ["rk", "large", "tangent", "clv", "stats"]
+which = sys.argv[1:] or ["rk", "large", "tangent", "clv", "stats", "round2"]
 
 
 def load(name):
@@ -78,3 +78,32 @@ if "stats" in which:
     f(0., rng.random((600, 20)))
     Df(0., rng.random((4, 20)))
     print("stats ok", flush=True)
+if "round2" in which:
+    # round 2: general-tableau kernel (half tiles), tail-wave launch, device-drawn start bases (step -1 of the Benettin
+    # kernels, packed and generic), member batches, initialize() on resident batches
+    f, Df = load("maooam36")
+    integ = RungeKuttaIntegrator(b=np.array([1., 3., 3., 1.]) / 8., c=np.array([0., 1. / 3, 2. / 3, 1.]),
+                                 a=np.array([[0., 0., 0., 0.], [1. / 3, 0., 0., 0.], [-1. / 3, 1., 0., 0.],
+                                             [1., -1., 1., 0.]]))
+    integ.set_func(f)
+    os.environ["QGSB_RK_ROWS_MAX"] = "0"
+    integ.integrate(0., 0.3, 0.1, ic=rng.random((200, 36)) * 0.01, write_steps=2)       # rk_general_kernel
+    integ = RungeKuttaIntegrator()
+    integ.set_func(f)
+    n_tail = (_lib.device_info()["sm_count"] * 2 + 5) * 128                             # one full wave + 5 tail tiles
+    integ.integrate(0., 0.2, 0.1, ic=rng.random((n_tail, 36)) * 0.01, write_steps=0)
+    os.environ.pop("QGSB_RK_ROWS_MAX")
+    integ.device_batch = 50
+    integ.initialize(0.3, 0.1, reconvergence_time=0.2, number_of_trajectories=120, ic=rng.random((120, 36)) * 0.01,
+                     reconverge=True)
+    ic = rng.random((9, 36)) * 0.01
+    os.environ["QGSB_TANGENT_BUDGET_MB"] = "1"
+    for kern in ("pack", "generic"):
+        os.environ["QGSB_TGLS_KERNEL"] = kern
+        est = LyapunovsEstimator()
+        est.set_func(f, Df)
+        est.compute_lyapunovs(0., 0.2, 0.5, 0.1, 0.1, ic=ic, write_steps=1, n_vec=36 if kern == "pack" else 5)
+        est.compute_lyapunovs(0., 0.2, 0.5, 0.1, 0.1, ic=ic, write_steps=2, n_vec=12, vectors=False)
+    os.environ.pop("QGSB_TGLS_KERNEL")
+    os.environ.pop("QGSB_TANGENT_BUDGET_MB")
+    print("round2 ok", flush=True)
