@@ -17,7 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 GEN = os.path.join(CSRC, "generated")
 LIB = os.path.join(HERE, "libqgsb.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + \
+    os.environ.get("QGSB_NVCC_EXTRA", "").split()          # e.g. -DQGSB_PACK_THREADS=324 for A/B builds
 
 
 def nvcc():

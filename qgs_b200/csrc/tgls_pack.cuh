@@ -33,7 +33,10 @@
 namespace qgsb {
 namespace pack {
 
-constexpr int MAX_THREADS = 256;
+#ifndef QGSB_PACK_THREADS
+#define QGSB_PACK_THREADS 256
+#endif
+constexpr int MAX_THREADS = QGSB_PACK_THREADS;
 
 // launch geometry decided on the host
 struct Geometry {
