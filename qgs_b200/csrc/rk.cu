@@ -1171,17 +1171,34 @@ static void stream_trajectories(const qgsb_tensor *t, double *d_y, long ld, long
         QGSB_CUDA(cudaEventCreateWithFlags(&freed[q], cudaEventDisableTiming));
     }
     QGSB_CUDA(cudaEventRecord(cx.ev0, st));
-    int buf = 0;
-    auto ship = [&](double *d_out, long r0, long count) {
+    // A chunk is shipped AFTER the next one has been launched: with a pageable destination the copy blocks the host
+    // thread until the chunk has arrived, and in this order it does so while the GPU integrates the next chunk (with a
+    // pinned destination everything is asynchronous and the order does not matter).
+    struct Pending {
+        double *d_out;
+        long r0, count;
+        int buf;
+        bool valid;
+    } pending = {nullptr, 0, 0, 0, false};
+    bool used[2] = {false, false};
+    auto ship = [&](const Pending &p) {
         // host columns [h0, h0 + count) of every (member, variable) row; the record axis is reversed for backward runs
-        const long h0 = flip ? R - (r0 + count) : r0;
+        const long h0 = flip ? R - (p.r0 + p.count) : p.r0;
+        QGSB_CUDA(cudaStreamWaitEvent(so, ready[p.buf], 0));
+        QGSB_CUDA(cudaMemcpy2DAsync(traj + h0, (size_t)R * sizeof(double), p.d_out, (size_t)p.count * sizeof(double),
+                                    (size_t)p.count * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, so));
+        QGSB_CUDA(cudaEventRecord(freed[p.buf], so));
+    };
+    int buf = 0;
+    auto produce = [&](long r0, long count, const double *d_src, long src_records, int src_flip) {
+        double *d_out = buf ? d_out1.p : d_out0.p;
+        if (used[buf]) QGSB_CUDA(cudaStreamWaitEvent(st, freed[buf], 0));      // the buffer's last shipment has left
+        launch_rec_to_api(d_src, d_out, N, n, src_records, ld, src_flip);
         QGSB_CUDA(cudaEventRecord(ready[buf], st));
-        QGSB_CUDA(cudaStreamWaitEvent(so, ready[buf], 0));
-        QGSB_CUDA(cudaMemcpy2DAsync(traj + h0, (size_t)R * sizeof(double), d_out, (size_t)count * sizeof(double),
-                                    (size_t)count * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, so));
-        QGSB_CUDA(cudaEventRecord(freed[buf], so));
+        used[buf] = true;
+        const Pending mine = {d_out, r0, count, buf, true};
         buf ^= 1;
-        QGSB_CUDA(cudaStreamWaitEvent(st, freed[buf], 0));    // the buffer about to be refilled has been shipped
+        return mine;
     };
     if (write_steps > 0) {
         for (long r0 = 0; r0 < R - 1; r0 += per_chunk) {
@@ -1189,18 +1206,18 @@ static void stream_trajectories(const qgsb_tensor *t, double *d_y, long ld, long
             const long step0 = r0 * write_steps, step1 = std::min(n_steps, r1 * write_steps);
             const long steps = step1 - step0, rc = records_for(steps, write_steps);
             rk_advance(t, d_y, ld, N, steps, d_dt + step0, tab, write_steps, rc, d_rec.p);
-            double *d_out = buf ? d_out1.p : d_out0.p;
-            launch_rec_to_api(d_rec.p, d_out, N, n, r1 - r0, ld, flip ? 1 : 0);
-            ship(d_out, r0, r1 - r0);
+            const Pending mine = produce(r0, r1 - r0, d_rec.p, r1 - r0, flip ? 1 : 0);
+            if (pending.valid) ship(pending);
+            pending = mine;
         }
     } else {
         rk_advance(t, d_y, ld, N, n_steps, d_dt, tab, 0, 1, nullptr);
     }
     {
-        double *d_out = buf ? d_out1.p : d_out0.p;
-        launch_rec_to_api(d_y, d_out, N, n, 1, ld, 0);
+        const Pending last = produce(R - 1, 1, d_y, 1, 0);
         QGSB_CUDA(cudaEventRecord(cx.ev1, st));
-        ship(d_out, R - 1, 1);
+        if (pending.valid) ship(pending);
+        ship(last);
     }
     QGSB_CUDA(cudaStreamSynchronize(so));
     QGSB_CUDA(cudaStreamSynchronize(st));
@@ -1238,12 +1255,24 @@ static void rk_integrate_device(const qgsb_tensor *t, long N, const double *ic, 
                 QGSB_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
             }
             QGSB_CUDA(cudaStreamSynchronize(st));      // d_dt upload and earlier work on the pool buffers
-            for (long k = 0; k < n_chunks; ++k) {
+            // Issue order: compute(k) is launched BEFORE upload(k + 1) and download(k - 1) are issued.  With pinned
+            // host buffers every call below is asynchronous and the three streams overlap by themselves; with ordinary
+            // (pageable) numpy arrays a copy blocks the host thread -- an upload until the data is staged, a download
+            // until it has arrived -- and in this order it blocks while the GPU is busy with chunk k, so the copies of
+            // the neighbouring chunks still hide behind the integration.
+            auto upload = [&](long k) {
                 const long m0 = k * chunk, nk = std::min(chunk, N - m0);
                 QGSB_CUDA(cudaMemcpyAsync(d_ic.p + (size_t)m0 * n, ic + (size_t)m0 * n, sizeof(double) * nk * n,
                                           cudaMemcpyHostToDevice, s_in));
                 QGSB_CUDA(cudaEventRecord(up[k], s_in));
-            }
+            };
+            auto download = [&](long k) {
+                const long m0 = k * chunk, nk = std::min(chunk, N - m0);
+                QGSB_CUDA(cudaStreamWaitEvent(s_out, done[k], 0));
+                QGSB_CUDA(cudaMemcpyAsync(traj + (size_t)m0 * n, d_out.p + (size_t)m0 * n, sizeof(double) * nk * n,
+                                          cudaMemcpyDeviceToHost, s_out));
+            };
+            upload(0);
             QGSB_CUDA(cudaEventRecord(cx.ev0, st));
             for (long k = 0; k < n_chunks; ++k) {
                 const long m0 = k * chunk, nk = std::min(chunk, N - m0), ldk = round_up(nk, TILE);
@@ -1253,10 +1282,10 @@ static void rk_integrate_device(const qgsb_tensor *t, long N, const double *ic, 
                 rk_advance(t, yk, ldk, nk, n_steps, d_dt.p, tab, 0, 1, nullptr);
                 launch_soa_to_aos(yk, d_out.p + (size_t)m0 * n, nk, n, ldk);
                 QGSB_CUDA(cudaEventRecord(done[k], st));
-                QGSB_CUDA(cudaStreamWaitEvent(s_out, done[k], 0));
-                QGSB_CUDA(cudaMemcpyAsync(traj + (size_t)m0 * n, d_out.p + (size_t)m0 * n, sizeof(double) * nk * n,
-                                          cudaMemcpyDeviceToHost, s_out));
+                if (k + 1 < n_chunks) upload(k + 1);
+                if (k >= 1) download(k - 1);
             }
+            download(n_chunks - 1);
             QGSB_CUDA(cudaEventRecord(cx.ev1, st));
             QGSB_CUDA(cudaStreamSynchronize(s_out));
             QGSB_CUDA(cudaStreamSynchronize(st));

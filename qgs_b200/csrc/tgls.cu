@@ -12,6 +12,7 @@
 // writes contiguous chunks.
 #include <algorithm>
 #include <cmath>
+#include <memory>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -573,60 +574,94 @@ using namespace qgsb;
 
 extern "C" {
 
-// one device's share of qgsb_rk_tgls_integrate
-static void tgls_integrate_device(const qgsb_tensor *t, long N, const double *ic, int m, const double *tg_ic,
-                                  long n_steps, const double *dt, int s, const double *a, const double *b,
-                                  long write_steps, int time_direction, int adjoint, double inverse_sign, long R,
-                                  double *traj, double *fmat, double *device_ms)
-{
-    Context &cx = ctx();
-    cudaStream_t st = cx.stream;
-    const Tableau tab = make_tableau(s, a, b);
-    const int n = t->view.n;
-    const size_t nm = (size_t)n * m;
-    PoolBuf<double> d_y((size_t)N * n), d_fm((size_t)N * nm), d_dt(std::max<long>(n_steps, 1));
-    PoolBuf<double> d_ry((size_t)R * N * n), d_rf((size_t)R * N * nm), d_oy((size_t)R * N * n), d_of((size_t)R * N * nm);
+// One member batch of qgsb_rk_tgls_integrate on the calling thread's device: enqueue() uploads, launches the tangent
+// kernel and the record transposes, collect() brings the records to the caller's arrays -- called after the NEXT batch
+// has been enqueued, so that the downloads hide behind its integration (see BenettinBatch).
+struct TglsBatch {
+    long N = 0, R = 0;
+    int n = 0, m = 0;
+    double *traj = nullptr, *fmat = nullptr;
+    PoolBuf<double> d_y, d_fm, d_dt, d_ry, d_rf, d_oy, d_of;
     DevBuf<double> scratch;
-    d_y.upload(ic, (size_t)N * n, st);
-    d_fm.upload(tg_ic, (size_t)N * nm, st);
-    if (n_steps) d_dt.upload(dt, n_steps, st);
-    TgParams P;
-    fill_common(P, tab, N, m, adjoint, inverse_sign);
-    P.n_steps = n_steps;
-    P.dt = d_dt.p;
-    P.write_steps = write_steps;
-    P.n_records = R;
-    P.y = d_y.p;
-    P.fm = d_fm.p;
-    P.rec_y = d_ry.p;
-    P.rec_fm = d_rf.p;
-    QGSB_CUDA(cudaEventRecord(cx.ev0, st));
-    if (pack_tangent_supported(t, tab, m)) {
-        launch_pack_tangent(t, P, false);
-    } else if (t->view.rank == 5) {
-        const size_t bytes = place_matrices(t, P, scratch, 0);
-        set_smem_attr(tgls_kernel<5>, bytes);
-        tgls_kernel<5><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
-        count_launch();
-    } else {
-        const size_t bytes = place_matrices(t, P, scratch, 0);
-        set_smem_attr(tgls_kernel<3>, bytes);
-        tgls_kernel<3><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
-        count_launch();
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
+
+    ~TglsBatch()
+    {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (done) cudaEventDestroy(done);
     }
-    QGSB_CUDA(cudaGetLastError());
-    QGSB_CUDA(cudaEventRecord(cx.ev1, st));
-    launch_transpose_rec(d_ry.p, d_oy.p, R, (long)N * n, time_direction == -1);
-    launch_transpose_rec(d_rf.p, d_of.p, R, (long)N * (long)nm, time_direction == -1);
-    d_oy.download(traj, (size_t)R * N * n, st);
-    d_of.download(fmat, (size_t)R * N * nm, st);
-    QGSB_CUDA(cudaStreamSynchronize(st));
-    if (device_ms) {
+
+    void enqueue(const qgsb_tensor *t, long N_, const double *ic, int m_, const double *tg_ic, long n_steps,
+                 const double *dt, int s, const double *a, const double *b, long write_steps, int time_direction,
+                 int adjoint, double inverse_sign, long R_, double *traj_, double *fmat_)
+    {
+        Context &cx = ctx();
+        cudaStream_t st = cx.stream;
+        const Tableau tab = make_tableau(s, a, b);
+        N = N_;
+        R = R_;
+        n = t->view.n;
+        m = m_;
+        traj = traj_;
+        fmat = fmat_;
+        const size_t nm = (size_t)n * m;
+        QGSB_CUDA(cudaEventCreate(&ev0));
+        QGSB_CUDA(cudaEventCreate(&ev1));
+        QGSB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        d_y.alloc((size_t)N * n);
+        d_fm.alloc((size_t)N * nm);
+        d_dt.alloc(std::max<long>(n_steps, 1));
+        d_ry.alloc((size_t)R * N * n);
+        d_rf.alloc((size_t)R * N * nm);
+        d_oy.alloc((size_t)R * N * n);
+        d_of.alloc((size_t)R * N * nm);
+        d_y.upload(ic, (size_t)N * n, st);
+        d_fm.upload(tg_ic, (size_t)N * nm, st);
+        if (n_steps) d_dt.upload(dt, n_steps, st);
+        TgParams P;
+        fill_common(P, tab, N, m, adjoint, inverse_sign);
+        P.n_steps = n_steps;
+        P.dt = d_dt.p;
+        P.write_steps = write_steps;
+        P.n_records = R;
+        P.y = d_y.p;
+        P.fm = d_fm.p;
+        P.rec_y = d_ry.p;
+        P.rec_fm = d_rf.p;
+        QGSB_CUDA(cudaEventRecord(ev0, st));
+        if (pack_tangent_supported(t, tab, m)) {
+            launch_pack_tangent(t, P, false);
+        } else if (t->view.rank == 5) {
+            const size_t bytes = place_matrices(t, P, scratch, 0);
+            set_smem_attr(tgls_kernel<5>, bytes);
+            tgls_kernel<5><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
+            count_launch();
+        } else {
+            const size_t bytes = place_matrices(t, P, scratch, 0);
+            set_smem_attr(tgls_kernel<3>, bytes);
+            tgls_kernel<3><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
+            count_launch();
+        }
+        QGSB_CUDA(cudaGetLastError());
+        QGSB_CUDA(cudaEventRecord(ev1, st));
+        launch_transpose_rec(d_ry.p, d_oy.p, R, (long)N * n, time_direction == -1);
+        launch_transpose_rec(d_rf.p, d_of.p, R, (long)N * (long)nm, time_direction == -1);
+        QGSB_CUDA(cudaEventRecord(done, st));
+    }
+
+    double collect()
+    {
+        cudaStream_t so = ctx().copy_out;
+        QGSB_CUDA(cudaStreamWaitEvent(so, done, 0));
+        d_oy.download(traj, (size_t)R * N * n, so);
+        d_of.download(fmat, (size_t)R * N * n * m, so);
+        QGSB_CUDA(cudaStreamSynchronize(so));
         float ms = 0.f;
-        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
-        *device_ms = ms;
+        QGSB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        return ms;
     }
-}
+};
 
 // records kept on the device by one tangent / Benettin launch: bounded so that a long write_steps = 1 run is cut
 // into member batches instead of failing in cudaMalloc (the reference keeps such runs in host RAM)
@@ -664,16 +699,24 @@ int qgsb_rk_tgls_integrate(const qgsb_tensor *t, long N, const double *ic, int m
     std::vector<double> ms(parts, 0.);
     run_sharded(N, parts, [&](int g, long lo, long hi) {
         const qgsb_tensor *th = tensor_here(t);
-        // member batches sized to the device memory: records (R, batch, n + n m) twice (kernel order + API order)
-        const long batch = tangent_member_batch(hi - lo, (size_t)(2 * R + 1) * (n + nm) * sizeof(double));
+        // member batches sized to the device memory: records (R, batch, n + n m) twice (kernel order + API order), two
+        // batches alive at a time; a large shard is cut into at least four (whole waves of the packed kernel) so that
+        // the downloads of one batch hide behind the integration of the next
+        long batch = tangent_member_batch(hi - lo, 2 * (size_t)(2 * R + 1) * (n + nm) * sizeof(double));
+        const long wave = (long)ctx().sm_count * std::max(1, 256 / m);
+        if (hi - lo >= 4 * wave) batch = std::min(batch, ((hi - lo + 3) / 4 + wave - 1) / wave * wave);
+        std::unique_ptr<TglsBatch> previous;
         for (long m0 = lo; m0 < hi; m0 += batch) {
             const long nb = std::min(batch, hi - m0);
-            double part_ms = 0.;
-            tgls_integrate_device(th, nb, ic + (size_t)m0 * n, m, tg_ic + (size_t)m0 * nm, n_steps, dt, s, a, b,
-                                  write_steps, time_direction, adjoint, inverse_sign, R, traj + (size_t)m0 * n * R,
-                                  fmat + (size_t)m0 * nm * R, &part_ms);
-            ms[g] += part_ms;
+            std::unique_ptr<TglsBatch> current(new TglsBatch());
+            current->enqueue(th, nb, ic + (size_t)m0 * n, m, tg_ic + (size_t)m0 * nm, n_steps, dt, s, a, b, write_steps,
+                             time_direction, adjoint, inverse_sign, R, traj + (size_t)m0 * n * R,
+                             fmat + (size_t)m0 * nm * R);
+            if (previous) ms[g] += previous->collect();
+            previous = std::move(current);
         }
+        if (previous) ms[g] += previous->collect();
+        QGSB_CUDA(cudaStreamSynchronize(ctx().stream));
     });
     if (device_ms) *device_ms = *std::max_element(ms.begin(), ms.end());
     QGSB_API_END
@@ -705,123 +748,170 @@ __global__ void random_basis_kernel(double *__restrict__ q, long n_members, long
     q[idx] = (double)(h >> 11) * (1. / 9007199254740992.);     // 53 random bits -> [0, 1)
 }
 
-// one device's share of qgsb_lyap_benettin; member0 = index of the first member in the whole ensemble
-static void benettin_device(const qgsb_tensor *t, long N, long member0, const double *ic, int forward, int n_vec,
-                            const double *q0, const double *r0, long n_pre, long n_rec, const double *dt_macro,
-                            const long *sub_ptr, const double *sub_dt, int s, const double *a, const double *b,
-                            long write_steps, int adjoint, double inverse_sign, long R, double *rec_traj,
-                            double *rec_exp, double *rec_vec, double *r_all, double *q_all, double *device_ms)
-{
-    Context &cx = ctx();
-    cudaStream_t st = cx.stream;
-    const Tableau tab = make_tableau(s, a, b);
-    const int n = t->view.n, m = n_vec;
-    const size_t nm = (size_t)n * m;
-    const long steps = n_pre + n_rec;
-    // Micro steps of length exactly 0 are dropped: the reference's concatenate(arange(tt, tt + dt, mdt), [tt + dt])
-    // (lyapunov.py:598) often ends in two equal times when mdt divides dt (375 of the 1000 steps of arange(0, 100, 0.1)),
-    // and a Runge-Kutta step of length 0 leaves the state and the tangent matrix unchanged to the last bit
-    // (x + 0 * k = x), while costing a full step -- and hiding that the step is a single micro step of the macro length.
-    std::vector<long> f_ptr(steps + 1, 0);
-    std::vector<double> f_sub;
-    f_sub.reserve(sub_ptr[steps]);
-    for (long q = 0; q < steps; ++q) {
-        for (long e = sub_ptr[q]; e < sub_ptr[q + 1]; ++e)
-            if (sub_dt[e] != 0.) f_sub.push_back(sub_dt[e]);
-        f_ptr[q + 1] = (long)f_sub.size();
+// One member batch of qgsb_lyap_benettin on the calling thread's device; member0 = index of its first member in the whole
+// ensemble.  enqueue() uploads, launches the Benettin kernel and the record transposes; collect() brings the records to
+// the caller's arrays.  The caller enqueues batch k + 1 BEFORE it collects batch k: the downloads (which block the
+// host thread when the destination is an ordinary pageable numpy array) then run on the copy stream while the device
+// integrates the next batch.
+struct BenettinBatch {
+    long N = 0, steps = 0, n_rec = 0, R = 0;
+    int n = 0, m = 0;
+    double *rec_traj = nullptr, *rec_exp = nullptr, *rec_vec = nullptr, *r_all = nullptr, *q_all = nullptr;
+    std::vector<long> f_ptr, idx;
+    std::vector<double> f_sub, fdt;
+    PoolBuf<double> d_y, d_q, d_dtm, d_sub, d_ry, d_rv, d_re, d_oy, d_ov, d_oe;
+    PoolBuf<long> d_ptr, d_idx;
+    DevBuf<double> d_r0, d_rall, d_qall, d_stored, d_fdt, d_state, scratch;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
+
+    ~BenettinBatch()
+    {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (done) cudaEventDestroy(done);
     }
-    sub_ptr = f_ptr.data();
-    sub_dt = f_sub.data();
-    const long n_sub = sub_ptr[steps];
-    PoolBuf<double> d_y((size_t)N * n), d_q((size_t)N * nm), d_dtm(std::max<long>(steps, 1)), d_sub(std::max<long>(n_sub, 1));
-    PoolBuf<long> d_ptr(steps + 1), d_idx(std::max<long>(steps, 1));
-    DevBuf<double> d_r0, d_rall, d_qall, d_stored, d_ys, scratch;
-    // rec_vec == NULL: the vectors are not recorded (spectrum-only runs skip 8 n m bytes per member and record)
-    PoolBuf<double> d_ry((size_t)R * N * n), d_rv(rec_vec ? (size_t)R * N * nm : 0), d_re((size_t)R * N * m);
-    PoolBuf<double> d_oy((size_t)R * N * n), d_ov(rec_vec ? (size_t)R * N * nm : 0), d_oe((size_t)R * N * m);
-    d_y.upload(ic, (size_t)N * n, st);
-    if (q0) {
-        d_q.upload(q0, (size_t)N * nm, st);
-    } else {
-        const long total = N * (long)nm;
-        random_basis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_q.p, N, (long)nm, g_member_offset + member0,
-                                                                             g_seed);
-        count_launch();
+
+    void enqueue(const qgsb_tensor *t, long N_, long member0, const double *ic, int forward, int n_vec, const double *q0,
+                 const double *r0, long n_pre, long n_rec_, const double *dt_macro, const long *sub_ptr,
+                 const double *sub_dt, int s, const double *a, const double *b, long write_steps, int adjoint,
+                 double inverse_sign, long R_, double *rec_traj_, double *rec_exp_, double *rec_vec_, double *r_all_,
+                 double *q_all_)
+    {
+        Context &cx = ctx();
+        cudaStream_t st = cx.stream;
+        const Tableau tab = make_tableau(s, a, b);
+        N = N_;
+        n = t->view.n;
+        m = n_vec;
+        n_rec = n_rec_;
+        R = R_;
+        rec_traj = rec_traj_;
+        rec_exp = rec_exp_;
+        rec_vec = rec_vec_;
+        r_all = r_all_;
+        q_all = q_all_;
+        const size_t nm = (size_t)n * m;
+        steps = n_pre + n_rec;
+        QGSB_CUDA(cudaEventCreate(&ev0));
+        QGSB_CUDA(cudaEventCreate(&ev1));
+        QGSB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        // Micro steps of length exactly 0 are dropped: the reference's concatenate(arange(tt, tt + dt, mdt), [tt + dt])
+        // (lyapunov.py:598) often ends in two equal times when mdt divides dt (375 of the 1000 steps of
+        // arange(0, 100, 0.1)), and a Runge-Kutta step of length 0 leaves the state and the tangent matrix unchanged to
+        // the last bit (x + 0 * k = x), while costing a full step -- and hiding that the step is a single micro step of
+        // the macro length.
+        f_ptr.assign(steps + 1, 0);
+        f_sub.reserve(sub_ptr[steps]);
+        for (long q = 0; q < steps; ++q) {
+            for (long e = sub_ptr[q]; e < sub_ptr[q + 1]; ++e)
+                if (sub_dt[e] != 0.) f_sub.push_back(sub_dt[e]);
+            f_ptr[q + 1] = (long)f_sub.size();
+        }
+        const long n_sub = f_ptr[steps];
+        d_y.alloc((size_t)N * n);
+        d_q.alloc((size_t)N * nm);
+        d_dtm.alloc(std::max<long>(steps, 1));
+        d_sub.alloc(std::max<long>(n_sub, 1));
+        d_ptr.alloc(steps + 1);
+        d_idx.alloc(std::max<long>(steps, 1));
+        // rec_vec == NULL: the vectors are not recorded (spectrum-only runs skip 8 n m bytes per member and record)
+        d_ry.alloc((size_t)R * N * n);
+        d_rv.alloc(rec_vec ? (size_t)R * N * nm : 0);
+        d_re.alloc((size_t)R * N * m);
+        d_oy.alloc((size_t)R * N * n);
+        d_ov.alloc(rec_vec ? (size_t)R * N * nm : 0);
+        d_oe.alloc((size_t)R * N * m);
+        d_y.upload(ic, (size_t)N * n, st);
+        if (q0) {
+            d_q.upload(q0, (size_t)N * nm, st);
+        } else {
+            const long total = N * (long)nm;
+            random_basis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_q.p, N, (long)nm,
+                                                                                 g_member_offset + member0, g_seed);
+            count_launch();
+            QGSB_CUDA(cudaGetLastError());
+        }
+        if (steps) d_dtm.upload(dt_macro, steps, st);
+        if (n_sub) d_sub.upload(f_sub.data(), n_sub, st);
+        QGSB_CUDA(cudaMemcpyAsync(d_ptr.p, f_ptr.data(), sizeof(long) * (steps + 1), cudaMemcpyHostToDevice, st));
+        TgParams P;
+        fill_common(P, tab, N, m, adjoint, inverse_sign);
+        P.forward = forward;
+        P.n_pre = n_pre;
+        P.n_rec = n_rec;
+        P.dt_macro = d_dtm.p;
+        P.sub_ptr = d_ptr.p;
+        P.sub_dt = d_sub.p;
+        P.write_steps = write_steps;
+        P.n_records = R;
+        P.y = d_y.p;
+        P.fm = d_q.p;
+        P.rec_y = d_ry.p;
+        P.rec_fm = rec_vec ? d_rv.p : nullptr;
+        P.rec_exp = d_re.p;
+        P.qr_at_start = q0 ? 0 : 1;
+        if (r0 && q0) {
+            d_r0.alloc((size_t)N * m * m);
+            d_r0.upload(r0, (size_t)N * m * m, st);
+            P.r0 = d_r0.p;
+        }
+        if (r_all) {
+            d_rall.alloc((size_t)N * std::max<long>(steps, 1) * m * m);
+            P.r_all = d_rall.p;
+        }
+        if (q_all) {
+            d_qall.alloc((size_t)N * (n_rec + 1) * nm);
+            P.q_all = d_qall.p;
+        }
+        QGSB_CUDA(cudaEventRecord(ev0, st));
+        if (forward == 1) {
+            // lyapunov.py:474: store the whole write_steps=1 trajectory, then walk it backwards.  The
+            // steps come in execution (backward) order with negative dt; the forward integration uses
+            // them reversed and positive.
+            const long ld = round_up(N, TILE);
+            fdt.resize(steps);
+            for (long q = 0; q < steps; ++q) fdt[q] = -dt_macro[steps - 1 - q];
+            d_fdt.alloc(std::max<long>(steps, 1));
+            d_state.alloc((size_t)n * ld);
+            if (steps) d_fdt.upload(fdt.data(), steps, st);
+            d_stored.alloc((size_t)(steps + 1) * n * ld);
+            launch_aos_to_soa(d_y.p, d_state.p, N, n, ld);
+            rk_advance(t, d_state.p, ld, N, steps, d_fdt.p, tab, 1, steps + 1, d_stored.p);
+            idx.resize(std::max<long>(steps, 1));
+            for (long q = 0; q < steps; ++q) idx[q] = steps - q;  // step q starts from point steps - q
+            QGSB_CUDA(cudaMemcpyAsync(d_idx.p, idx.data(), sizeof(long) * std::max<long>(steps, 1),
+                                      cudaMemcpyHostToDevice, st));
+            P.stored = d_stored.p;
+            P.stored_ld = ld;
+            P.start_idx = d_idx.p;
+            P.final_idx = steps > 0 ? idx[steps - 1] : 0;   // lyapunov.py:549: y[0] of the last pass
+        }
+        benettin_dispatch(t, tab, P, scratch);
         QGSB_CUDA(cudaGetLastError());
+        QGSB_CUDA(cudaEventRecord(ev1, st));
+        launch_transpose_rec(d_ry.p, d_oy.p, R, (long)N * n, 0);
+        if (rec_vec) launch_transpose_rec(d_rv.p, d_ov.p, R, (long)N * (long)nm, 0);
+        launch_transpose_rec(d_re.p, d_oe.p, R, (long)N * m, 0);
+        QGSB_CUDA(cudaEventRecord(done, st));
     }
-    if (steps) d_dtm.upload(dt_macro, steps, st);
-    if (n_sub) d_sub.upload(sub_dt, n_sub, st);
-    QGSB_CUDA(cudaMemcpyAsync(d_ptr.p, sub_ptr, sizeof(long) * (steps + 1), cudaMemcpyHostToDevice, st));
-    TgParams P;
-    fill_common(P, tab, N, m, adjoint, inverse_sign);
-    P.forward = forward;
-    P.n_pre = n_pre;
-    P.n_rec = n_rec;
-    P.dt_macro = d_dtm.p;
-    P.sub_ptr = d_ptr.p;
-    P.sub_dt = d_sub.p;
-    P.write_steps = write_steps;
-    P.n_records = R;
-    P.y = d_y.p;
-    P.fm = d_q.p;
-    P.rec_y = d_ry.p;
-    P.rec_fm = rec_vec ? d_rv.p : nullptr;
-    P.rec_exp = d_re.p;
-    P.qr_at_start = q0 ? 0 : 1;
-    if (r0 && q0) {
-        d_r0.alloc((size_t)N * m * m);
-        d_r0.upload(r0, (size_t)N * m * m, st);
-        P.r0 = d_r0.p;
-    }
-    if (r_all) {
-        d_rall.alloc((size_t)N * std::max<long>(steps, 1) * m * m);
-        P.r_all = d_rall.p;
-    }
-    if (q_all) {
-        d_qall.alloc((size_t)N * (n_rec + 1) * nm);
-        P.q_all = d_qall.p;
-    }
-    QGSB_CUDA(cudaEventRecord(cx.ev0, st));
-    std::vector<long> idx;
-    if (forward == 1) {
-        // lyapunov.py:474: store the whole write_steps=1 trajectory, then walk it backwards.  The
-        // steps come in execution (backward) order with negative dt; the forward integration uses
-        // them reversed and positive.
-        const long ld = round_up(N, TILE);
-        std::vector<double> fdt(steps);
-        for (long q = 0; q < steps; ++q) fdt[q] = -dt_macro[steps - 1 - q];
-        DevBuf<double> d_fdt(std::max<long>(steps, 1)), d_state((size_t)n * ld);
-        if (steps) d_fdt.upload(fdt.data(), steps, st);
-        d_stored.alloc((size_t)(steps + 1) * n * ld);
-        launch_aos_to_soa(d_y.p, d_state.p, N, n, ld);
-        rk_advance(t, d_state.p, ld, N, steps, d_fdt.p, tab, 1, steps + 1, d_stored.p);
-        idx.resize(std::max<long>(steps, 1));
-        for (long q = 0; q < steps; ++q) idx[q] = steps - q;  // step q starts from point steps - q
-        QGSB_CUDA(cudaMemcpyAsync(d_idx.p, idx.data(), sizeof(long) * std::max<long>(steps, 1), cudaMemcpyHostToDevice, st));
-        P.stored = d_stored.p;
-        P.stored_ld = ld;
-        P.start_idx = d_idx.p;
-        P.final_idx = steps > 0 ? idx[steps - 1] : 0;   // lyapunov.py:549: y[0] of the last pass
-        QGSB_CUDA(cudaStreamSynchronize(st));           // fdt / idx host vectors must outlive the copies
-    }
-    benettin_dispatch(t, tab, P, scratch);
-    QGSB_CUDA(cudaGetLastError());
-    QGSB_CUDA(cudaEventRecord(cx.ev1, st));
-    launch_transpose_rec(d_ry.p, d_oy.p, R, (long)N * n, 0);
-    if (rec_vec) launch_transpose_rec(d_rv.p, d_ov.p, R, (long)N * (long)nm, 0);
-    launch_transpose_rec(d_re.p, d_oe.p, R, (long)N * m, 0);
-    d_oy.download(rec_traj, (size_t)R * N * n, st);
-    if (rec_vec) d_ov.download(rec_vec, (size_t)R * N * nm, st);
-    d_oe.download(rec_exp, (size_t)R * N * m, st);
-    if (r_all) d_rall.download(r_all, (size_t)N * steps * m * m, st);
-    if (q_all) d_qall.download(q_all, (size_t)N * (n_rec + 1) * nm, st);
-    QGSB_CUDA(cudaStreamSynchronize(st));
-    if (device_ms) {
+
+    double collect()
+    {
+        Context &cx = ctx();
+        cudaStream_t so = cx.copy_out;
+        const size_t nm = (size_t)n * m;
+        QGSB_CUDA(cudaStreamWaitEvent(so, done, 0));
+        d_oy.download(rec_traj, (size_t)R * N * n, so);
+        if (rec_vec) d_ov.download(rec_vec, (size_t)R * N * nm, so);
+        d_oe.download(rec_exp, (size_t)R * N * m, so);
+        if (r_all) d_rall.download(r_all, (size_t)N * steps * m * m, so);
+        if (q_all) d_qall.download(q_all, (size_t)N * (n_rec + 1) * nm, so);
+        QGSB_CUDA(cudaStreamSynchronize(so));
         float ms = 0.f;
-        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
-        *device_ms = ms;
+        QGSB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        return ms;
     }
-}
+};
 
 int qgsb_set_seed(uint64_t seed, long member_offset)
 {
@@ -866,18 +956,27 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
     std::vector<double> ms(parts, 0.);
     run_sharded(N, parts, [&](int g, long lo, long hi) {
         const qgsb_tensor *th = tensor_here(t);
-        const long batch = tangent_member_batch(hi - lo, per_member);
+        // Member batches: as many as device memory demands (two batches are alive at a time), and for a large shard at
+        // least four, cut at whole waves of the packed kernel, so that the record downloads of one batch hide behind
+        // the integration of the next.
+        long batch = tangent_member_batch(hi - lo, 2 * per_member);
+        const long wave = (long)ctx().sm_count * std::max(1, 256 / m);
+        if (hi - lo >= 4 * wave) batch = std::min(batch, ((hi - lo + 3) / 4 + wave - 1) / wave * wave);
+        std::unique_ptr<BenettinBatch> previous;
         for (long m0 = lo; m0 < hi; m0 += batch) {
             const long nb = std::min(batch, hi - m0);
-            double part_ms = 0.;
-            benettin_device(th, nb, m0, ic + (size_t)m0 * n, forward, n_vec, q0 ? q0 + (size_t)m0 * nm : nullptr,
-                            r0 ? r0 + (size_t)m0 * m * m : nullptr, n_pre, n_rec, dt_macro, sub_ptr, sub_dt, s, a, b,
-                            write_steps, adjoint, inverse_sign, R, rec_traj + (size_t)m0 * n * R,
-                            rec_exp + (size_t)m0 * m * R, rec_vec ? rec_vec + (size_t)m0 * nm * R : nullptr,
-                            r_all ? r_all + (size_t)m0 * steps * m * m : nullptr,
-                            q_all ? q_all + (size_t)m0 * (n_rec + 1) * nm : nullptr, &part_ms);
-            ms[g] += part_ms;
+            std::unique_ptr<BenettinBatch> current(new BenettinBatch());
+            current->enqueue(th, nb, m0, ic + (size_t)m0 * n, forward, n_vec, q0 ? q0 + (size_t)m0 * nm : nullptr,
+                             r0 ? r0 + (size_t)m0 * m * m : nullptr, n_pre, n_rec, dt_macro, sub_ptr, sub_dt, s, a, b,
+                             write_steps, adjoint, inverse_sign, R, rec_traj + (size_t)m0 * n * R,
+                             rec_exp + (size_t)m0 * m * R, rec_vec ? rec_vec + (size_t)m0 * nm * R : nullptr,
+                             r_all ? r_all + (size_t)m0 * steps * m * m : nullptr,
+                             q_all ? q_all + (size_t)m0 * (n_rec + 1) * nm : nullptr);
+            if (previous) ms[g] += previous->collect();
+            previous = std::move(current);
         }
+        if (previous) ms[g] += previous->collect();
+        QGSB_CUDA(cudaStreamSynchronize(ctx().stream));
     });
     if (device_ms) *device_ms = *std::max_element(ms.begin(), ms.end());
     QGSB_API_END
