@@ -18,7 +18,7 @@
  *     called from several host threads: entry points serialise on one process-wide lock.
  *   - devices: a process drives ONE device (one process per GPU under torchrun: LOCAL_RANK) or SEVERAL (any other
  *     process on a multi-GPU box, see qgsb_init).  With several, the host-buffer entry points qgsb_rk_integrate,
- *     qgsb_rk_tgls_integrate and qgsb_lyap_benettin split the members into contiguous blocks
+ *     qgsb_rk_tgls_integrate, qgsb_lyap_benettin and qgsb_clv_ginelli split the members into contiguous blocks
  *     [g N / G, (g + 1) N / G), one per device, and run them concurrently on the devices' own streams -- the
  *     reference's fan-out of one integrate() over num_threads worker processes (integrator.py:121-142, 386-395).
  *     Members are independent, nothing is exchanged, results are bitwise those of one device.  Handles and

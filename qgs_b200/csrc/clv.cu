@@ -246,22 +246,14 @@ __global__ void __launch_bounds__(64) subspace_kernel(const __grid_constant__ Su
 
 using namespace qgsb;
 
-extern "C" int qgsb_clv_ginelli(const qgsb_tensor *t, long N, const double *ic, int n_vec, const double *q0,
-                                const double *r0, long n_pre, long n_time, long n_after, const double *dt_macro,
-                                const long *sub_ptr, const double *sub_dt, int s, const double *a, const double *b,
-                                const double *c, long write_steps, double noise_pert, const double *am0,
-                                const double *noise, const double *dte, long R, double *rec_traj, double *rec_exp,
-                                double *rec_vec, double *device_ms)
+// one device's share of qgsb_clv_ginelli: members [0, N) of every member-major array, on the calling thread's device
+static void ginelli_device(const qgsb_tensor *t, long N, const double *ic, int n_vec, const double *q0,
+                           const double *r0, long n_pre, long n_time, long n_after, const double *dt_macro,
+                           const long *sub_ptr, const double *sub_dt, int s, const double *a, const double *b,
+                           long write_steps, double noise_pert, const double *am0, const double *noise,
+                           const double *dte, long R, double *rec_traj, double *rec_exp, double *rec_vec,
+                           double *device_ms)
 {
-    (void)c;
-    QGSB_API_BEGIN
-    QGSB_REQUIRE(t && ic && q0 && dt_macro && sub_ptr && sub_dt && am0 && dte && rec_traj && rec_exp && rec_vec,
-                 "null argument");
-    QGSB_REQUIRE(N >= 1 && n_pre >= 0 && n_time >= 0 && n_after >= 0 && write_steps >= 0, "bad sizes");
-    QGSB_REQUIRE(n_vec >= 1 && n_vec <= t->view.n && n_vec <= 1024, "n_vec must be in 1..min(n_dim, 1024)");
-    QGSB_REQUIRE(t->jnnz_in > 0, "tensor handle has no Jacobian tensor");
-    QGSB_REQUIRE(noise_pert == 0. || noise != nullptr, "noise_pert needs a noise array");
-    ensure_init();
     Context &cx = ctx();
     cudaStream_t st = cx.stream;
     const Tableau tab = make_tableau(s, a, b);
@@ -357,6 +349,38 @@ extern "C" int qgsb_clv_ginelli(const qgsb_tensor *t, long N, const double *ic, 
         total_ms += ms;
     }
     if (device_ms) *device_ms = total_ms;
+}
+
+extern "C" int qgsb_clv_ginelli(const qgsb_tensor *t, long N, const double *ic, int n_vec, const double *q0,
+                                const double *r0, long n_pre, long n_time, long n_after, const double *dt_macro,
+                                const long *sub_ptr, const double *sub_dt, int s, const double *a, const double *b,
+                                const double *c, long write_steps, double noise_pert, const double *am0,
+                                const double *noise, const double *dte, long R, double *rec_traj, double *rec_exp,
+                                double *rec_vec, double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t && ic && q0 && dt_macro && sub_ptr && sub_dt && am0 && dte && rec_traj && rec_exp && rec_vec,
+                 "null argument");
+    QGSB_REQUIRE(N >= 1 && n_pre >= 0 && n_time >= 0 && n_after >= 0 && write_steps >= 0, "bad sizes");
+    QGSB_REQUIRE(n_vec >= 1 && n_vec <= t->view.n && n_vec <= 1024, "n_vec must be in 1..min(n_dim, 1024)");
+    QGSB_REQUIRE(t->jnnz_in > 0, "tensor handle has no Jacobian tensor");
+    QGSB_REQUIRE(noise_pert == 0. || noise != nullptr, "noise_pert needs a noise array");
+    ensure_init();
+    // members are independent (every one carries its own basis and recursion): contiguous blocks, one per device
+    const int n = t->view.n, m = n_vec;
+    const size_t nm = (size_t)n * m, mm = (size_t)m * m;
+    const long tew = n_time + n_after;
+    const int parts = shard_count(N, 512);
+    std::vector<double> ms(parts, 0.);
+    run_sharded(N, parts, [&](int g, long lo, long hi) {
+        ginelli_device(tensor_here(t), hi - lo, ic + (size_t)lo * n, n_vec, q0 + (size_t)lo * nm,
+                       r0 ? r0 + (size_t)lo * mm : nullptr, n_pre, n_time, n_after, dt_macro, sub_ptr, sub_dt, s, a, b,
+                       write_steps, noise_pert, am0 + (size_t)lo * mm, noise ? noise + (size_t)lo * tew * m : nullptr,
+                       dte, R, rec_traj + (size_t)lo * n * R, rec_exp + (size_t)lo * m * R,
+                       rec_vec + (size_t)lo * nm * R, &ms[g]);
+    });
+    if (device_ms) *device_ms = *std::max_element(ms.begin(), ms.end());
     QGSB_API_END
 }
 

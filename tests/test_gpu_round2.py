@@ -154,8 +154,8 @@ def _n_devices():
 
 @pytest.mark.skipif("_n_devices() < 2")
 def test_members_sharded_over_the_devices_of_one_process_are_bitwise_one_device():
-    """qgsb_rk_integrate / qgsb_rk_tgls_integrate / qgsb_lyap_benettin split the members over every device the process
-    drives (the reference deals trajectories to num_threads workers, integrator.py:386-395).  Same results, bit for
+    """qgsb_rk_integrate / qgsb_rk_tgls_integrate / qgsb_lyap_benettin / qgsb_clv_ginelli split the members over every
+    device the process drives (the reference deals trajectories to num_threads workers, integrator.py:386-395).  Same results, bit for
     bit, as on one device -- through the unchanged Python classes."""
     from qgs_b200 import _lib
     from qgs_b200.integrators.integrator import RungeKuttaIntegrator, RungeKuttaTglsIntegrator
@@ -184,7 +184,15 @@ def test_members_sharded_over_the_devices_of_one_process_are_bitwise_one_device(
             np.random.seed(5)
             est.compute_lyapunovs(0., 0.5, 1.5, 0.1, 0.1, ic=ic[:4100], write_steps=5, n_vec=36, vectors=False)
             ly = est.get_lyapunovs()
-            res[len(devs)] = (end, traj, tl[1], tl[2], ly[1], ly[2])
+            from qgs_b200.toolbox.lyapunov import CovariantLyapunovsEstimator
+            frp, Dfrp, _ = model("rp")
+            clv = CovariantLyapunovsEstimator()
+            clv.set_func(frp, Dfrp)
+            np.random.seed(9)
+            clv.compute_clvs(0., 0.5, 1., 1.5, 0.1, 0.1, ic=np.random.default_rng(6).random((1100, 20)) * 0.1,
+                             write_steps=2, method=0)
+            cv = clv.get_clvs()
+            res[len(devs)] = (end, traj, tl[1], tl[2], ly[1], ly[2], cv[1], cv[2], cv[3])
     finally:
         _lib.set_devices([0])
     for x, y in zip(res[1], res[G]):
