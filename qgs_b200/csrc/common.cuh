@@ -269,7 +269,14 @@ const qgsb_tensor *tensor_here(const qgsb_tensor *t);
 struct qgsb_ensemble {
     const qgsb_tensor *tensor = nullptr;
     long N = 0, ld = 0;
+    int device = 0;                  // CUDA ordinal the arrays below live on
     qgsb::DevBuf<double> d_y;        // (n, ld)
     qgsb::DevBuf<double> d_stage;    // scratch for AoS <-> SoA staging (N * n)
     qgsb::DevBuf<double> d_dt;       // step lengths of the launch in flight
+    // A large ensemble created while the library drives several devices is a COMPOSITE: its members live in contiguous
+    // blocks [lo[g], lo[g + 1]) on the devices, each block an ordinary single-device ensemble; the handle itself then
+    // owns no device memory and every call fans out over the parts (run_sharded).
+    std::vector<qgsb_ensemble *> parts;
+    std::vector<long> lo;
+    ~qgsb_ensemble();
 };

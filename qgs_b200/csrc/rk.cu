@@ -1357,17 +1357,27 @@ int qgsb_rk_integrate(const qgsb_tensor *t, long N, const double *ic, long n_ste
 }
 
 // ---- resident ensemble ---------------------------------------------------------------------------
-int qgsb_ensemble_create(const qgsb_tensor *t, long N, qgsb_ensemble **out)
+// Every entry point has a single-device implementation (the code of round 1, on the calling thread's device) and a
+// wrapper that runs it directly or, for a composite ensemble, once per part on the part's device.
+}  // extern "C"
+
+qgsb_ensemble::~qgsb_ensemble()
 {
-    QGSB_API_BEGIN
-    QGSB_REQUIRE(t && out, "null argument");
-    QGSB_REQUIRE(N >= 1, "need at least one trajectory");
-    ensure_init();
+    for (qgsb_ensemble *p : parts) {
+        cudaSetDevice(p->device);
+        delete p;
+    }
+    if (!parts.empty() && qgsb::device_slots() > 0) cudaSetDevice(qgsb::ctx().device);
+}
+
+static qgsb_ensemble *ensemble_create_device(const qgsb_tensor *t, long N)
+{
     qgsb_ensemble *e = new qgsb_ensemble();
     try {
         e->tensor = t;
         e->N = N;
         e->ld = round_up(N, TILE);
+        e->device = ctx().device;
         e->d_y.alloc((size_t)t->view.n * e->ld);
         e->d_stage.alloc((size_t)N * t->view.n);
         QGSB_CUDA(cudaMemsetAsync(e->d_y.p, 0, sizeof(double) * t->view.n * e->ld, ctx().stream));
@@ -1375,42 +1385,22 @@ int qgsb_ensemble_create(const qgsb_tensor *t, long N, qgsb_ensemble **out)
         delete e;
         throw;
     }
-    *out = e;
-    QGSB_API_END
+    return e;
 }
 
-void qgsb_ensemble_destroy(qgsb_ensemble *e)
+static void ensemble_upload_device(qgsb_ensemble *e, const double *ic)
 {
-    if (!e) return;
-    QGSB_API_LOCK
-    if (ctx().ready) {
-        cudaSetDevice(ctx().device);
-        cudaStreamSynchronize(ctx().stream);
-    }
-    delete e;
-}
-
-int qgsb_ensemble_upload(qgsb_ensemble *e, const double *ic)
-{
-    QGSB_API_BEGIN
-    QGSB_REQUIRE(e && ic, "null argument");
-    ensure_init();
     const int n = e->tensor->view.n;
     e->d_stage.upload(ic, (size_t)e->N * n, ctx().stream);
     launch_aos_to_soa(e->d_stage.p, e->d_y.p, e->N, n, e->ld);
-    QGSB_API_END
 }
 
-int qgsb_ensemble_download(qgsb_ensemble *e, double *out)
+static void ensemble_download_device(qgsb_ensemble *e, double *out)
 {
-    QGSB_API_BEGIN
-    QGSB_REQUIRE(e && out, "null argument");
-    ensure_init();
     const int n = e->tensor->view.n;
     launch_soa_to_aos(e->d_y.p, e->d_stage.p, e->N, n, e->ld);
     e->d_stage.download(out, (size_t)e->N * n, ctx().stream);
     QGSB_CUDA(cudaStreamSynchronize(ctx().stream));
-    QGSB_API_END
 }
 
 static void ensemble_run(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a, const double *b,
@@ -1418,7 +1408,6 @@ static void ensemble_run(qgsb_ensemble *e, long n_steps, const double *dt, int s
 {
     QGSB_REQUIRE(e, "null ensemble");
     QGSB_REQUIRE(n_steps >= 0, "negative step count");
-    ensure_init();
     Context &cx = ctx();
     const Tableau tab = make_tableau(s, a, b);
     // dt staging buffer lives with the ensemble so the launch can stay asynchronous
@@ -1439,43 +1428,13 @@ static void ensemble_run(qgsb_ensemble *e, long n_steps, const double *dt, int s
     }
 }
 
-int qgsb_ensemble_integrate(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
-                            const double *b, const double *c, double *device_ms)
-{
-    (void)c;
-    QGSB_API_BEGIN
-    ensemble_run(e, n_steps, dt, s, a, b, 0, 1, nullptr, device_ms);
-    QGSB_API_END
-}
-
-int qgsb_ensemble_integrate_record(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
-                                   const double *b, const double *c, long write_steps, long R, double *d_rec,
-                                   double *device_ms)
-{
-    (void)c;
-    QGSB_API_BEGIN
-    QGSB_REQUIRE(d_rec != nullptr, "null record buffer");
-    QGSB_REQUIRE(R == records_for(n_steps, write_steps), "n_records %ld inconsistent with %ld steps / write_steps %ld",
-                 R, n_steps, write_steps);
-    ensemble_run(e, n_steps, dt, s, a, b, write_steps, R, d_rec, device_ms);
-    QGSB_API_END
-}
-
 // Ensemble statistics without the (N, n, R) dump of TrajectoriesStatistics.compute_stats
 // (qgs/integrators/statistics.py:33-66): integrate, keep the records of a bounded number of write steps in HBM,
 // reduce them to per-record sums on the device, continue.  Record semantics are those of integrate.py:190-221.
-int qgsb_ensemble_integrate_moments(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
-                                    const double *b, const double *c, long write_steps, long R, double *sum,
-                                    double *sumsq, double *device_ms)
+static void ensemble_moments_run_device(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                                        const double *b, long write_steps, long R, double *sum, double *sumsq,
+                                        double *device_ms)
 {
-    (void)c;
-    QGSB_API_BEGIN
-    QGSB_REQUIRE(e && sum && sumsq, "null argument");
-    QGSB_REQUIRE(n_steps >= 0 && write_steps >= 0, "negative step count");
-    QGSB_REQUIRE(n_steps == 0 || dt != nullptr, "null dt array");
-    QGSB_REQUIRE(R == records_for(n_steps, write_steps), "n_records %ld inconsistent with %ld steps / write_steps %ld",
-                 R, n_steps, write_steps);
-    ensure_init();
     Context &cx = ctx();
     cudaStream_t st = cx.stream;
     const Tableau tab = make_tableau(s, a, b);
@@ -1511,6 +1470,187 @@ int qgsb_ensemble_integrate_moments(qgsb_ensemble *e, long n_steps, const double
         QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
         *device_ms = ms;
     }
+}
+
+static void ensemble_trajectories_device(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                                         const double *b, long write_steps, int time_direction, long R, double *traj,
+                                         double *device_ms)
+{
+    Context &cx = ctx();
+    const Tableau tab = make_tableau(s, a, b);
+    PoolBuf<double> d_dt(std::max<long>(n_steps, 1));
+    if (n_steps) d_dt.upload(dt, n_steps, cx.stream);
+    stream_trajectories(e->tensor, e->d_y.p, e->ld, e->N, n_steps, d_dt.p, tab, write_steps, time_direction, R, traj);
+    if (device_ms) {
+        float ms = 0.f;
+        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
+        *device_ms = ms;
+    }
+}
+
+// runs body(g, part, first member of the part) for every part of a composite on the part's device; returns the largest
+// of the device times the bodies report
+template <class F>
+static double over_parts(qgsb_ensemble *e, F &&body)
+{
+    const int parts = (int)e->parts.size();
+    std::vector<double> ms(parts, 0.);
+    run_sharded(e->N, parts, [&](int g, long, long) { ms[g] = body(g, e->parts[g], e->lo[g]); });
+    return *std::max_element(ms.begin(), ms.end());
+}
+
+extern "C" {
+
+int qgsb_ensemble_create(const qgsb_tensor *t, long N, qgsb_ensemble **out)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(t && out, "null argument");
+    QGSB_REQUIRE(N >= 1, "need at least one trajectory");
+    ensure_init();
+    const int parts = shard_count(N, std::max<long>(4096, 2 * rows_threshold()));
+    if (parts <= 1) {
+        *out = ensemble_create_device(t, N);
+        return 0;
+    }
+    qgsb_ensemble *e = new qgsb_ensemble();
+    e->tensor = t;
+    e->N = N;
+    e->device = ctx().device;
+    e->parts.assign(parts, nullptr);
+    e->lo.assign(parts + 1, 0);
+    for (int g = 0; g <= parts; ++g) e->lo[g] = (long)((__int128)g * N / parts);      // shard_range of run_sharded
+    try {
+        run_sharded(N, parts, [&](int g, long lo, long hi) { e->parts[g] = ensemble_create_device(tensor_here(t), hi - lo); });
+    } catch (...) {
+        delete e;
+        throw;
+    }
+    *out = e;
+    QGSB_API_END
+}
+
+void qgsb_ensemble_destroy(qgsb_ensemble *e)
+{
+    if (!e) return;
+    QGSB_API_LOCK
+    if (device_slots() > 0 && ctx().ready) {
+        cudaSetDevice(ctx().device);
+        cudaStreamSynchronize(ctx().stream);
+    }
+    delete e;
+}
+
+int qgsb_ensemble_upload(qgsb_ensemble *e, const double *ic)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(e && ic, "null argument");
+    ensure_init();
+    const int n = e->tensor->view.n;
+    if (e->parts.empty()) {
+        ensemble_upload_device(e, ic);
+    } else {
+        over_parts(e, [&](int, qgsb_ensemble *p, long lo) {
+            ensemble_upload_device(p, ic + (size_t)lo * n);
+            QGSB_CUDA(cudaStreamSynchronize(ctx().stream));     // the worker thread's stream must be done before it leaves
+            return 0.;
+        });
+    }
+    QGSB_API_END
+}
+
+int qgsb_ensemble_download(qgsb_ensemble *e, double *out)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(e && out, "null argument");
+    ensure_init();
+    const int n = e->tensor->view.n;
+    if (e->parts.empty()) {
+        ensemble_download_device(e, out);
+    } else {
+        over_parts(e, [&](int, qgsb_ensemble *p, long lo) {
+            ensemble_download_device(p, out + (size_t)lo * n);
+            return 0.;
+        });
+    }
+    QGSB_API_END
+}
+
+int qgsb_ensemble_integrate(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                            const double *b, const double *c, double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(e, "null ensemble");
+    ensure_init();
+    if (e->parts.empty()) {
+        ensemble_run(e, n_steps, dt, s, a, b, 0, 1, nullptr, device_ms);
+    } else {
+        // a composite is always integrated to completion: the worker threads do not outlive the call
+        const double ms = over_parts(e, [&](int, qgsb_ensemble *p, long) {
+            double part = 0.;
+            ensemble_run(p, n_steps, dt, s, a, b, 0, 1, nullptr, &part);
+            return part;
+        });
+        if (device_ms) *device_ms = ms;
+    }
+    QGSB_API_END
+}
+
+int qgsb_ensemble_integrate_record(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                                   const double *b, const double *c, long write_steps, long R, double *d_rec,
+                                   double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(e, "null ensemble");
+    QGSB_REQUIRE(d_rec != nullptr, "null record buffer");
+    QGSB_REQUIRE(e->parts.empty(), "a record buffer on one device cannot take an ensemble spread over %zu devices; use "
+                 "qgsb_ensemble_integrate_trajectories or create the ensemble under qgsb_set_devices(1, ...)",
+                 e->parts.size());
+    QGSB_REQUIRE(R == records_for(n_steps, write_steps), "n_records %ld inconsistent with %ld steps / write_steps %ld",
+                 R, n_steps, write_steps);
+    ensure_init();
+    ensemble_run(e, n_steps, dt, s, a, b, write_steps, R, d_rec, device_ms);
+    QGSB_API_END
+}
+
+int qgsb_ensemble_integrate_moments(qgsb_ensemble *e, long n_steps, const double *dt, int s, const double *a,
+                                    const double *b, const double *c, long write_steps, long R, double *sum,
+                                    double *sumsq, double *device_ms)
+{
+    (void)c;
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(e && sum && sumsq, "null argument");
+    QGSB_REQUIRE(n_steps >= 0 && write_steps >= 0, "negative step count");
+    QGSB_REQUIRE(n_steps == 0 || dt != nullptr, "null dt array");
+    QGSB_REQUIRE(R == records_for(n_steps, write_steps), "n_records %ld inconsistent with %ld steps / write_steps %ld",
+                 R, n_steps, write_steps);
+    ensure_init();
+    if (e->parts.empty()) {
+        ensemble_moments_run_device(e, n_steps, dt, s, a, b, write_steps, R, sum, sumsq, device_ms);
+    } else {
+        // per-part sums, added in part order (deterministic)
+        const int n = e->tensor->view.n;
+        const size_t len = (size_t)R * n;
+        const int parts = (int)e->parts.size();
+        std::vector<double> s1(len * parts), s2(len * parts);
+        const double ms = over_parts(e, [&](int g, qgsb_ensemble *p, long) {
+            double part = 0.;
+            ensemble_moments_run_device(p, n_steps, dt, s, a, b, write_steps, R, s1.data() + len * g,
+                                        s2.data() + len * g, &part);
+            return part;
+        });
+        for (size_t q = 0; q < len; ++q) {
+            double t1 = 0., t2 = 0.;
+            for (int g = 0; g < parts; ++g) {
+                t1 += s1[len * g + q];
+                t2 += s2[len * g + q];
+            }
+            sum[q] = t1;
+            sumsq[q] = t2;
+        }
+        if (device_ms) *device_ms = ms;
+    }
     QGSB_API_END
 }
 
@@ -1528,21 +1668,25 @@ int qgsb_ensemble_integrate_trajectories(qgsb_ensemble *e, long n_steps, const d
     QGSB_REQUIRE(R == records_for(n_steps, write_steps), "n_records %ld inconsistent with %ld steps / write_steps %ld",
                  R, n_steps, write_steps);
     ensure_init();
-    Context &cx = ctx();
-    const Tableau tab = make_tableau(s, a, b);
-    PoolBuf<double> d_dt(std::max<long>(n_steps, 1));
-    if (n_steps) d_dt.upload(dt, n_steps, cx.stream);
-    stream_trajectories(e->tensor, e->d_y.p, e->ld, e->N, n_steps, d_dt.p, tab, write_steps, time_direction, R, traj);
-    if (device_ms) {
-        float ms = 0.f;
-        QGSB_CUDA(cudaEventElapsedTime(&ms, cx.ev0, cx.ev1));
-        *device_ms = ms;
+    if (e->parts.empty()) {
+        ensemble_trajectories_device(e, n_steps, dt, s, a, b, write_steps, time_direction, R, traj, device_ms);
+    } else {
+        const int n = e->tensor->view.n;
+        const double ms = over_parts(e, [&](int, qgsb_ensemble *p, long lo) {
+            double part = 0.;
+            ensemble_trajectories_device(p, n_steps, dt, s, a, b, write_steps, time_direction, R,
+                                         traj + (size_t)lo * n * R, &part);
+            return part;
+        });
+        if (device_ms) *device_ms = ms;
     }
     QGSB_API_END
 }
 
-void *qgsb_ensemble_device_ptr(qgsb_ensemble *e) { return e ? (void *)e->d_y.p : nullptr; }
-long qgsb_ensemble_ld(const qgsb_ensemble *e) { return e ? e->ld : 0; }
+// Device pointer / leading dimension of the state: defined for an ensemble on ONE device only (a composite returns
+// NULL / 0).
+void *qgsb_ensemble_device_ptr(qgsb_ensemble *e) { return (e && e->parts.empty()) ? (void *)e->d_y.p : nullptr; }
+long qgsb_ensemble_ld(const qgsb_ensemble *e) { return (e && e->parts.empty()) ? e->ld : 0; }
 
 int qgsb_dmma_peak(double *tflops)
 {

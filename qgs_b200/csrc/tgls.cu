@@ -982,17 +982,40 @@ int qgsb_lyap_benettin(const qgsb_tensor *t, long N, const double *ic, int forwa
     QGSB_API_END
 }
 
-int qgsb_ensemble_moments(qgsb_ensemble *e, double *sum, double *sumsq)
+static void ensemble_moments_device(qgsb_ensemble *e, double *sum, double *sumsq)
 {
-    QGSB_API_BEGIN
-    QGSB_REQUIRE(e && sum && sumsq, "null argument");
-    ensure_init();
     const int n = e->tensor->view.n;
     PoolBuf<double> d_out((size_t)2 * n);
     launch_record_moments(e->d_y.p, 1, e->N, n, e->ld, d_out.p, d_out.p + n);
     d_out.download(sum, n, ctx().stream);
     QGSB_CUDA(cudaMemcpyAsync(sumsq, d_out.p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx().stream));
     QGSB_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+
+int qgsb_ensemble_moments(qgsb_ensemble *e, double *sum, double *sumsq)
+{
+    QGSB_API_BEGIN
+    QGSB_REQUIRE(e && sum && sumsq, "null argument");
+    ensure_init();
+    if (e->parts.empty()) {
+        ensemble_moments_device(e, sum, sumsq);
+    } else {
+        // per-part sums on the parts' devices, added in part order (deterministic)
+        const int n = e->tensor->view.n, parts = (int)e->parts.size();
+        std::vector<double> s1((size_t)n * parts), s2((size_t)n * parts);
+        run_sharded(e->N, parts, [&](int g, long, long) {
+            ensemble_moments_device(e->parts[g], s1.data() + (size_t)n * g, s2.data() + (size_t)n * g);
+        });
+        for (int i = 0; i < n; ++i) {
+            double t1 = 0., t2 = 0.;
+            for (int g = 0; g < parts; ++g) {
+                t1 += s1[(size_t)n * g + i];
+                t2 += s2[(size_t)n * g + i];
+            }
+            sum[i] = t1;
+            sumsq[i] = t2;
+        }
+    }
     QGSB_API_END
 }
 

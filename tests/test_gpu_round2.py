@@ -199,6 +199,38 @@ def test_members_sharded_over_the_devices_of_one_process_are_bitwise_one_device(
         assert np.array_equal(x, y)
 
 
+@pytest.mark.skipif("_n_devices() < 2")
+def test_resident_ensemble_spread_over_the_devices_of_one_process():
+    """qgsb_ensemble_* with several devices: a large resident ensemble is a composite of one block per device.  States
+    and streamed trajectories are bitwise those of one device; the moments agree to rounding (other summation order)."""
+    from qgs_b200 import _lib
+    from qgs_b200.ensemble import DeviceEnsemble
+    f, Df, T = model("maooam36")
+    ic = np.random.default_rng(14).random((2 * 8192 + 300, 36)) * 0.01
+    G = _n_devices()
+    res = {}
+    try:
+        for devs in ([0], list(range(G))):
+            _lib.set_devices(devs)
+            ens = DeviceEnsemble(f, ic)
+            ens.integrate(0., 1., 0.1)
+            a = ens.states()
+            t, traj = ens.integrate_trajectories(1., 1.6, 0.1, write_steps=2)
+            tm, mean, var = ens.integrate_moments(1.6, 2.2, 0.1, write_steps=3)
+            m1, v1 = ens.moments()
+            ens.set_states(a)
+            b = ens.states()
+            ens.close()
+            res[len(devs)] = (a, traj, mean, var, m1, v1, b)
+    finally:
+        _lib.set_devices([0])
+    one, many = res[1], res[G]
+    assert np.array_equal(one[0], many[0]) and np.array_equal(one[1], many[1]) and np.array_equal(one[6], many[6])
+    assert np.array_equal(one[0], one[6])
+    for k in (2, 3, 4, 5):
+        assert np.allclose(one[k], many[k], rtol=1e-12, atol=1e-18)
+
+
 # ---- long-run statistics on the headline model ---------------------------------------------------------------------------
 def test_maooam36_long_run_moments_and_leading_exponents_match_the_oracle():
     """BASELINE.json's third criterion on MAOOAM-36 itself: an ensemble is spun up ON THE GPU to the attractor
