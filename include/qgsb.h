@@ -21,8 +21,9 @@
  *     qgsb_rk_tgls_integrate, qgsb_lyap_benettin and qgsb_clv_ginelli split the members into contiguous blocks
  *     [g N / G, (g + 1) N / G), one per device, and run them concurrently on the devices' own streams -- the
  *     reference's fan-out of one integrate() over num_threads worker processes (integrator.py:121-142, 386-395).
- *     Members are independent, nothing is exchanged, results are bitwise those of one device.  Handles and
- *     resident ensembles live on the primary device (the first of the list).
+ *     Members are independent, nothing is exchanged, results are bitwise those of one device.  Tensor handles
+ *     live on the primary device (the first of the list; the library replicates them where needed); a large resident
+ *     ensemble is spread over the devices like the host-buffer calls are.
  *   - there is no CPU fallback: without a CUDA device every compute call fails with an error.
  */
 #ifndef QGSB_H
@@ -216,6 +217,8 @@ QGSB_API int qgsb_ensemble_integrate_moments(qgsb_ensemble *e, long n_steps, con
                                              const double *b, const double *c, long write_steps, long n_records,
                                              double *sum /* host (R, n) */, double *sumsq /* host (R, n) */,
                                              double *device_ms);
+/* Device pointer / leading dimension of the state -- for an ensemble that lives on ONE device; NULL / 0 for an ensemble
+ * spread over several (qgsb_ensemble_integrate_record, which takes a device record buffer, refuses those too). */
 QGSB_API void *qgsb_ensemble_device_ptr(qgsb_ensemble *e);
 QGSB_API long qgsb_ensemble_ld(const qgsb_ensemble *e);
 QGSB_API int qgsb_synchronize(void);
