@@ -22,7 +22,15 @@ namespace qgsb {
 
 struct TgShared {
     double *xs, *y, *Y, *K, *Jv, *rdiag, *mexp, *red, *fm, *kms, *KM;
+    double *Jd;      // dense Jacobian of the member in the global scratch (large bases), else null
+    double *tile;    // shared-memory staging of one 32 x 32 block of the stage input (dense product)
 };
+
+constexpr int DP_KB = 32;             // rows of the stage input staged per block
+constexpr int DP_NB = 32;             // columns per chunk (four 8-wide tensor-core tiles)
+constexpr int DP_STRIDE = 36;         // row stride of the staged block in doubles: the 16 lanes of a half warp read
+                                      // rows 0..3 x columns 0..3 of a tile -- 36 = 4 mod 16 spreads them over all banks
+constexpr int DP_TILE_DOUBLES = DP_KB * DP_STRIDE;
 
 __device__ __forceinline__ TgShared carve(unsigned char *raw, const TensorView &T, const TgParams &P, long member)
 {
@@ -33,7 +41,8 @@ __device__ __forceinline__ TgShared carve(unsigned char *raw, const TensorView &
     S.y = p;             p += n;
     S.Y = p;             p += n;
     S.K = p;             p += (size_t)s * n;
-    S.Jv = p;            p += T.jac.npos;
+    S.Jv = p;            p += P.jd_ld ? 0 : T.jac.npos;     // dense J lives in the scratch instead
+    S.tile = p;          p += P.jd_ld ? DP_TILE_DOUBLES : 0;
     S.rdiag = p;         p += m;
     S.mexp = p;          p += m;      // local exponent of every vector at the last macro step
     S.red = p;           p += 64;
@@ -41,6 +50,7 @@ __device__ __forceinline__ TgShared carve(unsigned char *raw, const TensorView &
     S.fm = mat;
     S.kms = mat + (size_t)n * m;
     S.KM = mat + (size_t)2 * n * m;
+    S.Jd = P.jd_ld ? mat + (size_t)(s + 2) * n * m : nullptr;
     return S;
 }
 
@@ -70,8 +80,81 @@ __device__ void nl_step(const TensorView &T, const TgParams &P, const TgShared &
     __syncthreads();
 }
 
+// ---- large bases: out = scale * Jd @ X on the FP64 tensor cores ---------------------------------------------------------
+// BASELINE.json allows the tensor cores "only where a dense formulation is measured to beat the sparse kernel for large
+// bases".  For the TENDENCIES it never does (section 4.2 of DESIGN.md: 100x the flops at the same peak).  For the
+// tangent product it does: the Jacobian of the 228-variable model has 26 140 structurally non-zero positions of 51 984
+// (50 % dense, 79 % of the 8 x 4 operand tiles non-empty), the sparse product walks them once per COLUMN of X with
+// operands in L2, and the dense product is a GEMM, (n x n) @ (n x m) per stage and member, whose operands are reused
+// from registers and shared memory.  mma.sync.m8n8k4.f64: A (8 x 4) lane l holds A[l / 4][l % 4]; B (4 x 8) lane l holds
+// B[l % 4][l / 4]; C (8 x 8) lane l holds C[l / 4][2 (l % 4) + {0, 1}].
+// Jd is (ld x ld) row-major with rows / columns >= n zero; X and out are (n x m) row-major.  A warp owns row tiles
+// w, w + 4, ... (at most 8) and sweeps the columns in chunks of 32: the 32 x 32 block of X of every k step is staged in
+// shared memory once for the four warps, the A fragments come straight from L2 (each is used for the four column tiles
+// of the chunk).
+__device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ void dense_product(const double *__restrict__ Jd, int ld, const double *__restrict__ X, double *__restrict__ out,
+                              int n, int m, double scale, double *tile)
+{
+    constexpr int WARPS = TG_THREADS / 32, MAX_RT = 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row_tiles = ld / 8;
+    const int ar = lane >> 2, ac = lane & 3;          // A: row in tile, column in k chunk;  B: ac = row in k chunk, ar = column
+    for (int c0 = 0; c0 < m; c0 += DP_NB) {
+        double acc[MAX_RT][4][2];
+#pragma unroll
+        for (int r = 0; r < MAX_RT; ++r)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[r][t][0] = acc[r][t][1] = 0.;
+        for (int kb = 0; kb < ld; kb += DP_KB) {
+            __syncthreads();                           // the previous block has been consumed
+            for (int q = tid; q < DP_KB * DP_NB; q += TG_THREADS) {
+                const int kr = q / DP_NB, cc = q - kr * DP_NB;
+                const int row = kb + kr, col = c0 + cc;
+                tile[kr * DP_STRIDE + cc] = (row < n && col < m) ? X[(size_t)row * m + col] : 0.;
+            }
+            __syncthreads();
+#pragma unroll 2
+            for (int kk = 0; kk < DP_KB / 4; ++kk) {
+                if (kb + kk * 4 >= ld) break;
+                double bf[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) bf[t] = tile[(kk * 4 + ac) * DP_STRIDE + t * 8 + ar];
+                double af[MAX_RT];
+#pragma unroll
+                for (int r = 0; r < MAX_RT; ++r) {
+                    const int rt = warp + r * WARPS;
+                    af[r] = rt < row_tiles ? Jd[(size_t)(rt * 8 + ar) * ld + kb + kk * 4 + ac] : 0.;
+                }
+#pragma unroll
+                for (int r = 0; r < MAX_RT; ++r)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) dmma_884(acc[r][t][0], acc[r][t][1], af[r], bf[t]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < MAX_RT; ++r) {
+            const int row = (warp + r * WARPS) * 8 + ar;
+            if (row >= n) continue;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int col = c0 + t * 8 + 2 * ac;
+                if (col < m) out[(size_t)row * m + col] = scale * acc[r][t][0];
+                if (col + 1 < m) out[(size_t)row * m + col + 1] = scale * acc[r][t][1];
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // one step of the coupled system (integrate.py:590-609): S.y and S.fm advance by dt
-template <int RANK>
+template <int RANK, bool DENSE>
 __device__ void tg_step(const TensorView &T, const TgParams &P, const TgShared &S, double dt)
 {
     const int n = T.n, m = P.m, s = P.s, tid = threadIdx.x;
@@ -98,10 +181,22 @@ __device__ void tg_step(const TensorView &T, const TgParams &P, const TgShared &
         __syncthreads();
         // tendencies and Jacobian positions at the stage state
         for (int r = tid; r < n; r += TG_THREADS) S.K[(size_t)st * n + r] = f_row<RANK>(T, r + 1, S.xs);
+        double *out = S.KM + (size_t)st * nm;
+        if (DENSE) {
+            // large bases: the position values go into the member's dense matrix (transposed for the adjoint; the
+            // structural zeros were written once at kernel start) and the product runs on the tensor cores
+            const int ld = P.jd_ld;
+            for (int p = tid; p < J.npos; p += TG_THREADS) {
+                const int i = J.pos_i[p] - 1, j = J.pos_j[p] - 1;
+                S.Jd[P.adjoint ? (size_t)j * ld + i : (size_t)i * ld + j] = jac_pos<RANK>(J, p, S.xs);
+            }
+            __syncthreads();
+            dense_product(S.Jd, ld, S.kms, out, n, m, P.inverse, S.tile);
+            continue;
+        }
         for (int p = tid; p < J.npos; p += TG_THREADS) S.Jv[p] = jac_pos<RANK>(J, p, S.xs);
         __syncthreads();
         // km_i = inverse * (J or J^T) @ km_s          :601-603 with boundary == 0
-        double *out = S.KM + (size_t)st * nm;
         for (int q = tid; q < nm; q += TG_THREADS) {
             const int r = q / m + 1, c = q - (r - 1) * m;
             double acc = 0.;
@@ -134,7 +229,7 @@ __device__ void tg_step(const TensorView &T, const TgParams &P, const TgShared &
 // ------------------------------------------------------------------------------------------------
 // plain TGLS integration
 // ------------------------------------------------------------------------------------------------
-template <int RANK>
+template <int RANK, bool DENSE>
 __global__ void __launch_bounds__(TG_THREADS) tgls_kernel(TensorView T, const __grid_constant__ TgParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -143,6 +238,8 @@ __global__ void __launch_bounds__(TG_THREADS) tgls_kernel(TensorView T, const __
     TgShared S = carve(smem_raw, T, P, member);
     for (int r = tid; r < n; r += TG_THREADS) S.y[r] = P.y[member * n + r];
     for (int q = tid; q < nm; q += TG_THREADS) S.fm[q] = P.fm[member * nm + q];
+    if (DENSE)
+        for (int q = tid; q < P.jd_ld * P.jd_ld; q += TG_THREADS) S.Jd[q] = 0.;     // structural zeros, written once
     if (tid == 0) S.xs[0] = 1.;
     __syncthreads();
     long iw = 0;
@@ -154,7 +251,7 @@ __global__ void __launch_bounds__(TG_THREADS) tgls_kernel(TensorView T, const __
             for (int q = tid; q < nm; q += TG_THREADS) rf[q] = S.fm[q];
             ++iw;
         }
-        tg_step<RANK>(T, P, S, P.dt[ti]);
+        tg_step<RANK, DENSE>(T, P, S, P.dt[ti]);
     }
     if (P.rec_y) {                                                           // integrate.py:611-612
         double *ry = P.rec_y + ((size_t)(P.n_records - 1) * P.n_members + member) * n;
@@ -278,7 +375,7 @@ __device__ void block_qr(int n, int m, double *A, double *W, double *rdiag, doub
 // ------------------------------------------------------------------------------------------------
 // Benettin loop
 // ------------------------------------------------------------------------------------------------
-template <int RANK>
+template <int RANK, bool DENSE>
 __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __grid_constant__ TgParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -291,6 +388,8 @@ __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __
     for (int r = tid; r < n; r += TG_THREADS) S.Y[r] = P.y[member * n + r];
     for (int q = tid; q < nm; q += TG_THREADS) S.fm[q] = P.fm[member * nm + q];
     for (int c = tid; c < m; c += TG_THREADS) S.rdiag[c] = P.r0 ? P.r0[((size_t)member * m + c) * m + c] : 0.;
+    if (DENSE)
+        for (int q = tid; q < P.jd_ld * P.jd_ld; q += TG_THREADS) S.Jd[q] = 0.;     // structural zeros, written once
     if (tid == 0) S.xs[0] = 1.;
     __syncthreads();
     const size_t sbase = P.stored ? tile_base(member, n) : 0;
@@ -327,7 +426,7 @@ __global__ void __launch_bounds__(TG_THREADS) lyap_kernel(TensorView T, const __
         if (real) {
             for (int r = tid; r < n; r += TG_THREADS) S.y[r] = S.Y[r];
             __syncthreads();
-            for (long q = P.sub_ptr[step]; q < P.sub_ptr[step + 1]; ++q) tg_step<RANK>(T, P, S, P.sub_dt[q]);
+            for (long q = P.sub_ptr[step]; q < P.sub_ptr[step + 1]; ++q) tg_step<RANK, DENSE>(T, P, S, P.sub_dt[q]);
         }
         // q_new = prop @ q ; q, r = qr(q_new)   (:602-604) -- fm already holds prop @ q by linearity
         block_qr(n, m, S.fm, S.kms, S.rdiag, S.red, (real && P.r_all && step >= P.r_first) ? P.r_all + ((size_t)member * (steps - P.r_first) + (step - P.r_first)) * m * m : nullptr);
@@ -492,10 +591,20 @@ __global__ void moments_kernel(const double *__restrict__ y, long N, int n, doub
 }
 
 // ------------------------------------------------------------------------------------------------
-static size_t tg_small_doubles(const qgsb_tensor *t, int m, int s)
+static size_t tg_small_doubles(const qgsb_tensor *t, int m, int s, bool dense)
 {
     const int n = t->view.n;
-    return (size_t)(n + 1) + 2 * (size_t)n + (size_t)s * n + t->view.jac.npos + 2 * (size_t)m + 64;
+    return (size_t)(n + 1) + 2 * (size_t)n + (size_t)s * n + (dense ? DP_TILE_DOUBLES : t->view.jac.npos) +
+           2 * (size_t)m + 64;
+}
+
+// Large bases run the product J @ X as a dense GEMM on the FP64 tensor cores (dense_product): decided here, per launch.
+// QGSB_TGLS_DENSE = 0 / 1 forces the sparse / the dense product (A/B measurements, tests).
+static void choose_product(const qgsb_tensor *t, TgParams &P)
+{
+    const char *env = getenv("QGSB_TGLS_DENSE");
+    const bool dense = env ? env[0] != '0' : (t->view.n >= 64 && P.m >= 8);
+    P.jd_ld = dense ? (int)round_up(t->view.n, 8) : 0;
 }
 
 static void fill_common(TgParams &P, const Tableau &tab, long N, int m, int adjoint, double inverse)
@@ -516,8 +625,9 @@ static void fill_common(TgParams &P, const Tableau &tab, long N, int m, int adjo
 static size_t place_matrices(const qgsb_tensor *t, TgParams &P, DevBuf<double> &scratch, size_t extra_mats)
 {
     const int n = t->view.n;
-    const size_t small = tg_small_doubles(t, P.m, P.s) * 8;
-    const size_t mats = ((size_t)(P.s + 2) * n * P.m + extra_mats) * 8;
+    choose_product(t, P);
+    const size_t small = tg_small_doubles(t, P.m, P.s, P.jd_ld != 0) * 8;
+    const size_t mats = ((size_t)(P.s + 2) * n * P.m + extra_mats + (size_t)P.jd_ld * P.jd_ld) * 8;
     QGSB_REQUIRE(small + 1024 <= ctx().smem_optin, "model too large for the tangent-linear kernel (%zu bytes of state)",
                  small);
     if (small + mats <= ctx().smem_optin) {
@@ -544,16 +654,20 @@ void benettin_dispatch(const qgsb_tensor *t, const Tableau &tab, TgParams &P, De
     cudaStream_t st = ctx().stream;
     if (pack_tangent_supported(t, tab, m)) {
         launch_pack_tangent(t, P, true);
-    } else if (t->view.rank == 5) {
-        const size_t bytes = place_matrices(t, P, scratch, 0);
-        set_smem_attr(lyap_kernel<5>, bytes);
-        lyap_kernel<5><<<(unsigned)P.n_members, TG_THREADS, bytes, st>>>(t->view, P);
-        count_launch();
     } else {
         const size_t bytes = place_matrices(t, P, scratch, 0);
-        set_smem_attr(lyap_kernel<3>, bytes);
-        lyap_kernel<3><<<(unsigned)P.n_members, TG_THREADS, bytes, st>>>(t->view, P);
-        count_launch();
+        auto go = [&](auto kernel) {
+            set_smem_attr(kernel, bytes);
+            kernel<<<(unsigned)P.n_members, TG_THREADS, bytes, st>>>(t->view, P);
+            count_launch();
+        };
+        if (t->view.rank == 5) {
+            if (P.jd_ld) go(lyap_kernel<5, true>);
+            else go(lyap_kernel<5, false>);
+        } else {
+            if (P.jd_ld) go(lyap_kernel<3, true>);
+            else go(lyap_kernel<3, false>);
+        }
     }
     QGSB_CUDA(cudaGetLastError());
 }
@@ -632,16 +746,20 @@ struct TglsBatch {
         QGSB_CUDA(cudaEventRecord(ev0, st));
         if (pack_tangent_supported(t, tab, m)) {
             launch_pack_tangent(t, P, false);
-        } else if (t->view.rank == 5) {
-            const size_t bytes = place_matrices(t, P, scratch, 0);
-            set_smem_attr(tgls_kernel<5>, bytes);
-            tgls_kernel<5><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
-            count_launch();
         } else {
             const size_t bytes = place_matrices(t, P, scratch, 0);
-            set_smem_attr(tgls_kernel<3>, bytes);
-            tgls_kernel<3><<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
-            count_launch();
+            auto go = [&](auto kernel) {
+                set_smem_attr(kernel, bytes);
+                kernel<<<(unsigned)N, TG_THREADS, bytes, st>>>(t->view, P);
+                count_launch();
+            };
+            if (t->view.rank == 5) {
+                if (P.jd_ld) go(tgls_kernel<5, true>);
+                else go(tgls_kernel<5, false>);
+            } else {
+                if (P.jd_ld) go(tgls_kernel<3, true>);
+                else go(tgls_kernel<3, false>);
+            }
         }
         QGSB_CUDA(cudaGetLastError());
         QGSB_CUDA(cudaEventRecord(ev1, st));

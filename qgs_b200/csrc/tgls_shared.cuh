@@ -43,6 +43,8 @@ struct TgParams {
     // --- placement of the big matrices ---
     double *scratch;          // global scratch when shared memory is too small, else null
     size_t scratch_per_member;
+    // --- large bases: J as a dense (jd_ld x jd_ld) matrix per member in the scratch, product on the FP64 tensor cores ---
+    int jd_ld;                // 0: sparse product over the position list; else leading dimension (n rounded up to 8)
 };
 
 template <int RANK>

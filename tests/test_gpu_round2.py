@@ -337,3 +337,43 @@ def test_initialize_in_device_batches_matches_an_oracle_replay_of_the_same_draws
     integ.initialize(1., 0.1, ic=ref[:5])
     one = oracle.integrate_runge_kutta_jit(T, tv(1.), ref[:5], 1, 0, b, c, a)[:, :, 0]
     assert np.max(np.abs(integ.get_ic() - one)) < 1e-10 * np.max(np.abs(one))
+
+
+# ---- large bases: the tangent product as a dense GEMM on the FP64 tensor cores -------------------------------------------
+@pytest.mark.parametrize("name,m,adjoint", [("atm6x6", 16, False), ("atm6x6", 150, False), ("atm6x6", 9, True),
+                                            ("maooam36", 10, False), ("maooam36", 36, True), ("dynT", 38, False)])
+def test_dense_tensor_core_product_equals_the_sparse_product(name, m, adjoint):
+    """Generic tangent kernels: out = J @ X over the sparse position list (QGSB_TGLS_DENSE=0) or as a dense
+    (n x n) @ (n x m) product with mma.sync.m8n8k4.f64 (=1; the default from 64 variables on).  Same J, same X: the results
+    agree to rounding.  Small models are forced through the dense path too, for the padding (n, m not multiples of 8)."""
+    from qgs_b200.integrators.integrator import RungeKuttaTglsIntegrator
+    f, Df, T = model(name)
+    n = f.ndim
+    rng = np.random.default_rng(3)
+    ic = rng.random((5, n)) * 0.01
+    tg = rng.standard_normal((m, n))
+    out = []
+    for dense in ("0", "1"):
+        with env(QGSB_TGLS_KERNEL="generic", QGSB_TGLS_DENSE=dense):
+            integ = RungeKuttaTglsIntegrator()
+            integ.set_func(f, Df)
+            integ.integrate(0., 0.4, 0.1, ic=ic, tg_ic=tg, write_steps=2, adjoint=adjoint)
+            out.append(integ.get_trajectories())
+    assert np.array_equal(out[0][1], out[1][1])
+    scale = np.max(np.abs(out[0][2]))
+    assert np.max(np.abs(out[0][2] - out[1][2])) < 1e-12 * scale
+
+
+def test_dense_product_in_the_generic_benettin_kernel():
+    """The same switch inside the Benettin loop (generic kernel, 228 variables, 40 vectors): exponents and vectors of the
+    dense product agree with the sparse one's."""
+    f, Df, T = model("atm6x6")
+    rng = np.random.default_rng(4)
+    q0 = np.stack([np.linalg.qr(rng.random((228, 40)))[0] for _ in range(3)])
+    out = []
+    for dense in ("0", "1"):
+        with env(QGSB_TGLS_DENSE=dense):
+            out.append(_benettin("atm6x6", 3, 40, q0, None, t1=1.1))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.max(np.abs(out[0][1][:, :, 1:] - out[1][1][:, :, 1:])) < 1e-10 * np.max(np.abs(out[0][1][:, :, 1:]))
+    assert np.max(np.abs(out[0][2] - out[1][2])) < 1e-10
