@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqgsb.so")
+LIB_PATH = os.environ.get("QGSB_LIB") or os.path.join(HERE, "libqgsb.so")      # QGSB_LIB: A/B builds
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)

@@ -15,7 +15,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 GEN = os.path.join(CSRC, "generated")
-LIB = os.path.join(HERE, "libqgsb.so")
+# QGSB_BUILD_TAG=<tag> builds a variant next to the product library (libqgsb_<tag>.so, objects under _obj_<tag>/) for
+# A/B measurements; QGSB_LIB=<path> makes qgs_b200._lib load it.
+TAG = os.environ.get("QGSB_BUILD_TAG", "")
+LIB = os.path.join(HERE, "libqgsb%s.so" % ("_" + TAG if TAG else ""))
+OBJ = os.path.join(HERE, "_obj" + ("_" + TAG if TAG else ""))
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + \
     os.environ.get("QGSB_NVCC_EXTRA", "").split()          # e.g. -DQGSB_PACK_THREADS=324 for A/B builds
@@ -41,17 +45,21 @@ def compile_object(src, obj, extra=()):
 
 
 def build(force=False, verbose=False, generate=True):
-    os.makedirs(os.path.join(HERE, "_obj"), exist_ok=True)
+    os.makedirs(OBJ, exist_ok=True)
     if generate:
         from . import codegen
         codegen.generate_canonical(GEN)
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu"))) + sorted(glob.glob(os.path.join(GEN, "*.cu")))
+    only = os.environ.get("QGSB_BUILD_SPECS")              # A/B builds: only these generated modules, e.g. "maooam36,rp"
+    if only and TAG:
+        keep = {"spec_%s.cu" % n for n in only.split(",")}
+        sources = [s for s in sources if os.path.dirname(s) != GEN or os.path.basename(s) in keep]
     headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
         glob.glob(os.path.join(HERE, "..", "include", "*.h"))
     objs = []
     jobs = []
     for src in sources:
-        obj = os.path.join(HERE, "_obj", os.path.basename(src) + ".o")
+        obj = os.path.join(OBJ, os.path.basename(src) + ".o")
         objs.append(obj)
         if force or _newer(obj, [src] + headers):
             cmd = [nvcc()] + ARCH + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \

@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tgls_shared.cuh"
@@ -36,7 +37,11 @@ namespace pack {
 #ifndef QGSB_PACK_THREADS
 #define QGSB_PACK_THREADS 256
 #endif
+#ifndef QGSB_PACK_BLOCKS
+#define QGSB_PACK_BLOCKS 1
+#endif
 constexpr int MAX_THREADS = QGSB_PACK_THREADS;
+constexpr int MIN_BLOCKS = QGSB_PACK_BLOCKS;      // resident blocks per SM the register allocation is sized for
 
 // launch geometry decided on the host
 struct Geometry {
@@ -622,6 +627,278 @@ __device__ __forceinline__ void qr_rolled(const Mem<N> &S, int c, bool live, dou
     }
 }
 
+// ---- Cholesky QR on the FP64 tensor cores (steps whose Q and R nobody looks at) -----------------------------------------
+// The Benettin loop needs q, r = qr(prop @ q) every step (lyapunov.py:602-604), but between two records only
+// log|diag r| (:611) and the SUBSPACES spanned by the leading columns of q are used: Householder's Q does not depend on
+// the signs of the columns of the matrix it factorises (a reflector is the same for x and -x), so a step may return
+// Q D with any diagonal D = +-1 without changing the Q, R of a later Householder step.  For those steps the
+// factorisation is done as  G = A^T A  (a small GEMM per member: mma.sync.m8n8k4.f64, one warp per member, the
+// fragments straight from the row-major A the tangent step left in shared memory),  G = R^T R  (right-looking
+// Cholesky, lane = column in registers, one warp-level hand-over per pivot instead of a block barrier per reflector),
+// Q = A R^-1  (forward substitution, thread = row).  The chain of dependent instructions per column is
+// shuffle + rsqrt + multiply + FMA instead of Householder's reduction + sqrt + two reciprocals + update, and the O(n^3)
+// part runs on the tensor pipe with 1/8 of the instructions.  Orthogonality of Cholesky QR degrades with cond(A)^2:
+// A is an orthonormal basis propagated over ONE step, cond(A) ~ exp((l_1 - l_n) dt) = O(1); a pivot below
+// CHOL_PIVOT_MIN of the largest squared column norm (cond^2 > 1 / CHOL_PIVOT_MIN, or a rank-deficient basis) sends the
+// whole block through the Householder code for that step.  Steps whose Q or R is recorded or returned (vector
+// records, the Ginelli pass, the start and the final basis) always take Householder, so recorded vectors keep
+// np.linalg.qr's signs.
+constexpr double CHOL_PIVOT_MIN = 1e-4;
+#ifdef CHOL_PROF
+__device__ long long chol_prof[4];
+#endif
+
+// compile-time loop: nvcc stops honouring `#pragma unroll` on the outer loop of a large triangular nest (it unrolls by
+// four and indexes the register arrays dynamically, i.e. puts them in local memory)
+template <int I, int E, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < E) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, E>(f);
+    }
+}
+
+__device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// 1 / sqrt(x) for normal positive x: hardware seed (2^-22) + two Newton steps (2^-43, then to rounding)
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-h, y * y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h, y * y, 0.5);
+    return fma(y, e, y);
+}
+
+// x[k] -= q * row[k] for k = J + 1 .. N - 1 (row 16-byte aligned at even k, N even): LDS.128 where a pair is aligned
+template <int N, int J>
+__device__ __forceinline__ void row_axpy(double (&x)[N], const double *row, double q)
+{
+    constexpr int K0 = (J + 2) & ~1;                  // first even k > J
+    if (K0 != J + 1) x[J + 1] = fma(-q, row[J + 1], x[J + 1]);
+#pragma unroll
+    for (int k = K0; k < N; k += 2) {
+        const double2 r = *reinterpret_cast<const double2 *>(row + k);
+        x[k] = fma(-q, r.x, x[k]);
+        x[k + 1] = fma(-q, r.y, x[k + 1]);
+    }
+}
+
+// the same for two vectors sharing the loads of the row
+template <int N, int J>
+__device__ __forceinline__ void row_axpy2(double (&x)[N], double (&y)[N], const double *row, double q, double p)
+{
+    constexpr int K0 = (J + 2) & ~1;
+    if (K0 != J + 1) {
+        x[J + 1] = fma(-q, row[J + 1], x[J + 1]);
+        y[J + 1] = fma(-p, row[J + 1], y[J + 1]);
+    }
+#pragma unroll
+    for (int k = K0; k < N; k += 2) {
+        const double2 r = *reinterpret_cast<const double2 *>(row + k);
+        x[k] = fma(-q, r.x, x[k]);
+        x[k + 1] = fma(-q, r.y, x[k + 1]);
+        y[k] = fma(-p, r.x, y[k]);
+        y[k + 1] = fma(-p, r.y, y[k + 1]);
+    }
+}
+
+// ONE WARP, one member: S.fm holds A (N x m, row-major, ld = m).  Leaves R (rows < m; row-major with the COMPILE-TIME
+// leading dimension N, columns >= m zero, so that the inner loops carry no run-time bounds) in S.facc, 1 / R_jj in
+// S.scal, R_jj in S.rdiag; returns false when a pivot is too small (S.fm is not touched either way).
+// FULLM: m == N, no run-time bound anywhere -- the pivot steps then form one basic block, and ptxas overlaps the
+// rsqrt chain of pivot j + 1 with the trailing update of pivot j.
+// Columns in registers: lane l holds column l + E of G (rows <= l + E), E = max(N - 32, 0); the first E columns have
+// at most E rows above the diagonal and ride along in lanes 0 .. E - 1 as E extra values.
+template <int N, bool FULLM>
+__device__ __forceinline__ bool chol_factor(const Mem<N> &S, int lane)
+{
+    static_assert(N % 2 == 0 && N <= 48, "pairs of columns; N - 32 short extra columns");
+    constexpr int MT = (N + 7) / 8, KS = (N + 3) / 4;
+    constexpr int E = N > 32 ? N - 32 : 0, EA = E > 0 ? E : 1;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int m = FULLM ? N : S.m;
+    const int ar = lane >> 2, ac = lane & 3;
+    const double *A = S.fm;
+    double *G = S.facc;
+#ifdef CHOL_PROF
+    long long tp0 = clock64();
+#endif
+    {
+        // G = A^T A: the A operand of tile (tm, tn) is (A^T)[8 tm + ar][4 ks + ac], the B operand A[4 ks + ac][8 tn + ar]
+        // -- the same fragment shape, so one load per column tile and k step serves both
+        double acc[MT][MT][2];
+#pragma unroll
+        for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+            for (int tn = 0; tn < MT; ++tn) acc[tm][tn][0] = acc[tm][tn][1] = 0.;
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ++ks) {
+            const int row = 4 * ks + ac;
+            double f[MT];
+#pragma unroll
+            for (int t = 0; t < MT; ++t) {
+                const int col = 8 * t + ar;
+                f[t] = (row < N && col < m) ? A[row * m + col] : 0.;
+            }
+#pragma unroll
+            for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+                for (int tn = tm; tn < MT; ++tn)
+                    if (FULLM || 8 * tn < m) dmma_884(acc[tm][tn][0], acc[tm][tn][1], f[tm], f[tn]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+            for (int tn = tm; tn < MT; ++tn) {
+                const int r = 8 * tm + ar, c0 = 8 * tn + 2 * ac;
+                if (r < m && c0 < N) *reinterpret_cast<double2 *>(G + r * N + c0) = make_double2(acc[tm][tn][0], acc[tm][tn][1]);
+            }
+        __syncwarp();
+    }
+#ifdef CHOL_PROF
+    long long tp1 = clock64();
+#endif
+    const int cm = lane + E;                           // the lane's main column
+    const bool hasm = cm < N, hase = lane < E;
+    double gc[N], ge[EA];
+#pragma unroll
+    for (int i = 0; i < N; ++i) gc[i] = (i < m && i <= cm && hasm) ? G[i * N + cm] : 0.;
+#pragma unroll
+    for (int i = 0; i < EA; ++i) ge[i] = (i < m && i <= lane && hase) ? G[i * N + lane] : 0.;
+    double gmax = lane < m ? G[lane * N + lane] : 0.;
+    if (32 + lane < m) gmax = fmax(gmax, G[(32 + lane) * N + 32 + lane]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(FULL, gmax, o));
+    const double pmin = CHOL_PIVOT_MIN * gmax;
+    bool ok = gmax > 0.;
+    double p = __shfl_sync(FULL, E > 0 ? ge[0] : gc[0], 0);
+    double rinv = fast_rsqrt(p);
+    __syncwarp();
+#ifdef CHOL_PROF
+    long long tp2 = clock64();
+#endif
+    static_for<0, N>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        if (FULLM || j < m) {                          // uniform
+            ok = ok && (p > pmin);
+            const double rjc = gc[j] * rinv;
+            const double rje = j < E ? ge[j < E ? j : 0] * rinv : 0.;
+            if (lane == 0) {
+                S.rdiag[j] = p * rinv;
+                S.scal[j] = rinv;
+            }
+            // the next pivot straight from its owner's registers: G_{j+1,j+1} - R_{j,j+1}^2 needs only the owner's own
+            // R_{j,j+1}, not the round trip of row j through shared memory
+            if (j + 1 < N) {
+                constexpr int j1 = j + 1 < N ? j + 1 : 0;
+                const double pn = j1 < E ? fma(-rje, rje, ge[j1 < E ? j1 : 0]) : fma(-rjc, rjc, gc[j1]);
+                p = __shfl_sync(FULL, pn, j1 < E ? j1 : j1 - E);
+            }
+            double *row = G + j * N;
+            if (hasm && cm >= j) row[cm] = rjc;
+            if (j < E && hase && lane >= j) row[lane] = rje;
+            __syncwarp();
+            if (j + 1 < N) rinv = fast_rsqrt(p);
+            row_axpy<N, j>(gc, row, rjc);
+            if (j + 1 < E) {
+#pragma unroll
+                for (int i = j + 1; i < E; ++i) ge[i] = fma(-row[i], rje, ge[i]);
+            }
+        }
+    });
+#ifdef CHOL_PROF
+    if (lane == 0 && threadIdx.x == 0 && blockIdx.x == 0) {
+        long long tp3 = clock64();
+        chol_prof[0] += tp1 - tp0; chol_prof[1] += tp2 - tp1; chol_prof[2] += tp3 - tp2;
+    }
+#endif
+    return ok;
+}
+
+// Q = A R^-1 by forward substitution, TWO rows of one member per thread (the loads of R's rows are broadcasts that
+// cost the load/store unit as much as any other load: two rows per load halve them), A (S.fm) is overwritten.
+// idx enumerates (member, row pair); rows r and r + N / 2.
+template <int N, bool FULLM>
+__device__ __forceinline__ void chol_solve(const Mem<N> &S, int pr)
+{
+    const int m = FULLM ? N : S.m;
+    const double *R = S.facc;
+    double *arow = S.fm + pr * m, *brow = S.fm + (pr + N / 2) * m;
+    double a[N], b[N];
+    // beyond column m - 1 this reads into the next row (or the area behind the last one): finite numbers that only
+    // meet the zero columns of R and are never stored
+    if (FULLM) {                                       // m = N is even: rows are 16-byte aligned
+#pragma unroll
+        for (int k = 0; k < N; k += 2) {
+            const double2 va = *reinterpret_cast<const double2 *>(arow + k), vb = *reinterpret_cast<const double2 *>(brow + k);
+            a[k] = va.x, a[k + 1] = va.y, b[k] = vb.x, b[k + 1] = vb.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            a[k] = arow[k];
+            b[k] = brow[k];
+        }
+    }
+    static_for<0, N>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        if (FULLM || j < m) {                          // uniform
+            const double s = S.scal[j];
+            const double qa = a[j] * s, qb = b[j] * s;
+            a[j] = qa;
+            b[j] = qb;
+            if (j + 1 < N) row_axpy2<N, j>(a, b, R + j * N, qa, qb);
+        }
+    });
+    if (FULLM) {
+#pragma unroll
+        for (int k = 0; k < N; k += 2) {
+            *reinterpret_cast<double2 *>(arow + k) = make_double2(a[k], a[k + 1]);
+            *reinterpret_cast<double2 *>(brow + k) = make_double2(b[k], b[k + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            if (k < m) {
+                arow[k] = a[k];
+                brow[k] = b[k];
+            }
+    }
+}
+
+// the block's part of one Cholesky-QR step: A in S.fm of every member -> Q in S.fm, R_jj in S.rdiag; returns false
+// (S.fm untouched) when some member of the block refused a pivot.  Contains block barriers: call from all threads.
+template <int N, bool FULLM>
+__device__ __forceinline__ bool cholqr_block(double *smem, int stride, int jv, int m, int G, long n_members)
+{
+    const int t = threadIdx.x;
+    __syncthreads();                                   // A = the columns tangent_step left in S.fm
+    bool ok = true;
+    for (int gg = t >> 5; gg < G; gg += blockDim.x >> 5)
+        if ((long)blockIdx.x * G + gg < n_members)
+            ok = chol_factor<N, FULLM>(carve<N>(smem + (size_t)gg * stride, jv, m), t & 31) && ok;
+    if (__syncthreads_or(!ok)) return false;
+    // member index fastest: the rows of one lane are a whole row stride apart (8-way bank conflicts when neighbouring
+    // lanes take neighbouring rows), the members' areas are staggered by 16 bytes modulo 128
+    for (int idx = t; idx < G * (N / 2); idx += blockDim.x) {
+        const int pr = idx / G, gg = idx - pr * G;
+        if ((long)blockIdx.x * G + gg < n_members)
+            chol_solve<N, FULLM>(carve<N>(smem + (size_t)gg * stride, jv, m), pr);
+    }
+    __syncthreads();
+    return true;
+}
+
 template <int N, class Prod>
 __device__ __forceinline__ void init_member(const Mem<N> &S, int c, bool live)
 {
@@ -641,7 +918,7 @@ __device__ __forceinline__ void init_member(const Mem<N> &S, int c, bool live)
 
 // ---- plain tangent-linear integration (integrate.py:555-614) ----------------------------------------------------------
 template <int N, class Prod>
-__global__ void __launch_bounds__(MAX_THREADS, 1)
+__global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
 tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride)
 {
     extern __shared__ __align__(16) double smem_pack[];
@@ -694,8 +971,8 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
 
 // ---- Benettin loop (lyapunov.py:471-632) ---------------------------------------------------------------------------------
 template <int N, class Prod, bool ROLLED>
-__global__ void __launch_bounds__(MAX_THREADS, 1)
-lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride, int qr_remap)
+__global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
+lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables tab_g, int G, int stride, int qr_flags)
 {
     extern __shared__ __align__(16) double smem_pack[];
     const ShTab tab = stage_tables(tab_g, smem_pack + (size_t)G * stride, N);
@@ -711,7 +988,7 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
     // columns of all the members, so the warps whose columns are already finished skip a reflector altogether
     // (with the consecutive layout every warp has live columns until the very end).  The tangent steps keep the
     // consecutive layout, whose broadcast reads of J hit one or two addresses per warp.
-    const bool remap = qr_remap != 0;
+    const bool remap = (qr_flags & 1) != 0, chol = (qr_flags & 2) != 0;
     const int cq = remap ? t / G : c, gq = remap ? t - cq * G : g;
     const long memberq = (long)blockIdx.x * G + gq;
     const bool liveq = remap ? (cq < m && memberq < P.n_members) : live;
@@ -776,7 +1053,20 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
             for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, tab, P, S, P.sub_dt[q], col, c, live);
         }
         // q, r = qr(prop @ q)   (:602-604)
-        {
+        bool factorised = false;
+        if (chol && real && step + 1 < steps && !P.q_all && !P.r_all &&
+            !(P.rec_fm && P.write_steps > 0 && step + 1 >= P.n_pre && (step + 1 - P.n_pre) % P.write_steps == 0)) {
+            // nobody sees this step's Q or R: Cholesky QR (see chol_factor)
+            factorised = m == N ? cholqr_block<N, true>(smem_pack, stride, Prod::JV, m, G, P.n_members)
+                                : cholqr_block<N, false>(smem_pack, stride, Prod::JV, m, G, P.n_members);
+            // Q -- or, when a pivot was refused, the untouched A: the column does not stay in registers across the
+            // factorisation (72 registers that the Cholesky phase needs)
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) col[i] = S.fm[i * m + c];
+            }
+        }
+        if (!factorised) {
             double *Rout = (real && P.r_all && liveq && step >= P.r_first)
                                ? P.r_all + ((size_t)memberq * (steps - P.r_first) + (step - P.r_first)) * m * m : nullptr;
             if (remap) {                     // hand the columns over through the fm area (tangent_step left them there)
@@ -888,7 +1178,12 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
         }
         const char *env = getenv("QGSB_QR_REMAP");
         const int remap = env ? (env[0] != '0') : 1;
-        kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, tab, geo.G, geo.stride, remap);
+        // Cholesky QR for the steps whose Q, R are not observed (chol_factor); QGSB_QR_CHOL=0 keeps Householder everywhere
+        // [B200, 8192 members, exponents only: MAOOAM-36 36 vectors x1.42, 20 vectors x1.07, 10 vectors x0.78 (the
+        // unrolled pivot steps run over all N columns of the padded factor); RP-20 x1.19; dynamic-T 38 vectors x1.25]
+        const char *envc = getenv("QGSB_QR_CHOL");
+        const int chol = envc ? (envc[0] != '0') : (2 * P.m > N);
+        kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, tab, geo.G, geo.stride, remap | (chol << 1));
         return cudaGetLastError();
     };
     if (lyap) {
