@@ -661,7 +661,7 @@ def run_ours(args, rank, world, local_rank):
                     "roofline": {"bound": "fp64", "achieved": ly_ach, "peak": peak, "unit": "TFLOP/s",
                                  "frac": ly_ach / peak, "traffic": None, "peak_source": peak_note,
                                  "flops_per_member_step": LYAP_FLOPS_PER_MEMBER_STEP,
-                                 "kernel": "pack::lyap_kernel<36, bilinear product, pipelined QR>"},
+                                 "kernel": "pack::lyap_kernel<36, bilinear product; Cholesky QR on mma.sync.m8n8k4.f64 between records, Householder at observed steps>"},
                     "e2e": {"value": ly_steps * world / ly_e2e_s, "unit": UNIT,
                             "h2d_bytes_per_step": world * ly_bytes[0], "d2h_bytes_per_step": world * ly_bytes[1],
                             "call": "LyapunovsEstimator.compute_lyapunovs(..., vectors=False) + get_lyapunovs(): host "

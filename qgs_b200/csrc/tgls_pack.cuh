@@ -260,8 +260,14 @@ __device__ __forceinline__ ShTab stage_tables(const PackTables &tab, double *dst
 // synchronises before anybody reads another thread's data.
 template <int N, class Prod>
 __device__ __forceinline__ void tangent_step(const TensorView &T, const ShTab &tab, const TgParams &P,
-                                             const Mem<N> &S, double dt, double (&col)[N], int c, bool live)
+                                             const Mem<N> &S, double dt, double (&col)[N], int c, bool live,
+                                             const Mem<N> &Sr, int cr, bool liver)
 {
+    // (Sr, cr, liver): the member and rows r = cr, cr + m, ... whose tendencies this thread evaluates.  They need not
+    // be the thread's own member: dealt member-fastest, the lanes of a warp read the SAME table entries and gather
+    // from the staggered state areas of different members (fewer bank conflicts than 32 different rows of one state).
+    // Every access to y, yacc, kst and the row part of xs goes through this mapping, so no barrier is needed between
+    // them.
     const int s = P.s, m = S.m;
     double km[N];
     for (int st = 0; st < s; ++st) {
@@ -273,17 +279,17 @@ __device__ __forceinline__ void tangent_step(const TensorView &T, const ShTab &t
         // (generated bilinear form) then need ONE barrier per stage; those that read Jacobian values built by the
         // whole member need a second one.
         double *xs = (st & 1) ? S.xs2 : S.xs;
-        if (live)
-            for (int r = c; r < N; r += m) xs[r + 1] = st > 0 ? S.y[r] + wa_in * S.kst[r] : S.y[r];
+        double *xr = (st & 1) ? Sr.xs2 : Sr.xs;
+        if (liver)
+            for (int r = cr; r < N; r += m) xr[r + 1] = st > 0 ? Sr.y[r] + wa_in * Sr.kst[r] : Sr.y[r];
         __syncthreads();
-        if (live) {
-            for (int r = c; r < N; r += m) {
-                const double k = f_row_tab<N>(T, tab, r, xs);
-                S.kst[r] = k;
-                S.yacc[r] = st == 0 ? wb * k : S.yacc[r] + wb * k;
+        if (liver)
+            for (int r = cr; r < N; r += m) {
+                const double k = f_row_tab<N>(T, tab, r, xr);
+                Sr.kst[r] = k;
+                Sr.yacc[r] = st == 0 ? wb * k : Sr.yacc[r] + wb * k;
             }
-            if (Prod::kUsesJacobianValues) jac_build<N, Prod>(T, tab, xs, S.jv, c, m);
-        }
+        if (live && Prod::kUsesJacobianValues) jac_build<N, Prod>(T, tab, xs, S.jv, c, m);
         if (Prod::kUsesJacobianValues) __syncthreads();
         if (live) {
             // km = inverse * (J or J^T) @ col        integrate.py:601-603, boundary == 0
@@ -299,8 +305,9 @@ __device__ __forceinline__ void tangent_step(const TensorView &T, const ShTab &t
             }
         }
     }
+    if (liver)
+        for (int r = cr; r < N; r += m) Sr.y[r] += Sr.yacc[r];
     if (live) {
-        for (int r = c; r < N; r += m) S.y[r] += S.yacc[r];
         double *fmc = S.fm + c;
         const double *fc = S.facc + c;
 #pragma unroll
@@ -928,6 +935,10 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
     const long member = (long)blockIdx.x * G + g;
     const bool live = g < G && member < P.n_members;
     const Mem<N> S = carve<N>(smem_pack + (size_t)(live ? g : 0) * stride, Prod::JV, m);
+    // the tendencies are dealt out member-fastest (see tangent_step)
+    const int cq = t / G, gq = t - cq * G;
+    const bool liveq = cq < m && (long)blockIdx.x * G + gq < P.n_members;
+    const Mem<N> Sq = carve<N>(smem_pack + (size_t)(liveq ? gq : 0) * stride, Prod::JV, m);
     const int nm = N * m;
     double col[N];
     init_member<N, Prod>(S, c, live);
@@ -952,7 +963,7 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
             }
             ++iw;
         }
-        tangent_step<N, Prod>(T, tab, P, S, P.dt[ti], col, c, live);
+        tangent_step<N, Prod>(T, tab, P, S, P.dt[ti], col, c, live, Sq, cq, liveq);
         __syncthreads();
     }
     if (live) {
@@ -995,8 +1006,9 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
     const Mem<N> Sq = carve<N>(smem_pack + (size_t)(liveq ? gq : 0) * stride, Prod::JV, m);
     double col[N];
     init_member<N, Prod>(S, c, live);
-    if (live)
-        for (int r = c; r < N; r += m) S.Y[r] = P.y[member * N + r];
+    // rows of the state (y, Y): dealt out like the tendencies (Sq, cq -- see tangent_step), here and everywhere below
+    if (liveq)
+        for (int r = cq; r < N; r += m) Sq.Y[r] = P.y[memberq * N + r];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         col[i] = live ? P.fm[member * nm + i * m + c] : 0.;
@@ -1004,7 +1016,7 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
     }
     if (live) S.rdiag[c] = P.r0 ? P.r0[((size_t)member * m + c) * m + c] : 0.;
     __syncthreads();
-    const size_t sbase = (P.stored && live) ? tile_base(member, N) : 0;
+    const size_t sbase = (P.stored && liveq) ? tile_base(memberq, N) : 0;
     long iw = 0;
     double mexp = 0.;
     // step -1 (P.qr_at_start): the start matrix was drawn on the device and is only factorised here -- the
@@ -1013,27 +1025,32 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
     for (long step = P.qr_at_start ? -1 : 0; step < steps; ++step) {
         const bool real = step >= 0;
         if (real && P.stored) {                                           // lyapunov.py:513 / :527
-            if (live) {
+            if (liveq) {
                 const double *src = P.stored + (size_t)P.start_idx[step] * N * P.stored_ld + sbase;
-                for (int r = c; r < N; r += m) S.Y[r] = src[(size_t)r * TILE];
+                for (int r = cq; r < N; r += m) Sq.Y[r] = src[(size_t)r * TILE];
             }
             __syncthreads();
         }
         if (real && step >= P.n_pre) {
             const long ti = step - P.n_pre;
-            if (live) mexp = log(fabs(S.rdiag[c])) / P.dt_macro[step];   // :611 / :531
+            // :611 / :531 -- only where it is written: at a record, and in the last step for the record after the loop
+            const bool rec_now = P.write_steps > 0 && ti % P.write_steps == 0;
+            if (live && (rec_now || step + 1 == steps)) mexp = log(fabs(S.rdiag[c])) / P.dt_macro[step];
             if (P.q_all && live) {
                 double *qa = P.q_all + ((size_t)member * (P.n_rec + 1) + ti) * nm;
 #pragma unroll
                 for (int i = 0; i < N; ++i) qa[i * m + c] = col[i];
             }
-            if (P.write_steps > 0 && ti % P.write_steps == 0) {
+            if (rec_now) {
+                if (liveq) {
+                    const long rc = P.forward == 1 ? R - 1 - iw : iw;
+                    double *ry = P.rec_y + ((size_t)rc * P.n_members + memberq) * N;
+                    for (int r = cq; r < N; r += m) ry[r] = Sq.Y[r];
+                }
                 if (live) {
                     const long rc = P.forward == 1 ? R - 1 - iw : iw;
-                    double *ry = P.rec_y + ((size_t)rc * P.n_members + member) * N;
                     double *rv = P.rec_fm + ((size_t)rc * P.n_members + member) * nm;
                     double *re = P.rec_exp + ((size_t)rc * P.n_members + member) * m;
-                    for (int r = c; r < N; r += m) ry[r] = S.Y[r];
                     if (P.rec_fm) {
 #pragma unroll
                         for (int i = 0; i < N; ++i) rv[i * m + c] = col[i];
@@ -1046,11 +1063,11 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
         // propagate the basis over the micro steps starting from the stored point (:598-600)
         long q0 = 0, q1 = 0;
         if (real) {
-            if (live)
-                for (int r = c; r < N; r += m) S.y[r] = S.Y[r];
+            if (liveq)
+                for (int r = cq; r < N; r += m) Sq.y[r] = Sq.Y[r];
             q0 = P.sub_ptr[step];
             q1 = P.sub_ptr[step + 1];
-            for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, tab, P, S, P.sub_dt[q], col, c, live);
+            for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, tab, P, S, P.sub_dt[q], col, c, live, Sq, cq, liveq);
         }
         // q, r = qr(prop @ q)   (:602-604)
         bool factorised = false;
@@ -1092,22 +1109,28 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
         if (P.forward == 2 || (!P.stored && q1 - q0 == 1 && P.sub_dt[q0] == P.dt_macro[step])) {
             // Ginelli forward pass follows the micro steps; and with a single micro step of the macro length the
             // "stored" trajectory point (:601 / :622) is bit-for-bit the state the tangent step just produced
-            if (live)
-                for (int r = c; r < N; r += m) S.Y[r] = S.y[r];
+            if (liveq)
+                for (int r = cq; r < N; r += m) Sq.Y[r] = Sq.y[r];
         } else if (!P.stored) {                           // next stored-trajectory point (:601 / :622)
-            nl_step<N>(T, tab, P, S, P.dt_macro[step], c, live);
+            nl_step<N>(T, tab, P, Sq, P.dt_macro[step], cq, liveq);
+        }
+    }
+    if (liveq) {
+        if (P.stored) {
+            const double *src = P.stored + (size_t)P.final_idx * N * P.stored_ld + sbase;
+            for (int r = cq; r < N; r += m) Sq.Y[r] = src[(size_t)r * TILE];
+        }
+        const long rc = P.forward == 1 ? 0 : R - 1;                       // :628-630 / :548-550
+        double *ry = P.rec_y + ((size_t)rc * P.n_members + memberq) * N;
+        for (int r = cq; r < N; r += m) {
+            ry[r] = Sq.Y[r];
+            P.y[memberq * N + r] = Sq.Y[r];
         }
     }
     if (live) {
-        if (P.stored) {
-            const double *src = P.stored + (size_t)P.final_idx * N * P.stored_ld + sbase;
-            for (int r = c; r < N; r += m) S.Y[r] = src[(size_t)r * TILE];
-        }
-        const long rc = P.forward == 1 ? 0 : R - 1;                       // :628-630 / :548-550
-        double *ry = P.rec_y + ((size_t)rc * P.n_members + member) * N;
+        const long rc = P.forward == 1 ? 0 : R - 1;
         double *rv = P.rec_fm + ((size_t)rc * P.n_members + member) * nm;
         double *re = P.rec_exp + ((size_t)rc * P.n_members + member) * m;
-        for (int r = c; r < N; r += m) ry[r] = S.Y[r];
         if (P.rec_fm) {
 #pragma unroll
             for (int i = 0; i < N; ++i) rv[i * m + c] = col[i];
@@ -1118,7 +1141,6 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
 #pragma unroll
             for (int i = 0; i < N; ++i) qa[i * m + c] = col[i];
         }
-        for (int r = c; r < N; r += m) P.y[member * N + r] = S.Y[r];
 #pragma unroll
         for (int i = 0; i < N; ++i) P.fm[member * nm + i * m + c] = col[i];
     }

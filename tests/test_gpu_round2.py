@@ -1,4 +1,4 @@
-"""GPU tests of the round-2 work: the pipelined Householder QR of the Benettin kernel, start bases drawn on the device,
+"""GPU tests of the round-2 work: the Householder and Cholesky QR of the Benettin kernel, start bases drawn on the device,
 member batches bounded by device memory, several devices behind one call, and the long-run statistical criterion of
 BASELINE.json on the model the metric is quoted on (MAOOAM-36).
 """
@@ -57,6 +57,66 @@ def _benettin(name, N, n_vec, q0, r0, seed=None, vectors=True, mode=0, mdt=0.1, 
     pre = np.concatenate((np.arange(0., 0.5, 0.1), [0.5]))
     tim = np.concatenate((np.arange(0.5, t1, 0.1), [t1]))
     return benettin(f, Df, ic, mode, n_vec, q0, r0, pre, tim, mdt, 3, False, 1., b, c, a, want_vectors=vectors, seed=seed)
+
+
+# ---- Cholesky QR on the steps nobody looks at --------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n_vec", [("maooam36", 36), ("maooam36", 24), ("rp", 20), ("dynT", 38)])
+@pytest.mark.parametrize("vectors", [True, False])
+def test_cholesky_qr_steps_reproduce_the_householder_run(name, n_vec, vectors):
+    """Between two records the Benettin kernel factorises with a Cholesky QR on the FP64 tensor cores (Gram matrix by
+    mma.sync, warp-level Cholesky, forward substitution: pack::chol_factor / chol_solve) and keeps Householder -- the
+    reference's np.linalg.qr, lyapunov.py:602-604 -- for every step whose Q or R is recorded or returned.  Householder's Q
+    does not depend on the signs of the columns it is given, so the RECORDED vectors keep np.linalg.qr's signs; the
+    run with QGSB_QR_CHOL=0 (Householder everywhere, what the golden tests pin against the reference) must be
+    reproduced to rounding: exponents (log|diag R|) and vectors, full and partial bases, with and without vector records."""
+    f, Df, T = model(name)
+    n = f.ndim
+    N = 23
+    rng = np.random.default_rng(11)
+    q0 = np.stack([np.linalg.qr(rng.random((n, n_vec)))[0] for _ in range(N)])
+    out = {}
+    for chol in ("0", "1"):
+        with env(QGSB_QR_CHOL=chol):
+            out[chol] = _benettin(name, N, n_vec, q0, None, vectors=vectors, t1=6.5)
+    assert np.array_equal(out["0"][0], out["1"][0])                       # the trajectory never sees the basis
+    assert np.abs(out["0"][1] - out["1"][1]).max() < 1e-11 * max(1., np.abs(out["0"][1]).max())
+    if vectors:
+        assert np.abs(out["0"][2] - out["1"][2]).max() < 1e-11
+        q = out["1"][2][..., -1]
+        assert np.abs(np.einsum("nij,nik->njk", q, q) - np.eye(n_vec)).max() < 1e-13
+
+
+def test_cholesky_qr_falls_back_to_householder_on_an_ill_conditioned_step():
+    """Orthogonality of a Cholesky QR degrades with cond(A)^2, and the Gram matrix of a rank-deficient basis has no
+    Cholesky factor at all.  A start basis whose second column repeats the first, and whose fourth is the third up to
+    1e-9, makes the first propagated matrix singular to working precision: the pivot test of chol_factor must refuse,
+    the block then takes the Householder code for that step (whose arithmetic is exactly the Householder-only run's),
+    and everything stays finite and orthonormal.  Later steps are well conditioned again and differ from the
+    Householder-only run by rounding only."""
+    import oracle
+    from qgs_b200.toolbox.lyapunov import benettin
+    f, Df, T = model("maooam36")
+    n = f.ndim
+    N = 9
+    b, c, a = oracle.rk4_tableau()
+    rng = np.random.default_rng(3)
+    ic = rng.random((N, n)) * 0.01
+    q0 = np.stack([np.linalg.qr(rng.random((n, n)))[0] for _ in range(N)])
+    q0[:, :, 1] = q0[:, :, 0]
+    q0[:, :, 3] = q0[:, :, 2] + 1e-9 * q0[:, :, 5]
+    pre = np.concatenate((np.arange(0., 0.5, 0.1), [0.5]))
+    tim = np.concatenate((np.arange(0.5, 3.5, 0.1), [3.5]))
+    out = {}
+    for chol in ("0", "1"):
+        with env(QGSB_QR_CHOL=chol):
+            out[chol] = benettin(f, Df, ic, 0, n, q0, None, pre, tim, 0.1, 4, False, 1., b, c, a)
+    for x, y in zip(out["0"], out["1"]):
+        assert np.all(np.isfinite(x)) and np.all(np.isfinite(y))
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert np.abs(out["0"][1] - out["1"][1]).max() < 1e-9
+    assert np.abs(out["0"][2] - out["1"][2]).max() < 1e-9
+    q = out["1"][2][..., -1]
+    assert np.abs(np.einsum("nij,nik->njk", q, q) - np.eye(n)).max() < 1e-12
 
 
 # ---- the re-orthonormalisations are the same arithmetic -----------------------------------------------------------------
