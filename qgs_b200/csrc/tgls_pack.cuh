@@ -295,27 +295,30 @@ __device__ __forceinline__ void tangent_step(const TensorView &T, const ShTab &t
             // km = inverse * (J or J^T) @ col        integrate.py:601-603, boundary == 0
             Prod::apply(S.jv, xs, col, km);
             double *fc = S.facc + c;
-            const double *fmc = S.fm + c;
+            double *fmc = S.fm + c;
+            if (st + 1 < s) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double k = P.inverse * km[i];
-                const double f = st == 0 ? wb * k : fc[i * m] + wb * k;          // fm + sum dt b_j km_j  :605-607
-                fc[i * m] = f;
-                col[i] = fmc[i * m] + wa_out * k;                                // km_s of the next stage :598-600
+                for (int i = 0; i < N; ++i) {
+                    const double k = P.inverse * km[i];
+                    const double f = st == 0 ? wb * k : fc[i * m] + wb * k;      // fm + sum dt b_j km_j  :605-607
+                    fc[i * m] = f;
+                    col[i] = fmc[i * m] + wa_out * k;                            // km_s of the next stage :598-600
+                }
+            } else {
+                // last stage: the sum is complete, the new column is fm + sum -- the same operations in the same
+                // order as storing the sum and adding it in a second sweep, without that sweep's loads and stores
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double k = P.inverse * km[i];
+                    const double f = st == 0 ? wb * k : fc[i * m] + wb * k;
+                    col[i] = fmc[i * m] + f;
+                    fmc[i * m] = col[i];
+                }
             }
         }
     }
     if (liver)
         for (int r = cr; r < N; r += m) Sr.y[r] += Sr.yacc[r];
-    if (live) {
-        double *fmc = S.fm + c;
-        const double *fc = S.facc + c;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            col[i] = fmc[i * m] + fc[i * m];
-            fmc[i * m] = col[i];
-        }
-    }
     // an odd number of stages ends on the buffer the next step starts with
     if (s & 1) __syncthreads();
 }
