@@ -832,8 +832,12 @@ __device__ __forceinline__ bool chol_factor(const Mem<N> &S, int lane)
         chol_prof[0] += tp1 - tp0; chol_prof[1] += tp2 - tp1; chol_prof[2] += tp3 - tp2;
     }
 #endif
+    if (lane == 0) S.tau[0] = ok ? 1. : 0.;            // the member's verdict (chol_passed)
     return ok;
 }
+
+template <int N>
+__device__ __forceinline__ bool chol_passed(const Mem<N> &S) { return S.tau[0] != 0.; }
 
 // Q = A R^-1 by forward substitution, TWO rows of one member per thread (the loads of R's rows are broadcasts that
 // cost the load/store unit as much as any other load: two rows per load halve them), A (S.fm) is overwritten.
@@ -886,8 +890,10 @@ __device__ __forceinline__ void chol_solve(const Mem<N> &S, int pr)
     }
 }
 
-// the block's part of one Cholesky-QR step: A in S.fm of every member -> Q in S.fm, R_jj in S.rdiag; returns false
-// (S.fm untouched) when some member of the block refused a pivot.  Contains block barriers: call from all threads.
+// the block's part of one Cholesky-QR step: A in S.fm of every member -> Q in S.fm, R_jj in S.rdiag, for the members
+// whose factorisation passed the pivot test (chol_passed); the others keep A.  The verdict is per MEMBER, so that a
+// member's results do not depend on who shares its block (members sharded over devices or cut into batches must stay
+// bitwise what one launch gives).  Returns true when some member of the block refused.  Contains block barriers.
 template <int N, bool FULLM>
 __device__ __forceinline__ bool cholqr_block(double *smem, int stride, int jv, int m, int G, long n_members)
 {
@@ -897,16 +903,18 @@ __device__ __forceinline__ bool cholqr_block(double *smem, int stride, int jv, i
     for (int gg = t >> 5; gg < G; gg += blockDim.x >> 5)
         if ((long)blockIdx.x * G + gg < n_members)
             ok = chol_factor<N, FULLM>(carve<N>(smem + (size_t)gg * stride, jv, m), t & 31) && ok;
-    if (__syncthreads_or(!ok)) return false;
+    const bool refused = __syncthreads_or(!ok);
     // member index fastest: the rows of one lane are a whole row stride apart (8-way bank conflicts when neighbouring
     // lanes take neighbouring rows), the members' areas are staggered by 16 bytes modulo 128
     for (int idx = t; idx < G * (N / 2); idx += blockDim.x) {
         const int pr = idx / G, gg = idx - pr * G;
-        if ((long)blockIdx.x * G + gg < n_members)
-            chol_solve<N, FULLM>(carve<N>(smem + (size_t)gg * stride, jv, m), pr);
+        if ((long)blockIdx.x * G + gg < n_members) {
+            const Mem<N> Sg = carve<N>(smem + (size_t)gg * stride, jv, m);
+            if (!refused || chol_passed<N>(Sg)) chol_solve<N, FULLM>(Sg, pr);
+        }
     }
     __syncthreads();
-    return true;
+    return refused;
 }
 
 template <int N, class Prod>
@@ -1073,34 +1081,40 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
             for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, tab, P, S, P.sub_dt[q], col, c, live, Sq, cq, liveq);
         }
         // q, r = qr(prop @ q)   (:602-604)
-        bool factorised = false;
+        // hh / hhq: the thread's Householder roles (its own column; with the remap the column it factorises)
+        bool householder = true, partial = false, hh = live, hhq = liveq;
         if (chol && real && step + 1 < steps && !P.q_all && !P.r_all &&
             !(P.rec_fm && P.write_steps > 0 && step + 1 >= P.n_pre && (step + 1 - P.n_pre) % P.write_steps == 0)) {
-            // nobody sees this step's Q or R: Cholesky QR (see chol_factor)
-            factorised = m == N ? cholqr_block<N, true>(smem_pack, stride, Prod::JV, m, G, P.n_members)
-                                : cholqr_block<N, false>(smem_pack, stride, Prod::JV, m, G, P.n_members);
-            // Q -- or, when a pivot was refused, the untouched A: the column does not stay in registers across the
+            // nobody sees this step's Q or R: Cholesky QR (see chol_factor); members that refuse a pivot, and only
+            // they, go through the Householder code below
+            householder = partial = m == N ? cholqr_block<N, true>(smem_pack, stride, Prod::JV, m, G, P.n_members)
+                                           : cholqr_block<N, false>(smem_pack, stride, Prod::JV, m, G, P.n_members);
+            if (partial) {
+                hh = live && !chol_passed<N>(S);
+                hhq = liveq && !chol_passed<N>(Sq);
+            }
+            // Q -- or, for a member that refused, the untouched A: the column does not stay in registers across the
             // factorisation (72 registers that the Cholesky phase needs)
             if (live) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) col[i] = S.fm[i * m + c];
             }
         }
-        if (!factorised) {
+        if (householder) {
             double *Rout = (real && P.r_all && liveq && step >= P.r_first)
                                ? P.r_all + ((size_t)memberq * (steps - P.r_first) + (step - P.r_first)) * m * m : nullptr;
             if (remap) {                     // hand the columns over through the fm area (tangent_step left them there)
                 __syncthreads();
-                if (liveq) {
+                if (hhq) {
 #pragma unroll
                     for (int i = 0; i < N; ++i) col[i] = Sq.fm[i * m + cq];
                 }
             }
             if (ROLLED)
-                qr_rolled<N>(Sq, cq, liveq, col, Rout);
+                qr_rolled<N>(Sq, cq, hhq, col, Rout);
             else
-                qr<N>(Sq, cq, liveq, col, Rout);
-            if (remap) {
+                qr<N>(Sq, cq, hhq, col, Rout);
+            if (remap || partial) {          // (the factorisation leaves unit vectors in the registers of idle threads)
                 __syncthreads();
                 if (live) {
 #pragma unroll
@@ -1151,8 +1165,12 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
 // table_bytes: size of the ELL tables, which are always staged in shared memory behind the members' areas
+// n_members / sm_count > 0: among the block sizes that fit, take the one that minimises (waves of blocks) x (time of a
+// block, modelled as half fixed and half proportional to its members): 8192 members with 10 vectors are 328 blocks of
+// 25 = 2.2 waves that cost three; 432 blocks of 19 fill three waves with faster blocks.  A launch that does not fill the
+// SMs gets small blocks for the same reason.
 template <int N>
-inline Geometry geometry(int jv, int m, size_t smem_limit, size_t table_bytes)
+inline Geometry geometry(int jv, int m, size_t smem_limit, size_t table_bytes, long n_members = 0, int sm_count = 0)
 {
     Geometry geo;
     const Carve<N> c(jv, m);
@@ -1163,6 +1181,16 @@ inline Geometry geometry(int jv, int m, size_t smem_limit, size_t table_bytes)
     if (const char *env = getenv("QGSB_PACK_G")) G = std::max(1, std::min(G, atoi(env)));   // A/B measurements
     if (table_bytes >= smem_limit) G = 0;
     else if ((size_t)G * per_member + table_bytes > smem_limit) G = (int)((smem_limit - table_bytes) / per_member);
+    if (G > 1 && n_members > 0 && sm_count > 0 && !getenv("QGSB_PACK_G")) {
+        int best = G;
+        long best_cost = -1;
+        for (int g = G; g >= (G + 1) / 2; --g) {
+            const long blocks = (n_members + g - 1) / g, waves = (blocks + sm_count - 1) / sm_count;
+            const long cost = waves * (2 * g + G);         // a block's time: about half fixed, half per member
+            if (best_cost < 0 || cost < best_cost) best = g, best_cost = cost;
+        }
+        G = best;
+    }
     geo.G = G;
     geo.threads = G > 0 ? ((G * m + 31) / 32) * 32 : 0;
     geo.smem = (size_t)G * per_member + table_bytes;
@@ -1184,7 +1212,10 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
 {
     static_assert(Fwd::JV == Adj::JV, "both directions of a product share one Jacobian layout");
     if (P.m < 1 || P.m > MAX_THREADS) return cudaErrorInvalidValue;
-    const Geometry geo = geometry<N>(Fwd::JV, P.m, smem_limit, table_bytes(tables, N));
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const Geometry geo = geometry<N>(Fwd::JV, P.m, smem_limit, table_bytes(tables, N), P.n_members, sms);
     if (geo.G < 1) return cudaErrorInvalidValue;
     const PackTables &tab = tables;
     const unsigned blocks = (unsigned)((P.n_members + geo.G - 1) / geo.G);

@@ -119,6 +119,32 @@ def test_cholesky_qr_falls_back_to_householder_on_an_ill_conditioned_step():
     assert np.abs(np.einsum("nij,nik->njk", q, q) - np.eye(n)).max() < 1e-12
 
 
+def test_a_refused_cholesky_step_does_not_touch_the_other_members_of_the_block():
+    """The pivot test is per member: a member with a singular basis goes through the Householder code for that step, the
+    members that share its thread block keep their Cholesky QR -- their results are BITWISE what they are when the
+    singular member is not there.  (Members sharded over devices or cut into batches must stay bitwise one launch.)"""
+    import oracle
+    from qgs_b200.toolbox.lyapunov import benettin
+    f, Df, T = model("maooam36")
+    n = f.ndim
+    N = 9
+    b, c, a = oracle.rk4_tableau()
+    rng = np.random.default_rng(4)
+    ic = rng.random((N, n)) * 0.01
+    q0 = np.stack([np.linalg.qr(rng.random((n, n)))[0] for _ in range(N)])
+    bad = q0.copy()
+    bad[3, :, 7] = bad[3, :, 6]
+    pre = np.concatenate((np.arange(0., 0.5, 0.1), [0.5]))
+    tim = np.concatenate((np.arange(0.5, 2.5, 0.1), [2.5]))
+    good = benettin(f, Df, ic, 0, n, q0, None, pre, tim, 0.1, 4, False, 1., b, c, a)
+    mixed = benettin(f, Df, ic, 0, n, bad, None, pre, tim, 0.1, 4, False, 1., b, c, a)
+    others = [g for g in range(N) if g != 3]
+    for x, y in zip(good, mixed):
+        assert np.all(np.isfinite(y))
+        assert np.array_equal(x[others], y[others])
+    assert not np.array_equal(good[2][3], mixed[2][3])
+
+
 # ---- the re-orthonormalisations are the same arithmetic -----------------------------------------------------------------
 @pytest.mark.parametrize("name,n_vec", [("maooam36", 36), ("maooam36", 10), ("rp", 20), ("dynT", 38)])
 def test_rolled_and_unrolled_qr_are_bitwise_equal(name, n_vec):
