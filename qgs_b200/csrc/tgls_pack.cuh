@@ -721,19 +721,20 @@ __device__ __forceinline__ void row_axpy2(double (&x)[N], double (&y)[N], const 
     }
 }
 
-// ONE WARP, one member: S.fm holds A (N x m, row-major, ld = m).  Leaves R (rows < m; row-major with the COMPILE-TIME
-// leading dimension N, columns >= m zero, so that the inner loops carry no run-time bounds) in S.facc, 1 / R_jj in
-// S.scal, R_jj in S.rdiag; returns false when a pivot is too small (S.fm is not touched either way).
-// FULLM: m == N, no run-time bound anywhere -- the pivot steps then form one basic block, and ptxas overlaps the
+// ONE WARP, one member: S.fm holds A (N x m, row-major, ld = m).  MP >= m is the COMPILE-TIME column capacity: R
+// (rows < m) is left row-major with leading dimension MP and columns >= m zero in S.facc, so that the inner loops
+// carry no run-time bounds; 1 / R_jj in S.scal, R_jj in S.rdiag; the verdict of the pivot test is returned and left for
+// chol_passed (S.fm is not touched either way).
+// FULLM: m == MP == N, no run-time bound anywhere -- the pivot steps then form one basic block, and ptxas overlaps the
 // rsqrt chain of pivot j + 1 with the trailing update of pivot j.
-// Columns in registers: lane l holds column l + E of G (rows <= l + E), E = max(N - 32, 0); the first E columns have
+// Columns in registers: lane l holds column l + E of G (rows <= l + E), E = max(MP - 32, 0); the first E columns have
 // at most E rows above the diagonal and ride along in lanes 0 .. E - 1 as E extra values.
-template <int N, bool FULLM>
+template <int N, int MP, bool FULLM>
 __device__ __forceinline__ bool chol_factor(const Mem<N> &S, int lane)
 {
-    static_assert(N % 2 == 0 && N <= 48, "pairs of columns; N - 32 short extra columns");
-    constexpr int MT = (N + 7) / 8, KS = (N + 3) / 4;
-    constexpr int E = N > 32 ? N - 32 : 0, EA = E > 0 ? E : 1;
+    static_assert(MP % 2 == 0 && MP <= 48 && MP <= N && (!FULLM || MP == N), "pairs of columns; MP - 32 short extra columns");
+    constexpr int MT = (MP + 7) / 8, KS = (N + 3) / 4;
+    constexpr int E = MP > 32 ? MP - 32 : 0, EA = E > 0 ? E : 1;
     constexpr unsigned FULL = 0xffffffffu;
     const int m = FULLM ? N : S.m;
     const int ar = lane >> 2, ac = lane & 3;
@@ -745,13 +746,18 @@ __device__ __forceinline__ bool chol_factor(const Mem<N> &S, int lane)
     {
         // G = A^T A: the A operand of tile (tm, tn) is (A^T)[8 tm + ar][4 ks + ac], the B operand A[4 ks + ac][8 tn + ar]
         // -- the same fragment shape, so one load per column tile and k step serves both
-        double acc[MT][MT][2];
+        // Few tiles (partial bases): the k steps of a tile are one chain of dependent DMMAs and nothing else is in
+        // flight, so the steps alternate between two accumulator sets and the loop is unrolled.
+        constexpr int SETS = MT <= 3 ? 2 : 1;
+        double acc[SETS][MT][MT][2];
 #pragma unroll
-        for (int tm = 0; tm < MT; ++tm)
+        for (int q = 0; q < SETS; ++q)
 #pragma unroll
-            for (int tn = 0; tn < MT; ++tn) acc[tm][tn][0] = acc[tm][tn][1] = 0.;
-#pragma unroll 1
-        for (int ks = 0; ks < KS; ++ks) {
+            for (int tm = 0; tm < MT; ++tm)
+#pragma unroll
+                for (int tn = 0; tn < MT; ++tn) acc[q][tm][tn][0] = acc[q][tm][tn][1] = 0.;
+        auto kstep = [&](int ks, auto qc) {
+            constexpr int q = decltype(qc)::value;
             const int row = 4 * ks + ac;
             double f[MT];
 #pragma unroll
@@ -762,8 +768,19 @@ __device__ __forceinline__ bool chol_factor(const Mem<N> &S, int lane)
 #pragma unroll
             for (int tm = 0; tm < MT; ++tm)
 #pragma unroll
-                for (int tn = tm; tn < MT; ++tn)
-                    if (FULLM || 8 * tn < m) dmma_884(acc[tm][tn][0], acc[tm][tn][1], f[tm], f[tn]);
+                for (int tn = tm; tn < MT; ++tn) dmma_884(acc[q][tm][tn][0], acc[q][tm][tn][1], f[tm], f[tn]);
+        };
+        if (SETS == 1) {
+#pragma unroll 1
+            for (int ks = 0; ks < KS; ++ks) kstep(ks, std::integral_constant<int, 0>{});
+        } else {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                if (ks & 1)
+                    kstep(ks, std::integral_constant<int, SETS - 1>{});
+                else
+                    kstep(ks, std::integral_constant<int, 0>{});
+            }
         }
         __syncwarp();
 #pragma unroll
@@ -771,7 +788,11 @@ __device__ __forceinline__ bool chol_factor(const Mem<N> &S, int lane)
 #pragma unroll
             for (int tn = tm; tn < MT; ++tn) {
                 const int r = 8 * tm + ar, c0 = 8 * tn + 2 * ac;
-                if (r < m && c0 < N) *reinterpret_cast<double2 *>(G + r * N + c0) = make_double2(acc[tm][tn][0], acc[tm][tn][1]);
+                if (r < m && c0 < MP)
+                    *reinterpret_cast<double2 *>(G + r * MP + c0) =
+                        SETS == 2 ? make_double2(acc[0][tm][tn][0] + acc[SETS - 1][tm][tn][0],
+                                                 acc[0][tm][tn][1] + acc[SETS - 1][tm][tn][1])
+                                  : make_double2(acc[0][tm][tn][0], acc[0][tm][tn][1]);
             }
         __syncwarp();
     }
@@ -779,14 +800,14 @@ __device__ __forceinline__ bool chol_factor(const Mem<N> &S, int lane)
     long long tp1 = clock64();
 #endif
     const int cm = lane + E;                           // the lane's main column
-    const bool hasm = cm < N, hase = lane < E;
-    double gc[N], ge[EA];
+    const bool hasm = cm < MP, hase = lane < E;
+    double gc[MP], ge[EA];
 #pragma unroll
-    for (int i = 0; i < N; ++i) gc[i] = (i < m && i <= cm && hasm) ? G[i * N + cm] : 0.;
+    for (int i = 0; i < MP; ++i) gc[i] = (i < m && i <= cm && hasm) ? G[i * MP + cm] : 0.;
 #pragma unroll
-    for (int i = 0; i < EA; ++i) ge[i] = (i < m && i <= lane && hase) ? G[i * N + lane] : 0.;
-    double gmax = lane < m ? G[lane * N + lane] : 0.;
-    if (32 + lane < m) gmax = fmax(gmax, G[(32 + lane) * N + 32 + lane]);
+    for (int i = 0; i < EA; ++i) ge[i] = (i < m && i <= lane && hase) ? G[i * MP + lane] : 0.;
+    double gmax = lane < m ? G[lane * MP + lane] : 0.;
+    if (32 + lane < m) gmax = fmax(gmax, G[(32 + lane) * MP + 32 + lane]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(FULL, gmax, o));
     const double pmin = CHOL_PIVOT_MIN * gmax;
@@ -797,7 +818,7 @@ __device__ __forceinline__ bool chol_factor(const Mem<N> &S, int lane)
 #ifdef CHOL_PROF
     long long tp2 = clock64();
 #endif
-    static_for<0, N>([&](auto jc) {
+    static_for<0, MP>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         if (FULLM || j < m) {                          // uniform
             ok = ok && (p > pmin);
@@ -809,17 +830,17 @@ __device__ __forceinline__ bool chol_factor(const Mem<N> &S, int lane)
             }
             // the next pivot straight from its owner's registers: G_{j+1,j+1} - R_{j,j+1}^2 needs only the owner's own
             // R_{j,j+1}, not the round trip of row j through shared memory
-            if (j + 1 < N) {
-                constexpr int j1 = j + 1 < N ? j + 1 : 0;
+            if (j + 1 < MP) {
+                constexpr int j1 = j + 1 < MP ? j + 1 : 0;
                 const double pn = j1 < E ? fma(-rje, rje, ge[j1 < E ? j1 : 0]) : fma(-rjc, rjc, gc[j1]);
                 p = __shfl_sync(FULL, pn, j1 < E ? j1 : j1 - E);
             }
-            double *row = G + j * N;
+            double *row = G + j * MP;
             if (hasm && cm >= j) row[cm] = rjc;
             if (j < E && hase && lane >= j) row[lane] = rje;
             __syncwarp();
-            if (j + 1 < N) rinv = fast_rsqrt(p);
-            row_axpy<N, j>(gc, row, rjc);
+            if (j + 1 < MP) rinv = fast_rsqrt(p);
+            row_axpy<MP, j>(gc, row, rjc);
             if (j + 1 < E) {
 #pragma unroll
                 for (int i = j + 1; i < E; ++i) ge[i] = fma(-row[i], rje, ge[i]);
@@ -842,47 +863,47 @@ __device__ __forceinline__ bool chol_passed(const Mem<N> &S) { return S.tau[0] !
 // Q = A R^-1 by forward substitution, TWO rows of one member per thread (the loads of R's rows are broadcasts that
 // cost the load/store unit as much as any other load: two rows per load halve them), A (S.fm) is overwritten.
 // idx enumerates (member, row pair); rows r and r + N / 2.
-template <int N, bool FULLM>
+template <int N, int MP, bool FULLM>
 __device__ __forceinline__ void chol_solve(const Mem<N> &S, int pr)
 {
-    const int m = FULLM ? N : S.m;
+    const int m = FULLM ? N : S.m;               // m <= MP
     const double *R = S.facc;
     double *arow = S.fm + pr * m, *brow = S.fm + (pr + N / 2) * m;
-    double a[N], b[N];
+    double a[MP], b[MP];
     // beyond column m - 1 this reads into the next row (or the area behind the last one): finite numbers that only
     // meet the zero columns of R and are never stored
     if (FULLM) {                                       // m = N is even: rows are 16-byte aligned
 #pragma unroll
-        for (int k = 0; k < N; k += 2) {
+        for (int k = 0; k < MP; k += 2) {
             const double2 va = *reinterpret_cast<const double2 *>(arow + k), vb = *reinterpret_cast<const double2 *>(brow + k);
             a[k] = va.x, a[k + 1] = va.y, b[k] = vb.x, b[k + 1] = vb.y;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
+        for (int k = 0; k < MP; ++k) {
             a[k] = arow[k];
             b[k] = brow[k];
         }
     }
-    static_for<0, N>([&](auto jc) {
+    static_for<0, MP>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         if (FULLM || j < m) {                          // uniform
             const double s = S.scal[j];
             const double qa = a[j] * s, qb = b[j] * s;
             a[j] = qa;
             b[j] = qb;
-            if (j + 1 < N) row_axpy2<N, j>(a, b, R + j * N, qa, qb);
+            if (j + 1 < MP) row_axpy2<MP, j>(a, b, R + j * MP, qa, qb);
         }
     });
     if (FULLM) {
 #pragma unroll
-        for (int k = 0; k < N; k += 2) {
+        for (int k = 0; k < MP; k += 2) {
             *reinterpret_cast<double2 *>(arow + k) = make_double2(a[k], a[k + 1]);
             *reinterpret_cast<double2 *>(brow + k) = make_double2(b[k], b[k + 1]);
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < N; ++k)
+        for (int k = 0; k < MP; ++k)
             if (k < m) {
                 arow[k] = a[k];
                 brow[k] = b[k];
@@ -894,7 +915,7 @@ __device__ __forceinline__ void chol_solve(const Mem<N> &S, int pr)
 // whose factorisation passed the pivot test (chol_passed); the others keep A.  The verdict is per MEMBER, so that a
 // member's results do not depend on who shares its block (members sharded over devices or cut into batches must stay
 // bitwise what one launch gives).  Returns true when some member of the block refused.  Contains block barriers.
-template <int N, bool FULLM>
+template <int N, int MP, bool FULLM>
 __device__ __forceinline__ bool cholqr_block(double *smem, int stride, int jv, int m, int G, long n_members)
 {
     const int t = threadIdx.x;
@@ -902,7 +923,7 @@ __device__ __forceinline__ bool cholqr_block(double *smem, int stride, int jv, i
     bool ok = true;
     for (int gg = t >> 5; gg < G; gg += blockDim.x >> 5)
         if ((long)blockIdx.x * G + gg < n_members)
-            ok = chol_factor<N, FULLM>(carve<N>(smem + (size_t)gg * stride, jv, m), t & 31) && ok;
+            ok = chol_factor<N, MP, FULLM>(carve<N>(smem + (size_t)gg * stride, jv, m), t & 31) && ok;
     const bool refused = __syncthreads_or(!ok);
     // member index fastest: the rows of one lane are a whole row stride apart (8-way bank conflicts when neighbouring
     // lanes take neighbouring rows), the members' areas are staggered by 16 bytes modulo 128
@@ -910,11 +931,32 @@ __device__ __forceinline__ bool cholqr_block(double *smem, int stride, int jv, i
         const int pr = idx / G, gg = idx - pr * G;
         if ((long)blockIdx.x * G + gg < n_members) {
             const Mem<N> Sg = carve<N>(smem + (size_t)gg * stride, jv, m);
-            if (!refused || chol_passed<N>(Sg)) chol_solve<N, FULLM>(Sg, pr);
+            if (!refused || chol_passed<N>(Sg)) chol_solve<N, MP, FULLM>(Sg, pr);
         }
     }
     __syncthreads();
     return refused;
+}
+
+// column capacities the Cholesky QR is instantiated for: the full basis (no run-time bounds at all) and 16 / 24 / 32
+// columns for partial bases (a 10-vector basis pays for 16 columns, not for N)
+template <int N>
+__host__ __device__ constexpr bool chol_capacity_exists(int m)
+{
+    return m == N || (m < N && m <= 32 && (m <= 16 ? 16 : m <= 24 ? 24 : 32) <= N);
+}
+
+template <int N>
+__device__ __forceinline__ bool cholqr_dispatch(double *smem, int stride, int jv, int m, int G, long n_members)
+{
+    if (m == N) return cholqr_block<N, N, true>(smem, stride, jv, m, G, n_members);
+    if constexpr (N >= 16)
+        if (m <= 16) return cholqr_block<N, 16, false>(smem, stride, jv, m, G, n_members);
+    if constexpr (N >= 24)
+        if (m <= 24) return cholqr_block<N, 24, false>(smem, stride, jv, m, G, n_members);
+    if constexpr (N >= 32)
+        if (m <= 32) return cholqr_block<N, 32, false>(smem, stride, jv, m, G, n_members);
+    return true;            // not reached: the launch only asks for capacities that exist (chol_capacity_exists)
 }
 
 template <int N, class Prod>
@@ -1087,8 +1129,7 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
             !(P.rec_fm && P.write_steps > 0 && step + 1 >= P.n_pre && (step + 1 - P.n_pre) % P.write_steps == 0)) {
             // nobody sees this step's Q or R: Cholesky QR (see chol_factor); members that refuse a pivot, and only
             // they, go through the Householder code below
-            householder = partial = m == N ? cholqr_block<N, true>(smem_pack, stride, Prod::JV, m, G, P.n_members)
-                                           : cholqr_block<N, false>(smem_pack, stride, Prod::JV, m, G, P.n_members);
+            householder = partial = cholqr_dispatch<N>(smem_pack, stride, Prod::JV, m, G, P.n_members);
             if (partial) {
                 hh = live && !chol_passed<N>(S);
                 hhq = liveq && !chol_passed<N>(Sq);
@@ -1238,7 +1279,7 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
         // [B200, 8192 members, exponents only: MAOOAM-36 36 vectors x1.42, 20 vectors x1.07, 10 vectors x0.78 (the
         // unrolled pivot steps run over all N columns of the padded factor); RP-20 x1.19; dynamic-T 38 vectors x1.25]
         const char *envc = getenv("QGSB_QR_CHOL");
-        const int chol = envc ? (envc[0] != '0') : (2 * P.m > N);
+        const int chol = chol_capacity_exists<N>(P.m) && (envc ? (envc[0] != '0') : (P.m >= 8));
         kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, tab, geo.G, geo.stride, remap | (chol << 1));
         return cudaGetLastError();
     };

@@ -23,8 +23,7 @@ __global__ void __launch_bounds__(256, 1) k_chol(double *buf, int m, int stride,
         __syncthreads();
         long long c1 = clock64();
         long long c2 = c1;
-        const bool done = m == N ? cholqr_block<N, true>(smem_pack, stride, 0, m, GM, 1L << 40)
-                                 : cholqr_block<N, false>(smem_pack, stride, 0, m, GM, 1L << 40);
+        const bool done = !cholqr_dispatch<N>(smem_pack, stride, 0, m, GM, 1L << 40);
         if (!done && t == 0) *flag = 1;
         long long c3 = clock64();
         tl += c1 - c0; tf += c2 - c1; ts += c3 - c2;
@@ -64,6 +63,7 @@ int main(int argc, char **argv)
     cudaMemcpy(&hf, flag, 4, cudaMemcpyDeviceToHost);
     printf("launch: %s, refused pivots: %d\n", cudaGetErrorString(cudaGetLastError()), hf);
     double eo = 0., er = 0.;
+    const int ld = m == NN ? NN : m <= 16 ? 16 : m <= 24 ? 24 : 32;      // column capacity of the instantiation
     for (int b = 0; b < blocks * GM; ++b) {
         const double *Q = h.data() + (size_t)b * stride + cv.o_fm(), *R = h.data() + (size_t)b * stride + cv.o_facc();
         const double *A = h0.data() + (size_t)b * stride + cv.o_fm();
@@ -76,7 +76,7 @@ int main(int argc, char **argv)
         for (int i = 0; i < NN; ++i)
             for (int c = 0; c < m; ++c) {
                 double s = 0.;
-                for (int k = 0; k <= c; ++k) s += Q[i * m + k] * R[k * NN + c];
+                for (int k = 0; k <= c; ++k) s += Q[i * m + k] * R[k * ld + c];
                 er = fmax(er, fabs(s - A[i * m + c]));
             }
     }

@@ -6,5 +6,7 @@ from scripts.perf_probe2 import lyap, tgls
 _lib.init(0)
 if len(sys.argv) > 1 and sys.argv[1] == "tgls":
     tgls("maooam36", 2048, 10)
+elif len(sys.argv) > 1 and sys.argv[1].startswith("m="):
+    lyap("maooam36", 4096, 4, 16, m=int(sys.argv[1][2:]))
 else:
     lyap("maooam36", 2048, 4, 16)

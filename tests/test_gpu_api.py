@@ -434,7 +434,9 @@ def test_pipelined_host_buffer_path_is_bitwise_the_resident_path():
 
 
 def test_exponents_only_run_equals_the_full_run():
-    """compute_lyapunovs(vectors=False) skips the vector records; trajectory and exponents are unchanged."""
+    """compute_lyapunovs(vectors=False) skips the vector records; the trajectory is unchanged to the bit, the exponents to
+    rounding (without vector records the steps in front of a record take the Cholesky QR too instead of Householder:
+    same subspaces, same |diag R|, another rounding -- DESIGN.md section 4.3)."""
     from qgs_b200.toolbox.lyapunov import LyapunovsEstimator
     f, Df, T = model("maooam36")
     ic = np.random.default_rng(3).random((9, 36)) * 0.01
@@ -446,7 +448,8 @@ def test_exponents_only_run_equals_the_full_run():
         est.compute_lyapunovs(0., 1., 3., 0.1, 0.1, ic=ic, write_steps=4, n_vec=12, vectors=vectors)
         out.append(est.get_lyapunovs())
     assert out[1][3] is None and out[0][3].shape == (9, 36, 12, 6)
-    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.abs(out[0][2] - out[1][2]).max() < 1e-12
 
 
 # ---- callers pinned against outputs of the UNMODIFIED reference (tests/golden/make_golden_extra.py) ---------------------------

@@ -60,7 +60,8 @@ def _benettin(name, N, n_vec, q0, r0, seed=None, vectors=True, mode=0, mdt=0.1, 
 
 
 # ---- Cholesky QR on the steps nobody looks at --------------------------------------------------------------------------
-@pytest.mark.parametrize("name,n_vec", [("maooam36", 36), ("maooam36", 24), ("rp", 20), ("dynT", 38)])
+@pytest.mark.parametrize("name,n_vec", [("maooam36", 36), ("maooam36", 24), ("maooam36", 17), ("maooam36", 10),
+                                        ("maooam36", 9), ("rp", 20), ("rp", 12), ("dynT", 38), ("dynT", 30)])
 @pytest.mark.parametrize("vectors", [True, False])
 def test_cholesky_qr_steps_reproduce_the_householder_run(name, n_vec, vectors):
     """Between two records the Benettin kernel factorises with a Cholesky QR on the FP64 tensor cores (Gram matrix by
@@ -68,7 +69,8 @@ def test_cholesky_qr_steps_reproduce_the_householder_run(name, n_vec, vectors):
     reference's np.linalg.qr, lyapunov.py:602-604 -- for every step whose Q or R is recorded or returned.  Householder's Q
     does not depend on the signs of the columns it is given, so the RECORDED vectors keep np.linalg.qr's signs; the
     run with QGSB_QR_CHOL=0 (Householder everywhere, what the golden tests pin against the reference) must be
-    reproduced to rounding: exponents (log|diag R|) and vectors, full and partial bases, with and without vector records."""
+    reproduced to rounding: exponents (log|diag R|) and vectors, with and without vector records, the full basis and
+    partial bases in each compile-time column capacity (16, 24, 32), odd vector counts included."""
     f, Df, T = model(name)
     n = f.ndim
     N = 23
