@@ -258,7 +258,13 @@ __device__ __forceinline__ ShTab stage_tables(const PackTables &tab, double *dst
 // ---- one step of the coupled system (chain tableau) -----------------------------------------------------------------
 // col[] holds fm[:, c] on entry and on exit; S.y advances by dt.  No barrier at the end: the caller
 // synchronises before anybody reads another thread's data.
-template <int N, class Prod>
+// FAREG: the weighted sum of the stage derivatives of the column stays in registers (fa) instead of in the column's
+// slice of S.facc.  In shared memory the sum costs a load and a store per element and stage, a third of the stage
+// epilogue's traffic; in registers it is 2 N more of them next to the column and the product.  [B200, 8192 members]
+// tangent-linear kernel: MAOOAM-36 5.42 -> 6.11e7 member-steps/s, RP-20 1.24 -> 1.38e8; Benettin kernel: RP-20 6.36 ->
+// 6.85e7, but MAOOAM-36 2.49 -> 2.40e7 (the Benettin loop keeps more state live across the step and spills 688 bytes
+// at 36 variables): the plain integration always takes it, the Benettin loop only for small bases (N <= 24).
+template <int N, class Prod, bool FAREG>
 __device__ __forceinline__ void tangent_step(const TensorView &T, const ShTab &tab, const TgParams &P,
                                              const Mem<N> &S, double dt, double (&col)[N], int c, bool live,
                                              const Mem<N> &Sr, int cr, bool liver)
@@ -269,7 +275,7 @@ __device__ __forceinline__ void tangent_step(const TensorView &T, const ShTab &t
     // Every access to y, yacc, kst and the row part of xs goes through this mapping, so no barrier is needed between
     // them.
     const int s = P.s, m = S.m;
-    double km[N];
+    double km[N], fa[FAREG ? N : 1];
     for (int st = 0; st < s; ++st) {
         const double wa_in = st > 0 ? dt * P.a[st * s + st - 1] : 0.;       // (dt a[st]) @ k   integrate.py:216
         const double wb = dt * P.b[st];
@@ -294,14 +300,18 @@ __device__ __forceinline__ void tangent_step(const TensorView &T, const ShTab &t
         if (live) {
             // km = inverse * (J or J^T) @ col        integrate.py:601-603, boundary == 0
             Prod::apply(S.jv, xs, col, km);
-            double *fc = S.facc + c;
             double *fmc = S.fm + c;
+            double *fc = S.facc + c;
             if (st + 1 < s) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     const double k = P.inverse * km[i];
-                    const double f = st == 0 ? wb * k : fc[i * m] + wb * k;      // fm + sum dt b_j km_j  :605-607
-                    fc[i * m] = f;
+                    if (FAREG) {
+                        fa[i] = st == 0 ? wb * k : fa[i] + wb * k;               // sum dt b_j km_j  :605-607
+                    } else {
+                        const double f = st == 0 ? wb * k : fc[i * m] + wb * k;
+                        fc[i * m] = f;
+                    }
                     col[i] = fmc[i * m] + wa_out * k;                            // km_s of the next stage :598-600
                 }
             } else {
@@ -310,7 +320,7 @@ __device__ __forceinline__ void tangent_step(const TensorView &T, const ShTab &t
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     const double k = P.inverse * km[i];
-                    const double f = st == 0 ? wb * k : fc[i * m] + wb * k;
+                    const double f = st == 0 ? wb * k : (FAREG ? fa[i] : fc[i * m]) + wb * k;
                     col[i] = fmc[i * m] + f;
                     fmc[i * m] = col[i];
                 }
@@ -1016,7 +1026,7 @@ tgls_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
             }
             ++iw;
         }
-        tangent_step<N, Prod>(T, tab, P, S, P.dt[ti], col, c, live, Sq, cq, liveq);
+        tangent_step<N, Prod, true>(T, tab, P, S, P.dt[ti], col, c, live, Sq, cq, liveq);
         __syncthreads();
     }
     if (live) {
@@ -1120,7 +1130,7 @@ lyap_kernel(TensorView T, const __grid_constant__ TgParams P, const PackTables t
                 for (int r = cq; r < N; r += m) Sq.y[r] = Sq.Y[r];
             q0 = P.sub_ptr[step];
             q1 = P.sub_ptr[step + 1];
-            for (long q = q0; q < q1; ++q) tangent_step<N, Prod>(T, tab, P, S, P.sub_dt[q], col, c, live, Sq, cq, liveq);
+            for (long q = q0; q < q1; ++q) tangent_step<N, Prod, (N <= 24)>(T, tab, P, S, P.sub_dt[q], col, c, live, Sq, cq, liveq);
         }
         // q, r = qr(prop @ q)   (:602-604)
         // hh / hhq: the thread's Householder roles (its own column; with the remap the column it factorises)
