@@ -24,12 +24,14 @@ static int forced_kernel()
     return 0;
 }
 
-template <int N>
-static cudaError_t launch_dense(const TensorView &T, const TgParams &P, const PackTables &tab, bool lyap)
-{
-    return pack::launch<N, pack::DenseProduct<N, false>, pack::DenseProduct<N, true>>(T, P, tab, lyap, ctx().smem_optin,
-                                                                                       ctx().stream);
-}
+// dense-product kernels of one ndim: each instantiation lives in its own translation unit (tgls_pack_dense_<n>.cu),
+// so that the three of them compile side by side
+cudaError_t launch_pack_dense_20(const TensorView &T, const TgParams &P, const PackTables &tab, bool lyap, size_t smem,
+                                 cudaStream_t stream);
+cudaError_t launch_pack_dense_36(const TensorView &T, const TgParams &P, const PackTables &tab, bool lyap, size_t smem,
+                                 cudaStream_t stream);
+cudaError_t launch_pack_dense_38(const TensorView &T, const TgParams &P, const PackTables &tab, bool lyap, size_t smem,
+                                 cudaStream_t stream);
 
 static bool dense_ndim(int n) { return n == 20 || n == 36 || n == 38; }
 
@@ -176,9 +178,9 @@ void launch_pack_tangent(const qgsb_tensor *t, const TgParams &P, bool lyap)
     } else {
         const PackTables &tab = pack_tables(t, false);
         switch (t->view.n) {
-            case 20: err = launch_dense<20>(t->view, P, tab, lyap); break;
-            case 36: err = launch_dense<36>(t->view, P, tab, lyap); break;
-            case 38: err = launch_dense<38>(t->view, P, tab, lyap); break;
+            case 20: err = launch_pack_dense_20(t->view, P, tab, lyap, ctx().smem_optin, ctx().stream); break;
+            case 36: err = launch_pack_dense_36(t->view, P, tab, lyap, ctx().smem_optin, ctx().stream); break;
+            case 38: err = launch_pack_dense_38(t->view, P, tab, lyap, ctx().smem_optin, ctx().stream); break;
             default: err = cudaErrorInvalidValue;
         }
     }
