@@ -880,8 +880,6 @@ __device__ __forceinline__ void chol_solve(const Mem<N> &S, int pr)
     const double *R = S.facc;
     double *arow = S.fm + pr * m, *brow = S.fm + (pr + N / 2) * m;
     double a[MP], b[MP];
-    // beyond column m - 1 this reads into the next row (or the area behind the last one): finite numbers that only
-    // meet the zero columns of R and are never stored
     if (FULLM) {                                       // m = N is even: rows are 16-byte aligned
 #pragma unroll
         for (int k = 0; k < MP; k += 2) {
@@ -889,10 +887,11 @@ __device__ __forceinline__ void chol_solve(const Mem<N> &S, int pr)
             a[k] = va.x, a[k + 1] = va.y, b[k] = vb.x, b[k + 1] = vb.y;
         }
     } else {
+        // columns m .. MP - 1 do not exist (they would be the next row, which another thread is rewriting)
 #pragma unroll
         for (int k = 0; k < MP; ++k) {
-            a[k] = arow[k];
-            b[k] = brow[k];
+            a[k] = k < m ? arow[k] : 0.;
+            b[k] = k < m ? brow[k] : 0.;
         }
     }
     static_for<0, MP>([&](auto jc) {

@@ -107,3 +107,28 @@ if "round2" in which:
     os.environ.pop("QGSB_TGLS_KERNEL")
     os.environ.pop("QGSB_TANGENT_BUDGET_MB")
     print("round2 ok", flush=True)
+
+if "cholqr" in which:
+    # Cholesky QR of the packed Benettin kernel (pack::chol_factor / chol_solve): every column capacity, with and
+    # without vector records (write_steps = 3: two Cholesky steps, one Householder step), a basis with a repeated column
+    # (pivot refused, per-member Householder fallback), the tangent-linear kernel with the stage sum in registers
+    from qgs_b200.toolbox.lyapunov import benettin
+    from qgs_b200.integrators.integrate import rk4_tableau
+    b_, c_, a_ = rk4_tableau()
+    pre = np.concatenate((np.arange(0., 0.3, 0.1), [0.3]))
+    tim = np.concatenate((np.arange(0.3, 1.0, 0.1), [1.0]))
+    for name, vecs in (("maooam36", (36, 20, 10)), ("rp", (20, 12)), ("dynT", (38, 30))):
+        f, Df = load(name)
+        n = f.ndim
+        ic = rng.random((9, n)) * 0.01
+        for m in vecs:
+            q0 = np.stack([np.linalg.qr(rng.random((n, m)))[0] for _ in range(9)])
+            for vectors in (True, False):
+                benettin(f, Df, ic, 0, m, q0, None, pre, tim, 0.1, 3, False, 1., b_, c_, a_, want_vectors=vectors)
+        q0 = np.stack([np.linalg.qr(rng.random((n, n)))[0] for _ in range(9)])
+        q0[4, :, 3] = q0[4, :, 2]
+        benettin(f, Df, ic, 0, n, q0, None, pre, tim, 0.1, 3, False, 1., b_, c_, a_, want_vectors=False)
+        tg = RungeKuttaTglsIntegrator()
+        tg.set_func(f, Df)
+        tg.integrate(0., 0.3, 0.1, ic=ic, write_steps=1)
+    print("cholqr ok", flush=True)
