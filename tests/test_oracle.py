@@ -147,3 +147,23 @@ def test_n_records_rule():
                 tot = time[::ws]
                 exp = len(tot) + (1 if tot[-1] != time[-1] else 0)
             assert oracle.n_records(L, ws) == exp
+
+
+def test_householder_q_does_not_depend_on_the_signs_of_the_columns():
+    """The property the device's Cholesky-QR steps rest on: np.linalg.qr -- LAPACK's Householder
+    factorisation, lyapunov.py:602-604 -- returns the same Q for A and for A D, D = diag(+-1), and R with its columns
+    flipped.  So an unobserved Benettin step may hand on Q D instead of Q: the next Householder step gives the same Q and
+    the same |diag R|."""
+    rng = np.random.default_rng(12)
+    for n, m in ((36, 36), (36, 10), (20, 20)):
+        a = rng.standard_normal((n, m))
+        d = np.where(rng.random(m) < 0.5, -1., 1.)
+        q0, r0 = np.linalg.qr(a)
+        q1, r1 = np.linalg.qr(a * d)
+        assert np.abs(q0 - q1).max() < 1e-13
+        assert np.abs(r0 * d - r1).max() < 1e-13
+        # and a Cholesky QR spans the same nested subspaces: Q_chol = Q D' with D' = sign(diag R)
+        rc = np.linalg.cholesky(a.T @ a).T
+        qc = a @ np.linalg.inv(rc)
+        assert np.abs(qc - q0 * np.sign(np.diag(r0))).max() < 1e-11
+        assert np.abs(np.diag(rc) - np.abs(np.diag(r0))).max() < 1e-12
