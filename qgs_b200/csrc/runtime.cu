@@ -4,7 +4,9 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <cstring>
 #include <map>
+#include <memory>
 #include <numeric>
 #include <thread>
 
@@ -80,8 +82,11 @@ static void context_close(Context &c)
     c.ready = false;
 }
 
+void raw_cache_clear();
+
 static void close_all()
 {
+    raw_cache_clear();
     for (int g = 0; g < MAX_DEVICES; ++g) context_close(g_ctx[g]);
     g_slots = 0;
 }
@@ -871,35 +876,123 @@ int qgsb_tensor_use_specialised(qgsb_tensor *t, int enable)
 }
 
 // ---- raw contractions --------------------------------------------------------------------------
+// sparse_mul2/3/4/5 take the tensor as host arrays on every call.  A user loop that calls them with the same tensor
+// (what the reference's own f / Df closures do, tendencies.py:98-121) must not pay for sorting, four cudaMallocs and
+// the upload each time: the prepared device copy is kept in a small cache keyed by the CONTENT of (coo, val) -- a
+// 64-bit FNV-1a over the words of both arrays, plus rank, length and device -- and the vectors go through the
+// context's scratch pool.  The arrays may be freed or rewritten between calls: only their content is looked at.
+}  // extern "C"
+
+namespace {
+
+struct RawTensor {
+    uint64_t key = 0;
+    int rank = 0, n1 = 0, device = -1, npos = 0;
+    long nnz = 0;
+    bool mat = false;
+    uint64_t stamp = 0;
+    DevBuf<Entry> ent;
+    DevBuf<int> a, b, c;          // vec: row_ptr; mat: pos_ptr, pos_i, pos_j
+};
+
+std::vector<std::unique_ptr<RawTensor>> raw_cache;
+uint64_t raw_clock = 0;
+constexpr size_t RAW_CACHE_ENTRIES = 16;
+
+uint64_t content_key(int rank, int n1, long nnz, bool mat, const int32_t *coo, const double *val)
+{
+    uint64_t h = 1469598103934665603ULL;
+    auto mix = [&](uint64_t w) { h = (h ^ w) * 1099511628211ULL; };
+    mix((uint64_t)rank);
+    mix((uint64_t)n1);
+    mix((uint64_t)nnz);
+    mix(mat ? 1 : 0);
+    const size_t words = (size_t)nnz * rank;
+    for (size_t q = 0; q + 1 < words; q += 2) mix((uint64_t)(uint32_t)coo[q] | ((uint64_t)(uint32_t)coo[q + 1] << 32));
+    if (words & 1) mix((uint64_t)(uint32_t)coo[words - 1]);
+    for (long q = 0; q < nnz; ++q) {
+        uint64_t w;
+        memcpy(&w, val + q, sizeof(w));
+        mix(w);
+    }
+    return h;
+}
+
+RawTensor &raw_tensor(int rank, int n1, long nnz, bool mat, const int32_t *coo, const double *val)
+{
+    int device = 0;
+    QGSB_CUDA(cudaGetDevice(&device));
+    const uint64_t key = content_key(rank, n1, nnz, mat, coo, val);
+    for (auto &e : raw_cache)
+        if (e->key == key && e->rank == rank && e->n1 == n1 && e->nnz == nnz && e->mat == mat && e->device == device) {
+            e->stamp = ++raw_clock;
+            return *e;
+        }
+    if (raw_cache.size() >= RAW_CACHE_ENTRIES) {
+        size_t oldest = 0;
+        for (size_t q = 1; q < raw_cache.size(); ++q)
+            if (raw_cache[q]->stamp < raw_cache[oldest]->stamp) oldest = q;
+        raw_cache.erase(raw_cache.begin() + oldest);
+    }
+    std::unique_ptr<RawTensor> e(new RawTensor);
+    e->key = key;
+    e->rank = rank;
+    e->n1 = n1;
+    e->nnz = nnz;
+    e->mat = mat;
+    e->device = device;
+    e->stamp = ++raw_clock;
+    if (mat) {
+        HostJac h = prepare_mat(n1, rank, nnz, coo, val, true);
+        to_device(e->ent, h.ent);
+        to_device(e->a, h.pos_ptr);
+        to_device(e->b, h.pos_i);
+        to_device(e->c, h.pos_j);
+        e->npos = (int)h.pos_i.size();
+    } else {
+        HostTensor h = prepare_vec(n1, rank, nnz, coo, val);
+        to_device(e->ent, h.ent);
+        to_device(e->a, h.row_ptr);
+    }
+    raw_cache.push_back(std::move(e));
+    return *raw_cache.back();
+}
+
+}  // namespace
+
+// called when the contexts are closed (qgsb_shutdown, a change of the device list)
+namespace qgsb {
+void raw_cache_clear() { raw_cache.clear(); }
+}  // namespace qgsb
+
+extern "C" {
+
 static void raw_mulvec(int rank, long nnz, const int32_t *coo, const double *val, int n1, const double *va,
                        const double *vb, const double *vc, const double *vd, double *res)
 {
     ensure_init();
     cudaStream_t s = ctx().stream;
-    HostTensor h = prepare_vec(n1, rank, nnz, coo, val);
-    DevBuf<Entry> d_ent;
-    DevBuf<int> d_row;
-    to_device(d_ent, h.ent);
-    to_device(d_row, h.row_ptr);
-    DevBuf<double> d_v((size_t)4 * n1), d_out(n1);
+    RawTensor &R = raw_tensor(rank, n1, nnz, false, coo, val);
+    PoolBuf<double> d_v((size_t)5 * n1);
+    double *d_out = d_v.p + (size_t)4 * n1;
     const double *vs[4] = {va, vb, vc ? vc : va, vd ? vd : va};
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < (rank == 5 ? 4 : 2); ++q)
         QGSB_CUDA(cudaMemcpyAsync(d_v.p + (size_t)q * n1, vs[q], sizeof(double) * n1, cudaMemcpyHostToDevice, s));
     TensorView T;
     T.n = n1 - 1;
     T.rank = rank;
     T.nnz = (int)nnz;
-    T.ent = d_ent.p;
-    T.row_ptr = d_row.p;
+    T.ent = R.ent.p;
+    T.row_ptr = R.a.p;
     const int threads = 128, blocks = (n1 + threads - 1) / threads;
     if (rank == 5)
         mulvec_kernel<5><<<blocks, threads, 0, s>>>(T, 1, n1, d_v.p, d_v.p + n1, d_v.p + 2 * n1, d_v.p + 3 * n1, 0, 0,
-                                                    d_out.p, 0, n1);
+                                                    d_out, 0, n1);
     else
-        mulvec_kernel<3><<<blocks, threads, 0, s>>>(T, 1, n1, d_v.p, d_v.p + n1, d_v.p, d_v.p, 0, 0, d_out.p, 0, n1);
+        mulvec_kernel<3><<<blocks, threads, 0, s>>>(T, 1, n1, d_v.p, d_v.p + n1, d_v.p, d_v.p, 0, 0, d_out, 0, n1);
     count_launch();
     QGSB_CUDA(cudaGetLastError());
-    d_out.download(res, n1, s);
+    QGSB_CUDA(cudaMemcpyAsync(res, d_out, sizeof(double) * n1, cudaMemcpyDeviceToHost, s));
     QGSB_CUDA(cudaStreamSynchronize(s));
 }
 
@@ -908,34 +1001,29 @@ static void raw_mulmat(int rank, long nnz, const int32_t *coo, const double *val
 {
     ensure_init();
     cudaStream_t s = ctx().stream;
-    HostJac h = prepare_mat(n1, rank, nnz, coo, val, true);
-    DevBuf<Entry> d_ent;
-    DevBuf<int> d_pp, d_pi, d_pj;
-    to_device(d_ent, h.ent);
-    to_device(d_pp, h.pos_ptr);
-    to_device(d_pi, h.pos_i);
-    to_device(d_pj, h.pos_j);
-    DevBuf<double> d_v((size_t)3 * n1), d_out((size_t)n1 * n1);
+    RawTensor &R = raw_tensor(rank, n1, nnz, true, coo, val);
+    PoolBuf<double> d_v((size_t)3 * n1 + (size_t)n1 * n1);
+    double *d_out = d_v.p + (size_t)3 * n1;
     const double *vs[3] = {va, vb ? vb : va, vc ? vc : va};
-    for (int q = 0; q < 3; ++q)
+    for (int q = 0; q < (rank == 5 ? 3 : 1); ++q)
         QGSB_CUDA(cudaMemcpyAsync(d_v.p + (size_t)q * n1, vs[q], sizeof(double) * n1, cudaMemcpyHostToDevice, s));
-    QGSB_CUDA(cudaMemsetAsync(d_out.p, 0, sizeof(double) * n1 * n1, s));
+    QGSB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * n1 * n1, s));
     JacView J;
-    J.npos = (int)h.pos_i.size();
-    J.pos_ptr = d_pp.p;
-    J.ent = d_ent.p;
-    J.pos_i = d_pi.p;
-    J.pos_j = d_pj.p;
+    J.npos = R.npos;
+    J.pos_ptr = R.a.p;
+    J.ent = R.ent.p;
+    J.pos_i = R.b.p;
+    J.pos_j = R.c.p;
     if (J.npos > 0) {
         const int threads = 128, blocks = (J.npos + threads - 1) / threads;
         if (rank == 5)
-            mulmat_kernel<5><<<blocks, threads, 0, s>>>(J, 1, d_v.p, d_v.p + n1, d_v.p + 2 * n1, 0, 0, d_out.p, 0, n1);
+            mulmat_kernel<5><<<blocks, threads, 0, s>>>(J, 1, d_v.p, d_v.p + n1, d_v.p + 2 * n1, 0, 0, d_out, 0, n1);
         else
-            mulmat_kernel<3><<<blocks, threads, 0, s>>>(J, 1, d_v.p, d_v.p, d_v.p, 0, 0, d_out.p, 0, n1);
+            mulmat_kernel<3><<<blocks, threads, 0, s>>>(J, 1, d_v.p, d_v.p, d_v.p, 0, 0, d_out, 0, n1);
         count_launch();
         QGSB_CUDA(cudaGetLastError());
     }
-    d_out.download(res, (size_t)n1 * n1, s);
+    QGSB_CUDA(cudaMemcpyAsync(res, d_out, sizeof(double) * n1 * n1, cudaMemcpyDeviceToHost, s));
     QGSB_CUDA(cudaStreamSynchronize(s));
 }
 

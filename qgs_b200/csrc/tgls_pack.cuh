@@ -1285,8 +1285,9 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
         const char *env = getenv("QGSB_QR_REMAP");
         const int remap = env ? (env[0] != '0') : 1;
         // Cholesky QR for the steps whose Q, R are not observed (chol_factor); QGSB_QR_CHOL=0 keeps Householder everywhere
-        // [B200, 8192 members, exponents only: MAOOAM-36 36 vectors x1.42, 20 vectors x1.07, 10 vectors x0.78 (the
-        // unrolled pivot steps run over all N columns of the padded factor); RP-20 x1.19; dynamic-T 38 vectors x1.25]
+        // [B200, 8192 members, exponents only, against Householder everywhere: MAOOAM-36 36 vectors x1.51, 20 vectors
+        // x1.42, 10 vectors x1.04, 5 vectors x0.98; RP-20 x1.19; dynamic-T 38 vectors x1.23]: on from 8 vectors, where a
+        // column capacity exists (chol_capacity_exists)
         const char *envc = getenv("QGSB_QR_CHOL");
         const int chol = chol_capacity_exists<N>(P.m) && (envc ? (envc[0] != '0') : (P.m >= 8));
         kernel<<<blocks, geo.threads, geo.smem, stream>>>(T, P, tab, geo.G, geo.stride, remap | (chol << 1));

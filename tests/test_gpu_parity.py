@@ -61,6 +61,45 @@ def test_sparse_mul_raw(name):
     assert rel(m, g["mul_mat"]) < 1e-12
 
 
+def test_raw_contractions_reuse_the_device_tensor_by_content():
+    """sparse_mul2/3 take the tensor as host arrays on every call; the library keeps the prepared device copy in a cache
+    keyed by the CONTENT of (coo, val).  Repeated calls, a tensor rewritten in place, arrays that only share their
+    content, and more distinct tensors than the cache holds must all give what a fresh call gives."""
+    from qgs_b200.functions import sparse_mul as sm
+    rng = np.random.default_rng(6)
+    n1 = 13
+
+    def rand_tensor(nnz):
+        coo = np.stack([rng.integers(0, n1, nnz) for _ in range(3)], axis=1)
+        return coo, rng.standard_normal(nnz)
+
+    def expect3(coo, val, a, b):
+        out = np.zeros(n1)
+        np.add.at(out, coo[:, 0], val * a[coo[:, 1]] * b[coo[:, 2]])
+        out[0] = 1.
+        return out
+
+    def expect2(coo, val, a):
+        out = np.zeros((n1, n1))
+        np.add.at(out, (coo[:, 0], coo[:, 1]), val * a[coo[:, 2]])
+        return out
+
+    a, b = rng.standard_normal(n1), rng.standard_normal(n1)
+    coo, val = rand_tensor(60)
+    for _ in range(3):                                               # a hit after the first call
+        assert np.allclose(sm.sparse_mul3(coo, val, a, b), expect3(coo, val, a, b), rtol=1e-13, atol=1e-13)
+        assert np.allclose(sm.sparse_mul2(coo, val, a), expect2(coo, val, a), rtol=1e-13, atol=1e-13)
+    val[7] = 42.                                                     # the same arrays, another content
+    assert np.allclose(sm.sparse_mul3(coo, val, a, b), expect3(coo, val, a, b), rtol=1e-13, atol=1e-13)
+    coo[3] = (5, 2, 9)
+    assert np.allclose(sm.sparse_mul2(coo, val, a), expect2(coo, val, a), rtol=1e-13, atol=1e-13)
+    assert np.allclose(sm.sparse_mul3(coo.copy(), val.copy(), a, b), expect3(coo, val, a, b), rtol=1e-13, atol=1e-13)
+    tensors = [rand_tensor(20 + q) for q in range(40)]               # more than the cache keeps, twice round
+    for _ in range(2):
+        for c, v in tensors:
+            assert np.allclose(sm.sparse_mul3(c, v, a, b), expect3(c, v, a, b), rtol=1e-13, atol=1e-13)
+
+
 def test_sparse_mul_edge_cases():
     from qgs_b200.functions import sparse_mul as sm
     # empty tensor: res = 0 except res[0] = 1
