@@ -37,6 +37,12 @@ namespace pack {
 #ifndef QGSB_PACK_THREADS
 #define QGSB_PACK_THREADS 256
 #endif
+// 1: a lean build for modules compiled at run time (codegen.build_plugin): the rolled Householder kernels only (bitwise
+// the unrolled ones, a few per cent slower on full bases) and the Cholesky QR for the full basis only (partial bases
+// keep Householder).  The full set takes nvcc two minutes per module, the lean one half a minute.
+#ifndef QGSB_PACK_LEAN
+#define QGSB_PACK_LEAN 0
+#endif
 #ifndef QGSB_PACK_BLOCKS
 #define QGSB_PACK_BLOCKS 1
 #endif
@@ -952,18 +958,18 @@ __device__ __forceinline__ bool cholqr_block(double *smem, int stride, int jv, i
 template <int N>
 __host__ __device__ constexpr bool chol_capacity_exists(int m)
 {
-    return m == N || (m < N && m <= 32 && (m <= 16 ? 16 : m <= 24 ? 24 : 32) <= N);
+    return m == N || (!QGSB_PACK_LEAN && m < N && m <= 32 && (m <= 16 ? 16 : m <= 24 ? 24 : 32) <= N);
 }
 
 template <int N>
 __device__ __forceinline__ bool cholqr_dispatch(double *smem, int stride, int jv, int m, int G, long n_members)
 {
     if (m == N) return cholqr_block<N, N, true>(smem, stride, jv, m, G, n_members);
-    if constexpr (N >= 16)
+    if constexpr (N >= 16 && !QGSB_PACK_LEAN)
         if (m <= 16) return cholqr_block<N, 16, false>(smem, stride, jv, m, G, n_members);
-    if constexpr (N >= 24)
+    if constexpr (N >= 24 && !QGSB_PACK_LEAN)
         if (m <= 24) return cholqr_block<N, 24, false>(smem, stride, jv, m, G, n_members);
-    if constexpr (N >= 32)
+    if constexpr (N >= 32 && !QGSB_PACK_LEAN)
         if (m <= 32) return cholqr_block<N, 32, false>(smem, stride, jv, m, G, n_members);
     return true;            // not reached: the launch only asks for capacities that exist (chol_capacity_exists)
 }
@@ -1305,9 +1311,11 @@ inline cudaError_t launch(const TensorView &T, const TgParams &P, const PackTabl
         // vectors, +5 % at 20: half the barriers, but the chain of dependent scalar instructions -- square root, two
         // reciprocals, ~19 deep per reflector at 12-19 cycles each -- is what a reflector costs, and it stays).
         const char *env = getenv("QGSB_QR_ROLLED");               // 0 / 1 forces one of them (A/B measurements)
-        const bool rolled = env ? (env[0] != '0') : (3 * P.m <= N);
+        const bool rolled = QGSB_PACK_LEAN || (env ? (env[0] != '0') : (3 * P.m <= N));
         if (rolled) return P.adjoint ? go_lyap(lyap_kernel<N, Adj, true>) : go_lyap(lyap_kernel<N, Fwd, true>);
-        return P.adjoint ? go_lyap(lyap_kernel<N, Adj, false>) : go_lyap(lyap_kernel<N, Fwd, false>);
+        if constexpr (!QGSB_PACK_LEAN)
+            return P.adjoint ? go_lyap(lyap_kernel<N, Adj, false>) : go_lyap(lyap_kernel<N, Fwd, false>);
+        return cudaErrorInvalidValue;       // not reached
     }
     return P.adjoint ? go(tgls_kernel<N, Adj>) : go(tgls_kernel<N, Fwd>);
 }

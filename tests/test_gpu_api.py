@@ -272,6 +272,20 @@ def test_runtime_specialised_plugin_matches_generic():
         del os.environ["QGSB_TGLS_KERNEL"]
     ys, ms = _integrate_runge_kutta_tgls_jit(fs2, Dfs, tt, ic[:9], tg, 1, 2, b, c, a, False, 1., _zeros_func)
     assert rel(ys, yg) < 1e-11 and rel(ms, mg) < 1e-10
+    # ... and its Benettin kernels (a run-time module is a lean build: Cholesky QR between records for the full basis,
+    # Householder for partial ones) against the generic block-per-member kernel
+    from qgs_b200.toolbox.lyapunov import benettin
+    rng = np.random.default_rng(2)
+    pre = np.concatenate((np.arange(0., 0.4, 0.1), [0.4]))
+    for n_vec in (36, 14):
+        q0 = np.stack([np.linalg.qr(rng.random((36, n_vec)))[0] for _ in range(9)])
+        os.environ["QGSB_TGLS_KERNEL"] = "generic"
+        try:
+            tg_, eg_, vg_ = benettin(fg2, Dfg, ic[:9], 0, n_vec, q0, None, pre, tt + 0.4, 0.1, 3, False, 1., b, c, a)
+        finally:
+            del os.environ["QGSB_TGLS_KERNEL"]
+        ts_, es_, vs_ = benettin(fs2, Dfs, ic[:9], 0, n_vec, q0, None, pre, tt + 0.4, 0.1, 3, False, 1., b, c, a)
+        assert rel(ts_, tg_) < 1e-11 and rel(es_, eg_) < 1e-9 and rel(vs_, vg_) < 1e-9
 
 
 # ---- properties at the BASELINE size (2**20 members) --------------------------------------------------------------------
