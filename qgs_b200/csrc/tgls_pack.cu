@@ -112,6 +112,11 @@ const PackTables &pack_tables(const qgsb_tensor *t, bool spec)
                     o.c = rank == 5 ? (unsigned short)(8 * (en.lm & 0xffffu)) : 0;
                     o.d = rank == 5 ? (unsigned short)(8 * (en.lm >> 16)) : 0;
                 }
+            // rank 3 leaves two index fields free: entry 0 of a row carries the row's true length, so that a thread
+            // stops at the end of ITS row instead of walking the padding up to the longest one (MAOOAM-36: 351 entries
+            // in 36 rows of up to 15)
+            if (rank == 3)
+                for (int r = 1; r <= n; ++r) h[r - 1].d = (unsigned short)(t->h_row_ptr[r + 1] - t->h_row_ptr[r]);
             pc->f.alloc(h.size());
             QGSB_CUDA(cudaMemcpy(pc->f.p, h.data(), h.size() * sizeof(PEnt), cudaMemcpyHostToDevice));
             pc->tab.f_ent = pc->f.p;

@@ -188,8 +188,12 @@ __device__ __forceinline__ double f_row_tab(const TensorView &T, const ShTab &ta
             acc += at(xs, en.a) * at(xs, en.b) * at(xs, en.c) * at(xs, en.d) * en.v;
         }
     } else {
+        // the row's own length (spare field of its entry 0): the lanes of a warp hold different rows, and the loads
+        // of a lane that is done are not issued -- shared-memory traffic follows the 351 real entries of MAOOAM-36
+        // instead of 36 rows x 15
+        const int len = e[0].d;
 #pragma unroll 5
-        for (int q = 0; q < tab.EF; ++q) {
+        for (int q = 0; q < len; ++q) {
             const PEnt en = e[q * N];
             acc += at(xs, en.a) * at(xs, en.b) * en.v;
         }

@@ -93,7 +93,8 @@ __device__ __forceinline__ double jac_pos_rt(const JacView &J, int rank, int p, 
 struct __align__(16) PEnt {
     double v;
     unsigned short a, b, c, d;   // BYTE offsets (8 * index) of the factors in the augmented state (0 = the constant 1);
-                                 // Jacobian tables: d of entry 0 = byte offset of the position's slot
+                                 // Jacobian tables: d of entry 0 = byte offset of the position's slot;
+                                 // tendency tables of rank 3: d of entry 0 = number of entries of the row
 };
 
 struct PackTables {
