@@ -88,6 +88,32 @@ def test_cholesky_qr_steps_reproduce_the_householder_run(name, n_vec, vectors):
         assert np.abs(np.einsum("nij,nik->njk", q, q) - np.eye(n_vec)).max() < 1e-13
 
 
+@pytest.mark.parametrize("mode,adjoint", [(1, False), (0, True), (1, True)])
+def test_cholesky_qr_steps_in_the_forward_vector_and_adjoint_modes(mode, adjoint):
+    """The same equivalence for the other drivers of the Benettin kernel: the forward-Lyapunov-vector pass (mode 1: stored
+    trajectory, time walked backwards, lyapunov.py:471-550) and the adjoint tangent model."""
+    import oracle
+    from qgs_b200.toolbox.lyapunov import benettin
+    f, Df, T = model("maooam36")
+    n = f.ndim
+    N = 11
+    b, c, a = oracle.rk4_tableau()
+    rng = np.random.default_rng(13)
+    ic = rng.random((N, n)) * 0.01
+    q0 = np.stack([np.linalg.qr(rng.random((n, n)))[0] for _ in range(N)])
+    pre = np.concatenate((np.arange(0., 0.5, 0.1), [0.5]))
+    tim = np.concatenate((np.arange(0.5, 4.5, 0.1), [4.5]))
+    if mode == 1:
+        pre, tim = tim[::-1].copy(), pre[::-1].copy()
+    out = {}
+    for chol in ("0", "1"):
+        with env(QGSB_QR_CHOL=chol):
+            out[chol] = benettin(f, Df, ic, mode, n, q0, None, pre, tim, 0.1, 3, adjoint, 1., b, c, a)
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert np.abs(out["0"][1] - out["1"][1]).max() < 1e-11
+    assert np.abs(out["0"][2] - out["1"][2]).max() < 1e-11
+
+
 def test_cholesky_qr_falls_back_to_householder_on_an_ill_conditioned_step():
     """Orthogonality of a Cholesky QR degrades with cond(A)^2, and the Gram matrix of a rank-deficient basis has no
     Cholesky factor at all.  A start basis whose second column repeats the first, and whose fourth is the third up to
