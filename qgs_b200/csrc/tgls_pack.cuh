@@ -665,14 +665,14 @@ __device__ __forceinline__ void qr_rolled(const Mem<N> &S, int c, bool live, dou
 // factorisation is done as  G = A^T A  (a small GEMM per member: mma.sync.m8n8k4.f64, one warp per member, the
 // fragments straight from the row-major A the tangent step left in shared memory),  G = R^T R  (right-looking
 // Cholesky, lane = column in registers, one warp-level hand-over per pivot instead of a block barrier per reflector),
-// Q = A R^-1  (forward substitution, thread = row).  The chain of dependent instructions per column is
-// shuffle + rsqrt + multiply + FMA instead of Householder's reduction + sqrt + two reciprocals + update, and the O(n^3)
-// part runs on the tensor pipe with 1/8 of the instructions.  Orthogonality of Cholesky QR degrades with cond(A)^2:
-// A is an orthonormal basis propagated over ONE step, cond(A) ~ exp((l_1 - l_n) dt) = O(1); a pivot below
-// CHOL_PIVOT_MIN of the largest squared column norm (cond^2 > 1 / CHOL_PIVOT_MIN, or a rank-deficient basis) sends the
-// whole block through the Householder code for that step.  Steps whose Q or R is recorded or returned (vector
-// records, the Ginelli pass, the start and the final basis) always take Householder, so recorded vectors keep
-// np.linalg.qr's signs.
+// Q = A R^-1  (forward substitution, two rows per thread).  The chain of dependent instructions per column is
+// shuffle + rsqrt + multiply + FMA instead of Householder's reduction + sqrt + two reciprocals + update, and the Gram
+// matrix -- half of the O(n^3) work -- runs on the tensor pipe with 1/8 of the instructions.  Orthogonality of Cholesky
+// QR degrades with cond(A)^2: A is an orthonormal basis propagated over ONE step, cond(A) ~ exp((l_1 - l_n) dt) = O(1);
+// a pivot below CHOL_PIVOT_MIN of the largest squared column norm (cond^2 > 1 / CHOL_PIVOT_MIN, or a rank-deficient
+// basis) sends THAT MEMBER through the Householder code for the step (the others keep their result: a member's numbers
+// must not depend on who shares its block).  Steps whose Q or R is recorded or returned (vector records, the Ginelli
+// pass, the start and the final basis) always take Householder, so recorded vectors keep np.linalg.qr's signs.
 constexpr double CHOL_PIVOT_MIN = 1e-4;
 #ifdef CHOL_PROF
 __device__ long long chol_prof[4];
