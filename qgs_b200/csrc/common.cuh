@@ -88,6 +88,10 @@ struct Context {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long launches = 0;
     std::vector<PoolBlock> pool;                          // grow-only scratch pool of this device
+    // Pinned, device-mapped staging area for calls on a handful of states (f(t, x), Df(t, x) on one state): the kernel
+    // reads its input from it and writes its result into it over the bus -- no cudaMemcpy in either direction.
+    double *h_stage = nullptr;
+    static constexpr size_t STAGE_IN = 4096, STAGE_OUT = 12288;   // doubles
 };
 Context &ctx();
 void ensure_init();

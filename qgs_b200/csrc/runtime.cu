@@ -61,6 +61,11 @@ static void context_open(Context &c, int slot, int device)
     QGSB_CUDA(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking));
     QGSB_CUDA(cudaEventCreate(&c.ev0));
     QGSB_CUDA(cudaEventCreate(&c.ev1));
+    if (cudaHostAlloc((void **)&c.h_stage, (Context::STAGE_IN + Context::STAGE_OUT) * sizeof(double),
+                      cudaHostAllocMapped) != cudaSuccess) {
+        c.h_stage = nullptr;            // the single-state calls then take the ordinary copies
+        cudaGetLastError();
+    }
     c.ready = true;
 }
 
@@ -77,6 +82,8 @@ static void context_close(Context &c)
     cudaStreamDestroy(c.copy_out);
     cudaEventDestroy(c.ev0);
     cudaEventDestroy(c.ev1);
+    if (c.h_stage) cudaFreeHost(c.h_stage);
+    c.h_stage = nullptr;
     c.own_stream = c.stream = c.copy_in = c.copy_out = nullptr;
     c.ev0 = c.ev1 = nullptr;
     c.ready = false;
@@ -1068,6 +1075,24 @@ int qgsb_tendencies(const qgsb_tensor *t, long N, const double *x, double *out)
     ensure_init();
     cudaStream_t s = ctx().stream;
     const int n = t->view.n;
+    if (ctx().h_stage && (size_t)N * n <= Context::STAGE_IN) {
+        // a handful of states (the reference's f(t, x) on one state, tendencies.py:98-112): through the mapped
+        // staging area, one launch and one synchronisation, no copies
+        double *hx = ctx().h_stage, *ho = hx + Context::STAGE_IN;
+        const long total = N * n;
+        memcpy(hx, x, sizeof(double) * total);
+        const int threads = 128;
+        const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+        if (t->view.rank == 5)
+            mulvec_kernel<5><<<blocks, threads, 0, s>>>(t->view, N, n + 1, hx, hx, hx, hx, n, 1, ho, 1, n);
+        else
+            mulvec_kernel<3><<<blocks, threads, 0, s>>>(t->view, N, n + 1, hx, hx, hx, hx, n, 1, ho, 1, n);
+        count_launch();
+        QGSB_CUDA(cudaGetLastError());
+        QGSB_CUDA(cudaStreamSynchronize(s));
+        memcpy(out, ho, sizeof(double) * total);
+        return 0;
+    }
     PoolBuf<double> d_x((size_t)N * n), d_out((size_t)N * n);
     d_x.upload(x, (size_t)N * n, s);
     if (t->spec && t->use_spec && t->spec->tendencies && N >= 512) {
@@ -1105,10 +1130,29 @@ int qgsb_jacobian(const qgsb_tensor *t, long N, const double *x, double *out)
     ensure_init();
     cudaStream_t s = ctx().stream;
     const int n = t->view.n;
-    DevBuf<double> d_x((size_t)N * n), d_out((size_t)N * n * n);
+    const long total = N * t->view.jac.npos;
+    if (ctx().h_stage && (size_t)N * n <= Context::STAGE_IN && (size_t)N * n * n <= Context::STAGE_OUT) {
+        // one state or a few (Df(t, x), tendencies.py:114-121): through the mapped staging area, see qgsb_tendencies
+        double *hx = ctx().h_stage, *ho = hx + Context::STAGE_IN;
+        memcpy(hx, x, sizeof(double) * N * n);
+        memset(ho, 0, sizeof(double) * N * n * n);
+        if (total > 0) {
+            const int threads = 128;
+            const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+            if (t->view.rank == 5)
+                mulmat_kernel<5><<<blocks, threads, 0, s>>>(t->view.jac, N, hx, hx, hx, n, 1, ho, 1, n);
+            else
+                mulmat_kernel<3><<<blocks, threads, 0, s>>>(t->view.jac, N, hx, hx, hx, n, 1, ho, 1, n);
+            count_launch();
+            QGSB_CUDA(cudaGetLastError());
+            QGSB_CUDA(cudaStreamSynchronize(s));
+        }
+        memcpy(out, ho, sizeof(double) * N * n * n);
+        return 0;
+    }
+    PoolBuf<double> d_x((size_t)N * n), d_out((size_t)N * n * n);
     d_x.upload(x, (size_t)N * n, s);
     QGSB_CUDA(cudaMemsetAsync(d_out.p, 0, sizeof(double) * N * n * n, s));
-    const long total = N * t->view.jac.npos;
     if (total > 0) {
         const int threads = 128;
         const unsigned blocks = (unsigned)((total + threads - 1) / threads);
